@@ -1,0 +1,184 @@
+/* include/posebyte_b200.h — C ABI of the B200-native PoseBYTE post-inference path.
+ *
+ * This is the drop-in boundary.  The reference (naveedprojects/yolo-pose-cpp) has no
+ * FFI layer: its boundary is a set of C++ classes over raw device pointers
+ * (include/cuda/gpu_postprocess.h:11-72, gpu_tracker.h:61-110, nms.h:11-60,
+ * kalman_filter.h:14-138, hungarian.h:11-160).  Every entry point below names the
+ * reference interface it replaces; include/cuda/ *.h re-creates those classes as
+ * header-only shims on top of this ABI, so main.cpp:207-224 compiles unchanged.
+ *
+ * Conventions: plain pointers and sizes only; device pointers are prefixed d_, host
+ * pointers h_; every function returns PB_OK (0) or a negative pb_status and never calls
+ * exit() (the reference prints-and-continues or exits, gpu_tracker.cu:9-16,
+ * hungarian.cu:11-19); pb_last_error() returns the text of the last failure on the
+ * calling thread.  A handle owns B independent streams (one tracker state each) that
+ * are processed by one launch; nothing is shared between streams.  All work is enqueued
+ * on the caller's CUDA stream; functions with "_sync" or host outputs synchronise it.
+ */
+#ifndef POSEBYTE_B200_H
+#define POSEBYTE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pb_stream_t;        /* == cudaStream_t */
+typedef struct pb_handle_st* pb_handle_t;
+
+typedef enum pb_status {
+    PB_OK = 0,
+    PB_ERR_INVALID = -1,     /* bad argument / configuration */
+    PB_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    PB_ERR_UNSUPPORTED = -3, /* configuration exceeds a compiled-in limit */
+    PB_ERR_NO_DEVICE = -4    /* no sm_100 device: there is no CPU fallback */
+} pb_status;
+
+/* GPUTrackerConfig (gpu_tracker.h:16-26) + GPUPostprocess ctor args
+ * (gpu_postprocess.h:13) + batching.  Zero-initialise, call pb_default_config, then edit. */
+typedef struct pb_config {
+    int num_streams;         /* B: independent video streams in this handle (new capability) */
+    int num_anchors;         /* N: 8400 @640, 33600 @1280 (GPUPostprocess num_anchors) */
+    int max_candidates;      /* GPUPostprocess max_detections, 1024 */
+    int max_keep;            /* hard-coded 256 upstream (gpu_postprocess.cu:224) */
+    int max_tracks;          /* 128 */
+    int max_detections;      /* 64: tracker input is truncated to this (gpu_tracker.cu:1066) */
+    float match_threshold;   /* 0.5 - kept for API parity, inert upstream (hungarian.cu:358-405) */
+    float high_thresh;       /* 0.30 - inert upstream (outputs never read, gpu_tracker.cu:595) */
+    float low_thresh;        /* 0.15 - inert upstream */
+    float new_track_thresh;  /* 0.30 */
+    int max_age;             /* 10 */
+    int min_hits;            /* 3 */
+    int use_cuda_graph;      /* kept for API parity, unused upstream (gpu_tracker.cu:1660) */
+    int gating_enabled;      /* extension: 0 replaces the spatial gate by all-ones (config 5) */
+    int device;              /* CUDA device ordinal */
+} pb_config;
+
+/* TrackerTiming (gpu_tracker.h:29-41), filled from device timestamps. */
+typedef struct pb_timing {
+    long long predict_us, gate_us, high_assoc_us, low_assoc_us, lost_assoc_us;
+    long long update_us, age_us, new_track_us, dedup_us, total_us;
+    int frame_count;
+} pb_timing;
+
+const char* pb_last_error(void);
+const char* pb_version(void);
+void pb_default_config(pb_config* cfg);
+
+/* GPUPostprocess::GPUPostprocess + GPUTracker::GPUTracker (gpu_postprocess.cu:319-347,
+ * gpu_tracker.cu:925-1010).  Fails with PB_ERR_NO_DEVICE when no GPU is present. */
+int pb_create(const pb_config* cfg, pb_handle_t* out);
+int pb_destroy(pb_handle_t h);
+/* Back to the freshly constructed state (all tracks dropped, ids restart at 1). */
+int pb_reset(pb_handle_t h, pb_stream_t stream);
+
+/* ---- the path ------------------------------------------------------------------ */
+
+/* GPUPostprocess::process for B streams (gpu_postprocess.cu:366-476): decode + confidence
+ * filter + OKS/IoU NMS.  d_heads = [B,56,N] fp32, borrowed.  Asynchronous. */
+int pb_postprocess(pb_handle_t h, const float* d_heads, float conf_threshold,
+                   float nms_threshold, pb_stream_t stream);
+
+/* GPUTracker::update for B streams (gpu_tracker.cu:1057-1158).
+ * d_det_poses [B, det_stride, 17, 3], d_det_scores [B, det_stride], d_num_dets [B]
+ * (device).  Passing NULL pointers uses the handle's own postprocess outputs (the chain
+ * main.cpp:207-221 builds).  Asynchronous. */
+int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_det_scores,
+                      const int* d_num_dets, int det_stride, int frame_id, pb_stream_t stream);
+
+/* detectGPUNative's tail + tracker.update + getActiveTracks assembly for B streams in one
+ * call (main.cpp:207-224).  Asynchronous; results stay on the device. */
+int pb_step(pb_handle_t h, const float* d_heads, float conf_threshold, float nms_threshold,
+            int frame_id, pb_stream_t stream);
+
+/* Same with HOST buffers: h_heads [B,56,N] (pinned or pageable) is staged to the device,
+ * the step runs, and the TrackOutput records are returned in h_tracks
+ * [B, max_detections] (228-byte records) with h_counts [B].  Synchronous. */
+int pb_step_host(pb_handle_t h, const float* h_heads, float conf_threshold,
+                 float nms_threshold, int frame_id, void* h_tracks, int* h_counts);
+
+/* ---- results --------------------------------------------------------------------- */
+
+/* GPUTracker::getActiveTracks (gpu_tracker.cu:1559-1639) for one stream; synchronises.
+ * out = TrackOutput[cap]. */
+int pb_get_tracks(pb_handle_t h, int stream_idx, void* out, int cap, int* n_out);
+/* All streams at once: out [B, max_detections] records, counts [B]. */
+int pb_get_tracks_all(pb_handle_t h, void* out, int* counts);
+/* update()'s return value per stream (active slots incl. lost/tentative). */
+int pb_get_num_active(pb_handle_t h, int* h_num_active /*[B]*/);
+
+/* Post-NMS detections of one stream (getDetectionPoses/Bboxes/Scores + d_keep_indices_):
+ * any pointer may be NULL.  poses [Kp,51], bboxes [Kp,4], scores [Kp], keep_slots [Kp]
+ * (candidate slots, = d_keep_indices_), keep_anchors [Kp].  Synchronises. */
+int pb_get_kept(pb_handle_t h, int stream_idx, float* poses, float* bboxes, float* scores,
+                int* keep_slots, int* keep_anchors, int cap, int* num_keep, int* num_cand);
+
+/* Raw tracker state of one stream (the "Kalman states" parity target); pointers may be
+ * NULL.  Sizes as in oracle/posebyte_oracle.h:orc_tracker_get_state.  Synchronises. */
+int pb_get_state(pb_handle_t h, int stream_idx, float* poses, float* vel, float* scores,
+                 int* states, int* ids, int* hits, int* ages, int* last_frame, int* active,
+                 int* row_assign, int* col_assign, float* cost, float* predicted,
+                 float* centers, int* scalars);
+
+/* Device pointers for chaining (getDetectionPoses / getTrackPosesDevice ...). */
+typedef struct pb_device_views {
+    float* det_poses;   /* [B, max_keep, 51] */
+    float* det_bboxes;  /* [B, max_keep, 4]  */
+    float* det_scores;  /* [B, max_keep]     */
+    int* num_keep;      /* [B] */
+    int* num_cand;      /* [B] */
+    int* keep_slots;    /* [B, max_keep] */
+    int* keep_anchors;  /* [B, max_keep] */
+    float* track_poses; /* [B, T, 51] */
+    float* track_scores;/* [B, T] */
+    int* track_states;  /* [B, T] */
+    int* track_ids;     /* [B, T] */
+    void* track_outputs;/* [B, max_detections] TrackOutput */
+    int* num_outputs;   /* [B] */
+    int* num_active;    /* [B] */
+} pb_device_views;
+int pb_get_device_views(pb_handle_t h, pb_device_views* out);
+int pb_get_timing(pb_handle_t h, pb_timing* out);
+/* Number of kernels this library has launched since process start (bench bookkeeping). */
+long long pb_launch_count(void);
+
+/* ---- stage-level entry points ------------------------------------------------------ */
+
+/* nms.h:48-60 declares this symbol and never defines it.  Device pointers; keep[i] in
+ * {0,1}.  Rule: pairwise OKS as nms.cu:25-117, stable score order, suppress at
+ * OKS > oks_threshold. */
+void launchPoseNMS(const float* poses, const float* scores, const float* sigmas, int* keep,
+                   int num_detections, int num_keypoints, float oks_threshold,
+                   float score_threshold, pb_stream_t stream);
+
+/* NMSCuda::apply / applyBatch rule set (nms.cu:142-330) on the device.
+ * d_dets = PoseDetection[total] (224 B), d_offsets [num_images+1]; d_keep [total]
+ * receives original indices (image-local) in score order, d_num_keep [num_images]. */
+int pb_nms_legacy(const void* d_dets, const int* d_offsets, int num_images, int max_per_image,
+                  float oks_threshold, float score_threshold, int* d_keep, int* d_num_keep,
+                  pb_stream_t stream);
+
+/* LinearAssignmentCUDA::solveDeviceAsyncWithActive (hungarian.cu:358-405) for `batch`
+ * independent problems: d_cost [batch, rows, cols], d_row_active [batch, rows] or NULL. */
+int pb_auction_solve(const float* d_cost, int batch, int num_rows, int num_cols,
+                     int* d_row_assign, int* d_col_assign, const int* d_row_active,
+                     pb_stream_t stream);
+
+/* KalmanFilterCUDA (kalman_filter.cu).  State: d_means [T,136], d_diag [T,136] (the
+ * covariance diagonal; off-diagonal entries are identically zero upstream). */
+int pb_kf3_initiate(float* d_means, float* d_diag, const float* d_dets, const int* d_slots,
+                    int num_new, pb_stream_t stream);
+int pb_kf3_predict(float* d_means, float* d_diag, int num_tracks, float accel_memory,
+                   float jerk_memory, pb_stream_t stream);
+int pb_kf3_update(float* d_means, float* d_diag, const float* d_dets, const int* d_matches,
+                  int num_matches, pb_stream_t stream);
+int pb_kf3_extract(const float* d_means, float* d_out_poses, const int* d_slots, int num_tracks,
+                   pb_stream_t stream);
+/* getState's full 136x136 matrix from the diagonal. */
+int pb_kf3_materialize_cov(const float* d_diag, int track, float* d_cov136x136, pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

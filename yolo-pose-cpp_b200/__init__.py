@@ -1,0 +1,325 @@
+"""posebyte-b200: B200-native PoseBYTE post-inference path (decode -> pose-NMS -> tracker).
+
+Python is the harness only: this module is a ctypes binding of the C ABI declared in
+``include/posebyte_b200.h`` (the product is ``lib/libposebyte_b200.so``, hand-written
+CUDA for sm_100a behind a C++17 host layer).  It mirrors the reference's call sequence
+(``GPUPostprocess::process`` -> ``GPUTracker::update`` -> ``getActiveTracks``,
+reference src/main.cpp:207-224) for B independent streams per call.
+
+There is no CPU fallback: creating a :class:`Pipeline` without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libposebyte_b200.so")
+SYNTH_PATH = os.path.join(LIB_DIR, "libpb_synth.so")
+
+PB_OK, PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_UNSUPPORTED, PB_ERR_NO_DEVICE = 0, -1, -2, -3, -4
+
+# TrackOutput (include/types.h): 228-byte record.
+TRACK_OUTPUT = np.dtype([("track_id", "<i4"), ("score", "<f4"), ("bbox", "<f4", (4,)),
+                         ("keypoints", "<f4", (17, 3))])
+assert TRACK_OUTPUT.itemsize == 228
+# PoseDetection (include/types.h): 224-byte record.
+POSE_DETECTION = np.dtype([("bbox", "<f4", (4,)), ("score", "<f4"), ("keypoints", "<f4", (17, 3))])
+assert POSE_DETECTION.itemsize == 224
+
+
+class PbError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"posebyte_b200 status {status}: {msg}")
+        self.status = status
+
+
+class PbConfig(C.Structure):
+    _fields_ = [("num_streams", C.c_int), ("num_anchors", C.c_int), ("max_candidates", C.c_int),
+                ("max_keep", C.c_int), ("max_tracks", C.c_int), ("max_detections", C.c_int),
+                ("match_threshold", C.c_float), ("high_thresh", C.c_float), ("low_thresh", C.c_float),
+                ("new_track_thresh", C.c_float), ("max_age", C.c_int), ("min_hits", C.c_int),
+                ("use_cuda_graph", C.c_int), ("gating_enabled", C.c_int), ("device", C.c_int)]
+
+
+class PbTiming(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in ("predict_us", "gate_us", "high_assoc_us", "low_assoc_us",
+                                            "lost_assoc_us", "update_us", "age_us", "new_track_us",
+                                            "dedup_us", "total_us")] + [("frame_count", C.c_int)]
+
+
+class PbDeviceViews(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("det_poses", "det_bboxes", "det_scores", "num_keep", "num_cand",
+                                          "keep_slots", "keep_anchors", "track_poses", "track_scores",
+                                          "track_states", "track_ids", "track_outputs", "num_outputs",
+                                          "num_active")]
+
+
+class SynthConfig(C.Structure):
+    _fields_ = [("num_anchors", C.c_int), ("canvas", C.c_int), ("persons", C.c_int), ("period", C.c_int),
+                ("clumps", C.c_int), ("occlusion", C.c_int), ("kp_drop_prob", C.c_float),
+                ("max_speed", C.c_float), ("seed", C.c_ulonglong)]
+
+
+# Every symbol include/posebyte_b200.h declares (tests check the library exports them all).
+ABI_SYMBOLS = [
+    "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
+    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_step_host", "pb_get_tracks",
+    "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
+    "pb_get_timing", "pb_launch_count", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
+    "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
+]
+
+_lib = None
+_synth = None
+
+
+def lib() -> C.CDLL:
+    """The product library.  Raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.pb_last_error.restype = C.c_char_p
+        L.pb_version.restype = C.c_char_p
+        L.pb_launch_count.restype = C.c_longlong
+        L.launchPoseNMS.restype = None
+        vp, ip, fp = C.c_void_p, C.c_int, C.c_float
+        L.pb_default_config.argtypes = [C.POINTER(PbConfig)]
+        L.pb_create.argtypes = [C.POINTER(PbConfig), C.POINTER(vp)]
+        L.pb_destroy.argtypes = [vp]
+        L.pb_reset.argtypes = [vp, vp]
+        L.pb_postprocess.argtypes = [vp, vp, fp, fp, vp]
+        L.pb_tracker_update.argtypes = [vp, vp, vp, vp, ip, ip, vp]
+        L.pb_step.argtypes = [vp, vp, fp, fp, ip, vp]
+        L.pb_step_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
+        L.pb_get_tracks.argtypes = [vp, ip, vp, ip, C.POINTER(ip)]
+        L.pb_get_tracks_all.argtypes = [vp, vp, vp]
+        L.pb_get_num_active.argtypes = [vp, vp]
+        L.pb_get_kept.argtypes = [vp, ip, vp, vp, vp, vp, vp, ip, C.POINTER(ip), C.POINTER(ip)]
+        L.pb_get_state.argtypes = [vp, ip] + [vp] * 15
+        L.pb_get_device_views.argtypes = [vp, C.POINTER(PbDeviceViews)]
+        L.pb_get_timing.argtypes = [vp, C.POINTER(PbTiming)]
+        L.launchPoseNMS.argtypes = [vp, vp, vp, vp, ip, ip, fp, fp, vp]
+        L.pb_nms_legacy.argtypes = [vp, vp, ip, ip, fp, fp, vp, vp, vp]
+        L.pb_auction_solve.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp]
+        L.pb_kf3_initiate.argtypes = [vp, vp, vp, vp, ip, vp]
+        L.pb_kf3_predict.argtypes = [vp, vp, ip, fp, fp, vp]
+        L.pb_kf3_update.argtypes = [vp, vp, vp, vp, ip, vp]
+        L.pb_kf3_extract.argtypes = [vp, vp, vp, ip, vp]
+        L.pb_kf3_materialize_cov.argtypes = [vp, ip, vp, vp]
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != PB_OK:
+        raise PbError(status, lib().pb_last_error().decode())
+
+
+def default_config(**kw) -> PbConfig:
+    cfg = PbConfig()
+    lib().pb_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(x):
+    """Device/host address of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()          # torch.Tensor
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+class Pipeline:
+    """B streams of decode + NMS + PoseBYTE tracking on one GPU (one handle)."""
+
+    def __init__(self, **cfg_kw):
+        self.cfg = default_config(**cfg_kw)
+        self._h = C.c_void_p()
+        check(lib().pb_create(C.byref(self.cfg), C.byref(self._h)))
+        self.B = self.cfg.num_streams
+        self.T = self.cfg.max_tracks
+        self.Dm = self.cfg.max_detections
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().pb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None):
+        check(lib().pb_reset(self._h, _stream_ptr(stream)))
+
+    # -- the path ---------------------------------------------------------------------
+    def postprocess(self, heads, conf=0.30, nms=0.65, stream=None):
+        check(lib().pb_postprocess(self._h, _ptr(heads), conf, nms, _stream_ptr(stream)))
+
+    def tracker_update(self, frame_id, det_poses=None, det_scores=None, num_dets=None, det_stride=0, stream=None):
+        check(lib().pb_tracker_update(self._h, _ptr(det_poses), _ptr(det_scores), _ptr(num_dets), det_stride,
+                                      frame_id, _stream_ptr(stream)))
+
+    def step(self, heads, frame_id, conf=0.30, nms=0.65, stream=None):
+        check(lib().pb_step(self._h, _ptr(heads), conf, nms, frame_id, _stream_ptr(stream)))
+
+    def step_host(self, heads_np: np.ndarray, frame_id, conf=0.30, nms=0.65):
+        out = np.zeros((self.B, self.Dm), dtype=TRACK_OUTPUT)
+        counts = np.zeros(self.B, dtype=np.int32)
+        check(lib().pb_step_host(self._h, heads_np.ctypes.data, conf, nms, frame_id, out.ctypes.data, counts.ctypes.data))
+        return out, counts
+
+    # -- results ----------------------------------------------------------------------
+    def get_tracks(self, b: int) -> np.ndarray:
+        out = np.zeros(self.Dm, dtype=TRACK_OUTPUT)
+        n = C.c_int(0)
+        check(lib().pb_get_tracks(self._h, b, out.ctypes.data, self.Dm, C.byref(n)))
+        return out[: n.value]
+
+    def get_tracks_all(self):
+        out = np.zeros((self.B, self.Dm), dtype=TRACK_OUTPUT)
+        counts = np.zeros(self.B, dtype=np.int32)
+        check(lib().pb_get_tracks_all(self._h, out.ctypes.data, counts.ctypes.data))
+        return out, counts
+
+    def get_num_active(self) -> np.ndarray:
+        out = np.zeros(self.B, dtype=np.int32)
+        check(lib().pb_get_num_active(self._h, out.ctypes.data))
+        return out
+
+    def get_kept(self, b: int) -> dict:
+        K = self.cfg.max_keep
+        poses = np.zeros((K, 51), np.float32); bboxes = np.zeros((K, 4), np.float32)
+        scores = np.zeros(K, np.float32); slots = np.zeros(K, np.int32); anchors = np.zeros(K, np.int32)
+        nk, nc = C.c_int(0), C.c_int(0)
+        check(lib().pb_get_kept(self._h, b, poses.ctypes.data, bboxes.ctypes.data, scores.ctypes.data,
+                                slots.ctypes.data, anchors.ctypes.data, K, C.byref(nk), C.byref(nc)))
+        n = nk.value
+        return dict(poses=poses[:n], bboxes=bboxes[:n], scores=scores[:n], keep_slots=slots[:n],
+                    keep_anchors=anchors[:n], num_keep=n, num_cand=nc.value)
+
+    def get_state(self, b: int) -> dict:
+        T, Dm = self.T, self.Dm
+        st = dict(poses=np.zeros((T, 51), np.float32), vel=np.zeros((T, 34), np.float32),
+                  scores=np.zeros(T, np.float32), states=np.zeros(T, np.int32), ids=np.zeros(T, np.int32),
+                  hits=np.zeros(T, np.int32), ages=np.zeros(T, np.int32), last_frame=np.zeros(T, np.int32),
+                  active=np.zeros(T, np.int32), row_assign=np.zeros(T, np.int32),
+                  col_assign=np.zeros(Dm, np.int32), cost=np.zeros(T * Dm, np.float32),
+                  predicted=np.zeros((T, 51), np.float32), centers=np.zeros((T, 4), np.float32),
+                  scalars=np.zeros(4, np.int32))
+        order = ["poses", "vel", "scores", "states", "ids", "hits", "ages", "last_frame", "active",
+                 "row_assign", "col_assign", "cost", "predicted", "centers", "scalars"]
+        check(lib().pb_get_state(self._h, b, *[st[k].ctypes.data for k in order]))
+        return st
+
+    def device_views(self) -> PbDeviceViews:
+        v = PbDeviceViews()
+        check(lib().pb_get_device_views(self._h, C.byref(v)))
+        return v
+
+    def timing(self) -> PbTiming:
+        t = PbTiming()
+        check(lib().pb_get_timing(self._h, C.byref(t)))
+        return t
+
+
+def launch_count() -> int:
+    return int(lib().pb_launch_count())
+
+
+# ---- synthetic input (host generator, lib/libpb_synth.so) -------------------------------
+def synth_lib() -> C.CDLL:
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_PATH):
+            raise FileNotFoundError(f"{SYNTH_PATH} missing: run __graft_entry__.build()")
+        S = C.CDLL(SYNTH_PATH)
+        S.pb_synth_head.argtypes = [C.POINTER(SynthConfig), C.c_int, C.c_int, C.c_void_p]
+        S.pb_synth_heads.argtypes = [C.POINTER(SynthConfig), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int]
+        S.pb_synth_dets.argtypes = [C.POINTER(SynthConfig), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        S.pb_synth_dets.restype = C.c_int
+        _synth = S
+    return _synth
+
+
+def num_anchors_for(canvas: int) -> int:
+    return (canvas // 8) ** 2 + (canvas // 16) ** 2 + (canvas // 32) ** 2
+
+
+def synth_config(canvas=640, persons=20, period=300, clumps=0, occlusion=0, kp_drop_prob=0.05,
+                 max_speed=3.0, seed=0x5EEDB200) -> SynthConfig:
+    return SynthConfig(num_anchors_for(canvas), canvas, persons, period, clumps, occlusion, kp_drop_prob,
+                       max_speed, seed)
+
+
+def synth_heads(cfg: SynthConfig, stream0: int, nstreams: int, frame0: int, nframes: int,
+                frame_major: bool = True, threads: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """[F,B,56,N] (frame_major) or [B,F,56,N] fp32 heads."""
+    shape = (nframes, nstreams, 56, cfg.num_anchors) if frame_major else (nstreams, nframes, 56, cfg.num_anchors)
+    if out is None:
+        out = np.empty(shape, dtype=np.float32)
+    assert out.shape == shape and out.dtype == np.float32 and out.flags.c_contiguous
+    threads = threads or min(os.cpu_count() or 1, 32)
+    synth_lib().pb_synth_heads(C.byref(cfg), stream0, nstreams, frame0, nframes, int(frame_major),
+                               out.ctypes.data, threads)
+    return out
+
+
+def synth_dets(cfg: SynthConfig, stream: int, frame: int):
+    poses = np.zeros((cfg.persons, 51), np.float32)
+    scores = np.zeros(cfg.persons, np.float32)
+    n = synth_lib().pb_synth_dets(C.byref(cfg), stream, frame, poses.ctypes.data, scores.ctypes.data)
+    return poses[:n], scores[:n]
+
+
+# ---- sharding of streams over ranks (no collective on the hot path) -----------------------
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    total_streams: int
+
+    @property
+    def count(self) -> int:
+        base, rem = divmod(self.total_streams, self.world)
+        return base + (1 if self.rank < rem else 0)
+
+    @property
+    def start(self) -> int:
+        base, rem = divmod(self.total_streams, self.world)
+        return self.rank * base + min(self.rank, rem)
+
+    def streams(self) -> range:
+        return range(self.start, self.start + self.count)
+
+
+def words_checksum(words_u32: np.ndarray, pos0: int = 0) -> int:
+    """Position-weighted 64-bit checksum of 32-bit words: the same function the CPU checker
+    applies to its outputs (order sensitive, wraps mod 2^64)."""
+    w = np.ascontiguousarray(words_u32).view(np.uint32).astype(np.uint64).ravel()
+    idx = np.arange(pos0, pos0 + w.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        mult = (idx * np.uint64(2) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        return int(((w + np.uint64(0x9E37)) * mult).sum(dtype=np.uint64))

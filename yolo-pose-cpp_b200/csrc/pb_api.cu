@@ -1,0 +1,344 @@
+// pb_api.cu — handle management and the C ABI of include/posebyte_b200.h (host C++17).
+//
+// A handle owns the device buffers of B independent streams (the reference allocates the
+// same buffers per GPUPostprocess / GPUTracker object: gpu_postprocess.cu:319-347,
+// gpu_tracker.cu:925-1010) as struct-of-arrays slabs, plus a pinned staging ring for the
+// host-buffer entry point.  There is no CPU fallback: pb_create fails without a device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "pb_common.cuh"
+
+namespace pb {
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace pb
+
+static thread_local char g_err[512] = "";
+void pb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+using namespace pb;
+
+struct pb_handle_st {
+    pb_config cfg;
+    PostBuffers post{};
+    TrackBuffers trk{};
+    TrackerPlan plan{};
+    std::vector<void*> allocs;
+    // host-buffer path
+    float* d_stage = nullptr;      // [B,56,N] device staging
+    void* h_out_pinned = nullptr;  // [B,Dm] TrackOutput
+    int* h_cnt_pinned = nullptr;   // [B]
+    cudaStream_t own_stream = nullptr;
+    int frames = 0;
+};
+
+#define PB_CUDA(call)                                                                         \
+    do { cudaError_t e_ = (call);                                                             \
+         if (e_ != cudaSuccess) { pb_set_error("%s failed: %s", #call, cudaGetErrorString(e_)); return PB_ERR_CUDA; } } while (0)
+
+template <typename T>
+static int dev_alloc(pb_handle_st* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) { pb_set_error("cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    e = cudaMemset(q, 0, count * sizeof(T) + 16);
+    if (e != cudaSuccess) { pb_set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return PB_OK;
+}
+#define PB_TRY(x) do { int r_ = (x); if (r_ != PB_OK) return r_; } while (0)
+
+extern "C" {
+
+const char* pb_last_error(void) { return g_err; }
+const char* pb_version(void) { return "posebyte-b200 0.1 (sm_100a)"; }
+long long pb_launch_count(void) { return g_launches.load(); }
+
+void pb_default_config(pb_config* c) {
+    if (!c) return;
+    c->num_streams = 1;
+    c->num_anchors = 8400;            // gpu_postprocess.h:13
+    c->max_candidates = 1024;         // gpu_postprocess.h:13
+    c->max_keep = 256;                // gpu_postprocess.cu:224
+    c->max_tracks = 128;              // gpu_tracker.h:17-25
+    c->max_detections = 64;
+    c->match_threshold = 0.5f;
+    c->high_thresh = 0.30f;
+    c->low_thresh = 0.15f;
+    c->new_track_thresh = 0.30f;
+    c->max_age = 10;
+    c->min_hits = 3;
+    c->use_cuda_graph = 0;
+    c->gating_enabled = 1;
+    c->device = 0;
+}
+
+static int build_handle(pb_handle_st* h) {
+    const pb_config& c = h->cfg;
+    const size_t B = c.num_streams, T = c.max_tracks, Dm = c.max_detections, K = c.max_keep;
+    PB_TRY(dev_alloc(h, &h->post.det_poses, B * K * POSE_F));
+    PB_TRY(dev_alloc(h, &h->post.det_bboxes, B * K * 4));
+    PB_TRY(dev_alloc(h, &h->post.det_scores, B * K));
+    PB_TRY(dev_alloc(h, &h->post.keep_slots, B * K));
+    PB_TRY(dev_alloc(h, &h->post.keep_anchors, B * K));
+    PB_TRY(dev_alloc(h, &h->post.num_keep, B));
+    PB_TRY(dev_alloc(h, &h->post.num_cand, B));
+    TrackBuffers& t = h->trk;
+    PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
+    PB_TRY(dev_alloc(h, &t.vel, B * T * 34));
+    PB_TRY(dev_alloc(h, &t.scores, B * T));
+    PB_TRY(dev_alloc(h, &t.predicted, B * T * POSE_F));
+    PB_TRY(dev_alloc(h, &t.tcent, B * T * 4));
+    PB_TRY(dev_alloc(h, &t.dcent, B * Dm * 4));
+    PB_TRY(dev_alloc(h, &t.cost, B * T * Dm));
+    PB_TRY(dev_alloc(h, &t.det_scores, B * Dm));
+    PB_TRY(dev_alloc(h, &t.states, B * T));
+    PB_TRY(dev_alloc(h, &t.ids, B * T));
+    PB_TRY(dev_alloc(h, &t.hits, B * T));
+    PB_TRY(dev_alloc(h, &t.ages, B * T));
+    PB_TRY(dev_alloc(h, &t.last_frame, B * T));
+    PB_TRY(dev_alloc(h, &t.active, B * T));
+    PB_TRY(dev_alloc(h, &t.pred_dirty, B * T));
+    PB_TRY(dev_alloc(h, &t.row_assign, B * T));
+    PB_TRY(dev_alloc(h, &t.col_assign, B * Dm));
+    PB_TRY(dev_alloc(h, &t.scalars, B * 4));
+    PB_TRY(dev_alloc(h, &t.num_outputs, B));
+    PB_TRY(dev_alloc(h, &t.det_poses_scratch, B * Dm * POSE_F));
+    PB_TRY(dev_alloc(h, &t.stage_ns, B * 12));
+    unsigned char* outp = nullptr;
+    PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
+    t.outputs = outp;
+    h->plan = tracker_plan(c.max_tracks, c.max_detections);
+    PB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    PB_CUDA(launch_tracker_reset(h->trk, c.num_streams, c.max_tracks, c.max_detections, h->own_stream));
+    PB_CUDA(cudaStreamSynchronize(h->own_stream));
+    return PB_OK;
+}
+
+int pb_create(const pb_config* cfg, pb_handle_t* out) {
+    if (!cfg || !out) { pb_set_error("pb_create: null argument"); return PB_ERR_INVALID; }
+    *out = nullptr;
+    const pb_config& c = *cfg;
+    if (c.num_streams < 1 || c.num_anchors < 1 || c.max_candidates < 1 || c.max_keep < 1 ||
+        c.max_tracks < 1 || c.max_detections < 1) { pb_set_error("pb_create: sizes must be positive"); return PB_ERR_INVALID; }
+    if (c.num_anchors > 65536) { pb_set_error("pb_create: num_anchors > 65536 unsupported"); return PB_ERR_UNSUPPORTED; }
+    if (c.max_tracks >= 65536 || c.max_detections >= 65536) { pb_set_error("pb_create: max_tracks/max_detections too large"); return PB_ERR_UNSUPPORTED; }
+    if (c.max_keep > c.max_candidates) { pb_set_error("pb_create: max_keep > max_candidates"); return PB_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c.device) {
+        (void)cudaGetLastError();
+        pb_set_error("pb_create: CUDA device %d not available (this library has no CPU path)", c.device);
+        return PB_ERR_NO_DEVICE;
+    }
+    PB_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop{};
+    PB_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 10) { pb_set_error("pb_create: device sm_%d%d, built for sm_100a only", prop.major, prop.minor); return PB_ERR_NO_DEVICE; }
+    if (decode_nms_smem_bytes(c.max_candidates, c.max_keep) > (size_t)prop.sharedMemPerBlockOptin) {
+        pb_set_error("pb_create: max_candidates=%d needs %zu B of shared memory (> %zu)", c.max_candidates,
+                     decode_nms_smem_bytes(c.max_candidates, c.max_keep), (size_t)prop.sharedMemPerBlockOptin);
+        return PB_ERR_UNSUPPORTED;
+    }
+    pb_handle_st* h = new (std::nothrow) pb_handle_st();
+    if (!h) { pb_set_error("pb_create: out of host memory"); return PB_ERR_INVALID; }
+    h->cfg = c;
+    int r = build_handle(h);
+    if (r != PB_OK) { pb_destroy(h); return r; }
+    *out = h;
+    return PB_OK;
+}
+
+int pb_destroy(pb_handle_t h) {
+    if (!h) return PB_OK;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->h_out_pinned) cudaFreeHost(h->h_out_pinned);
+    if (h->h_cnt_pinned) cudaFreeHost(h->h_cnt_pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return PB_OK;
+}
+
+int pb_reset(pb_handle_t h, pb_stream_t stream) {
+    if (!h) { pb_set_error("pb_reset: null handle"); return PB_ERR_INVALID; }
+    PB_CUDA(launch_tracker_reset(h->trk, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, (cudaStream_t)stream));
+    h->frames = 0;
+    return PB_OK;
+}
+
+int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, pb_stream_t stream) {
+    if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
+    const pb_config& c = h->cfg;
+    PB_CUDA(launch_decode_nms(d_heads, c.num_streams, c.num_anchors, c.max_candidates, c.max_keep, conf, nms,
+                              h->post, (cudaStream_t)stream));
+    return PB_OK;
+}
+
+int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_det_scores,
+                      const int* d_num_dets, int det_stride, int frame_id, pb_stream_t stream) {
+    if (!h) { pb_set_error("pb_tracker_update: null handle"); return PB_ERR_INVALID; }
+    const pb_config& c = h->cfg;
+    DetSource src;
+    if (d_det_poses == nullptr && d_det_scores == nullptr && d_num_dets == nullptr) {
+        src = {h->post.det_poses, h->post.det_scores, h->post.num_keep, c.max_keep};
+    } else {
+        if (!d_det_poses || !d_det_scores || !d_num_dets || det_stride < 1) {
+            pb_set_error("pb_tracker_update: detection pointers must be all NULL or all set");
+            return PB_ERR_INVALID;
+        }
+        src = {d_det_poses, d_det_scores, d_num_dets, det_stride};
+    }
+    TrackParams p{};
+    p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
+    p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
+    p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
+    PB_CUDA(launch_tracker(h->trk, p, src, h->plan, (cudaStream_t)stream));
+    h->frames++;
+    return PB_OK;
+}
+
+int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int frame_id, pb_stream_t stream) {
+    PB_TRY(pb_postprocess(h, d_heads, conf, nms, stream));
+    return pb_tracker_update(h, nullptr, nullptr, nullptr, 0, frame_id, stream);
+}
+
+int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
+                 void* h_tracks, int* h_counts) {
+    if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_step_host: null argument"); return PB_ERR_INVALID; }
+    const pb_config& c = h->cfg;
+    const size_t B = c.num_streams, Dm = c.max_detections;
+    const size_t head_bytes = B * HEAD_ROWS * (size_t)c.num_anchors * sizeof(float);
+    if (!h->d_stage) PB_CUDA(cudaMalloc(&h->d_stage, head_bytes));
+    if (!h->h_out_pinned) PB_CUDA(cudaMallocHost(&h->h_out_pinned, B * Dm * 228));
+    if (!h->h_cnt_pinned) PB_CUDA(cudaMallocHost(&h->h_cnt_pinned, B * sizeof(int)));
+    cudaStream_t s = h->own_stream;
+    PB_CUDA(cudaMemcpyAsync(h->d_stage, h_heads, head_bytes, cudaMemcpyHostToDevice, s));
+    PB_TRY(pb_step(h, h->d_stage, conf, nms, frame_id, (pb_stream_t)s));
+    PB_CUDA(cudaMemcpyAsync(h->h_cnt_pinned, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(h->h_out_pinned, h->trk.outputs, B * Dm * 228, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    memcpy(h_counts, h->h_cnt_pinned, B * sizeof(int));
+    memcpy(h_tracks, h->h_out_pinned, B * Dm * 228);
+    return PB_OK;
+}
+
+int pb_get_tracks(pb_handle_t h, int b, void* out, int cap, int* n_out) {
+    if (!h || b < 0 || b >= h->cfg.num_streams || !n_out) { pb_set_error("pb_get_tracks: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    int n = 0;
+    PB_CUDA(cudaMemcpy(&n, h->trk.num_outputs + b, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n > cap) n = cap;
+    if (n > 0 && out)
+        PB_CUDA(cudaMemcpy(out, static_cast<unsigned char*>(h->trk.outputs) + (size_t)b * h->cfg.max_detections * 228,
+                           (size_t)n * 228, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return PB_OK;
+}
+
+int pb_get_tracks_all(pb_handle_t h, void* out, int* counts) {
+    if (!h || !out || !counts) { pb_set_error("pb_get_tracks_all: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    const size_t B = h->cfg.num_streams;
+    PB_CUDA(cudaMemcpy(counts, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(out, h->trk.outputs, B * h->cfg.max_detections * 228, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+int pb_get_num_active(pb_handle_t h, int* out) {
+    if (!h || !out) { pb_set_error("pb_get_num_active: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    std::vector<int> sc((size_t)h->cfg.num_streams * 4);
+    PB_CUDA(cudaMemcpy(sc.data(), h->trk.scalars, sc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < h->cfg.num_streams; ++b) out[b] = sc[(size_t)b * 4 + 3];
+    return PB_OK;
+}
+
+#define PB_D2H(dst, src, count)                                                                     \
+    do { if (dst) PB_CUDA(cudaMemcpy(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyDeviceToHost)); } while (0)
+
+int pb_get_kept(pb_handle_t h, int b, float* poses, float* bboxes, float* scores, int* keep_slots,
+                int* keep_anchors, int cap, int* num_keep, int* num_cand) {
+    if (!h || b < 0 || b >= h->cfg.num_streams) { pb_set_error("pb_get_kept: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    const size_t K = h->cfg.max_keep;
+    int nk = 0, nc = 0;
+    PB_CUDA(cudaMemcpy(&nk, h->post.num_keep + b, sizeof(int), cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(&nc, h->post.num_cand + b, sizeof(int), cudaMemcpyDeviceToHost));
+    if (num_keep) *num_keep = nk;
+    if (num_cand) *num_cand = nc;
+    int n = nk < cap ? nk : cap;
+    if (n > 0) {
+        PB_D2H(poses, h->post.det_poses + b * K * POSE_F, (size_t)n * POSE_F);
+        PB_D2H(bboxes, h->post.det_bboxes + b * K * 4, (size_t)n * 4);
+        PB_D2H(scores, h->post.det_scores + b * K, n);
+        PB_D2H(keep_slots, h->post.keep_slots + b * K, n);
+        PB_D2H(keep_anchors, h->post.keep_anchors + b * K, n);
+    }
+    return PB_OK;
+}
+
+int pb_get_state(pb_handle_t h, int b, float* poses, float* vel, float* scores, int* states, int* ids,
+                 int* hits, int* ages, int* last_frame, int* active, int* row_assign, int* col_assign,
+                 float* cost, float* predicted, float* centers, int* scalars) {
+    if (!h || b < 0 || b >= h->cfg.num_streams) { pb_set_error("pb_get_state: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    const size_t T = h->cfg.max_tracks, Dm = h->cfg.max_detections;
+    const TrackBuffers& t = h->trk;
+    PB_D2H(poses, t.poses + b * T * POSE_F, T * POSE_F);
+    PB_D2H(vel, t.vel + b * T * 34, T * 34);
+    PB_D2H(scores, t.scores + b * T, T);
+    PB_D2H(states, t.states + b * T, T);
+    PB_D2H(ids, t.ids + b * T, T);
+    PB_D2H(hits, t.hits + b * T, T);
+    PB_D2H(ages, t.ages + b * T, T);
+    PB_D2H(last_frame, t.last_frame + b * T, T);
+    PB_D2H(active, t.active + b * T, T);
+    PB_D2H(row_assign, t.row_assign + b * T, T);
+    PB_D2H(col_assign, t.col_assign + b * Dm, Dm);
+    PB_D2H(cost, t.cost + b * T * Dm, T * Dm);
+    PB_D2H(predicted, t.predicted + b * T * POSE_F, T * POSE_F);
+    PB_D2H(centers, t.tcent + b * T * 4, T * 4);
+    PB_D2H(scalars, t.scalars + b * 4, 4);
+    return PB_OK;
+}
+
+int pb_get_device_views(pb_handle_t h, pb_device_views* v) {
+    if (!h || !v) { pb_set_error("pb_get_device_views: bad argument"); return PB_ERR_INVALID; }
+    v->det_poses = h->post.det_poses; v->det_bboxes = h->post.det_bboxes; v->det_scores = h->post.det_scores;
+    v->num_keep = h->post.num_keep; v->num_cand = h->post.num_cand;
+    v->keep_slots = h->post.keep_slots; v->keep_anchors = h->post.keep_anchors;
+    v->track_poses = h->trk.poses; v->track_scores = h->trk.scores; v->track_states = h->trk.states;
+    v->track_ids = h->trk.ids; v->track_outputs = h->trk.outputs; v->num_outputs = h->trk.num_outputs;
+    v->num_active = h->trk.scalars;
+    return PB_OK;
+}
+
+int pb_get_timing(pb_handle_t h, pb_timing* out) {
+    if (!h || !out) { pb_set_error("pb_get_timing: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    const int B = h->cfg.num_streams;
+    std::vector<unsigned long long> ns((size_t)B * 12);
+    PB_CUDA(cudaMemcpy(ns.data(), h->trk.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long acc[12] = {0};
+    for (int b = 0; b < B; ++b) for (int i = 0; i < 12; ++i) acc[i] += ns[(size_t)b * 12 + i];
+    auto us = [&](int i) { return (long long)(acc[i] / 1000ull / (unsigned long long)B); };   // mean over streams
+    out->predict_us = us(1); out->gate_us = us(2); out->high_assoc_us = us(3); out->low_assoc_us = us(4);
+    out->lost_assoc_us = us(5); out->update_us = us(6); out->age_us = us(7); out->new_track_us = us(8);
+    out->dedup_us = us(9); out->total_us = us(10);
+    out->frame_count = (int)(acc[11] / (unsigned long long)B);
+    return PB_OK;
+}
+
+}  // extern "C"

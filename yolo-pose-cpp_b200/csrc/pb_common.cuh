@@ -1,0 +1,109 @@
+// pb_common.cuh — shared declarations of the sm_100a kernels (internal).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pb_math.h"
+#include "../../include/posebyte_b200.h"
+
+namespace pb {
+
+constexpr int KP = 17;
+constexpr int POSE_F = 51;                 // floats per pose (17 x (x,y,conf))
+constexpr int ST_TENTATIVE = 0, ST_CONFIRMED = 1, ST_LOST = 2;   // reference gpu_tracker.cu:23-25
+constexpr int HEAD_ROWS = 56;
+
+__device__ __constant__ const float kSigmas[KP] = {
+    0.026f, 0.025f, 0.025f, 0.035f, 0.035f, 0.079f, 0.079f, 0.072f, 0.072f,
+    0.062f, 0.062f, 0.107f, 0.107f, 0.087f, 0.087f, 0.089f, 0.089f};
+
+// ---- post-process (decode + NMS) buffers, one slab per stream ------------------------
+struct PostBuffers {
+    float* det_poses;    // [B, Kcap, 51]  kept detections in score order
+    float* det_bboxes;   // [B, Kcap, 4]
+    float* det_scores;   // [B, Kcap]
+    int* keep_slots;     // [B, Kcap]  candidate slot (anchor-ordered list index)
+    int* keep_anchors;   // [B, Kcap]  anchor index
+    int* num_keep;       // [B]
+    int* num_cand;       // [B]
+};
+
+// ---- tracker state, struct-of-arrays over streams (all persistent across frames) ------
+struct TrackBuffers {
+    float* poses;        // [B, T, 51]
+    float* vel;          // [B, T, 34]
+    float* scores;       // [B, T]
+    float* predicted;    // [B, T, 51]
+    float* tcent;        // [B, T, 4]
+    float* dcent;        // [B, Dm, 4]
+    float* cost;         // [B, T*Dm]   flat, stride = this frame's D (reference quirk Q1)
+    float* det_scores;   // [B, Dm]
+    int* states;         // [B, T]
+    int* ids;            // [B, T]
+    int* hits;           // [B, T]
+    int* ages;           // [B, T]
+    int* last_frame;     // [B, T]
+    int* active;         // [B, T]
+    int* pred_dirty;     // [B, T]  predicted[t] changed since tcent[t] was last derived from it
+    int* row_assign;     // [B, T]
+    int* col_assign;     // [B, Dm]
+    int* scalars;        // [B, 4]  next_id, slot_hint, D, num_active
+    void* outputs;       // [B, Dm] TrackOutput (228 B)
+    int* num_outputs;    // [B]
+    float* det_poses_scratch;  // [B, Dm, 51]  used when the detections do not fit in shared memory
+    unsigned long long* stage_ns;  // [B, 12] globaltimer stamps per stage (telemetry)
+};
+
+struct TrackParams {
+    int B, T, Dm;
+    float new_track_thresh;
+    int max_age, min_hits, gating_enabled;
+    int frame_id;
+    // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
+    int cost_in_smem, det_in_smem, pred_in_smem;
+};
+
+struct DetSource {
+    const float* poses;   // [B, stride, 51]
+    const float* scores;  // [B, stride]
+    const int* num;       // [B]
+    int stride;
+};
+
+// ---- warp helpers ---------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream_f(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// host-side launchers (defined in the .cu files, called from pb_api.cu)
+size_t decode_nms_smem_bytes(int max_cand, int max_keep);
+cudaError_t launch_decode_nms(const float* d_heads, int B, int N, int max_cand, int max_keep,
+                              float conf_thr, float nms_thr, const PostBuffers& out,
+                              cudaStream_t stream);
+
+struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem; };
+TrackerPlan tracker_plan(int T, int Dm);
+cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
+                           const TrackerPlan& plan, cudaStream_t stream);
+cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, cudaStream_t stream);
+
+void count_launch(int n = 1);
+
+}  // namespace pb

@@ -1,0 +1,705 @@
+// tracker.cu — PoseBYTE tracker update for B independent streams, one CTA per stream.
+//
+// Replaces GPUTracker::update + getActiveTracks (reference src/cuda/gpu_tracker.cu:
+// 1057-1158, 1559-1639) — ~490 stream operations and 2 host synchronisations per frame
+// and stream upstream — with ONE launch for all streams.  The stage order, every
+// formula and every persistent buffer follow the reference literally (SURVEY.md §8a rows
+// A5-A16, quirks Q1-Q8); the stages run back to back inside the CTA with the working set
+// (cost matrix, detections, predicted poses, gate bitmasks, assignments, prices) in
+// shared memory:
+//   predict (:102-138) -> keypoint-box centres (:196-237) -> velocity-adaptive spatial
+//   gate (:241-317), bit-packed -> tier 1: visibility-masked OKS (:333-425) + auction +
+//   lock (:540-567) -> tier 2: torso OKS (:429-490) + auction + merge (:575-588) + lock
+//   -> tier 3: lost-track gate x1.3, OKS, auction, merge -> constant-gain update
+//   (:141-189, :612-648) -> ageing (:651-688) -> new tracks (:695-780, rules R3/R4) ->
+//   IoU de-duplication (:788-895, rule R5) -> TrackOutput assembly (:1594-1636).
+// The auction (hungarian.cu:27-123, 358-405) keeps the reference's bid arithmetic and
+// tie-breaks (R6): a warp scans one bidder row (shuffle top-2 reduction), bids meet in a
+// packed 64-bit shared atomicMax (bid bits | ~row), and the loop stops at the first
+// iteration without bidders — a fixed point of the reference's 50 fixed iterations.
+#include "pb_common.cuh"
+#include "auction.cuh"
+
+namespace pb {
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int DUP_CAP = 256;
+
+struct TkSmem {
+    int *active, *states, *hits, *ids, *ages, *row, *rowb, *act_list, *elig_list;   // [T]
+    int *col, *colb, *slot_for_det, *out_list;                                        // [Dm]
+    float *price, *dscore, *darea;                                                    // [Dm]
+    unsigned long long* colbid;                                                       // [Dm]
+    float *tcent, *tarea, *tav;                                                       // [T*4],[T],[T]
+    float* dcent;                                                                     // [Dm*4]
+    unsigned *gate, *lgate;                                                           // [T*Dw]
+    unsigned* colmask;                                                                // [Dw]
+    int* dup;                                                                         // [DUP_CAP]
+    int* misc;                                                                        // [32]
+    float *cost, *det, *pred;                                                         // optional
+};
+
+__host__ __device__ inline size_t tk_align(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, int cost_s, int det_s,
+                                           int pred_s, TkSmem* s) {
+    const int Dw = (Dm + 31) / 32;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = tk_align(off + bytes); return o; };
+    size_t o_colbid = take((size_t)Dm * 8);
+    size_t o_i[9]; for (int i = 0; i < 9; ++i) o_i[i] = take((size_t)T * 4);
+    size_t o_d[4]; for (int i = 0; i < 4; ++i) o_d[i] = take((size_t)Dm * 4);
+    size_t o_f[3]; for (int i = 0; i < 3; ++i) o_f[i] = take((size_t)Dm * 4);
+    size_t o_tcent = take((size_t)T * 16), o_tarea = take((size_t)T * 4), o_tav = take((size_t)T * 4);
+    size_t o_dcent = take((size_t)Dm * 16);
+    size_t o_gate = take((size_t)T * Dw * 4), o_lgate = take((size_t)T * Dw * 4), o_colmask = take((size_t)Dw * 4);
+    size_t o_dup = take(DUP_CAP * 4), o_misc = take(32 * 4);
+    size_t o_cost = cost_s ? take((size_t)T * Dm * 4) : 0;
+    size_t o_det = det_s ? take((size_t)Dm * POSE_F * 4) : 0;
+    size_t o_pred = pred_s ? take((size_t)T * POSE_F * 4) : 0;
+    if (s) {
+        s->colbid = (unsigned long long*)(base + o_colbid);
+        int** ip[9] = {&s->active, &s->states, &s->hits, &s->ids, &s->ages, &s->row, &s->rowb, &s->act_list, &s->elig_list};
+        for (int i = 0; i < 9; ++i) *ip[i] = (int*)(base + o_i[i]);
+        int** dp[4] = {&s->col, &s->colb, &s->slot_for_det, &s->out_list};
+        for (int i = 0; i < 4; ++i) *dp[i] = (int*)(base + o_d[i]);
+        float** fp[3] = {&s->price, &s->dscore, &s->darea};
+        for (int i = 0; i < 3; ++i) *fp[i] = (float*)(base + o_f[i]);
+        s->tcent = (float*)(base + o_tcent); s->tarea = (float*)(base + o_tarea); s->tav = (float*)(base + o_tav);
+        s->dcent = (float*)(base + o_dcent);
+        s->gate = (unsigned*)(base + o_gate); s->lgate = (unsigned*)(base + o_lgate);
+        s->colmask = (unsigned*)(base + o_colmask);
+        s->dup = (int*)(base + o_dup); s->misc = (int*)(base + o_misc);
+        s->cost = cost_s ? (float*)(base + o_cost) : nullptr;
+        s->det = det_s ? (float*)(base + o_det) : nullptr;
+        s->pred = pred_s ? (float*)(base + o_pred) : nullptr;
+    }
+    return off;
+}
+
+TrackerPlan tracker_plan(int T, int Dm) {
+    TrackerPlan p{};
+    const size_t budget = 200 * 1024;
+    p.cost_in_smem = p.det_in_smem = p.pred_in_smem = 0;
+    size_t base = tk_carve(nullptr, T, Dm, 0, 0, 0, nullptr);
+    size_t cost_b = tk_align((size_t)T * Dm * 4), det_b = tk_align((size_t)Dm * POSE_F * 4), pred_b = tk_align((size_t)T * POSE_F * 4);
+    size_t used = base;
+    if (used + cost_b <= budget) { p.cost_in_smem = 1; used += cost_b; }
+    if (used + det_b <= budget) { p.det_in_smem = 1; used += det_b; }
+    if (used + pred_b <= budget) { p.pred_in_smem = 1; used += pred_b; }
+    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, nullptr);
+    const long cells = (long)T * Dm;
+    p.threads = cells <= 16384 ? 256 : (cells <= 65536 ? 512 : 1024);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// keypoint-box statistics of one pose (17 lanes of a warp would be overkill: T+D poses)
+// centres as kernelComputeBboxCenters (:196-237); area as the scale term of
+// kernelOKSWithGating (:364-392).  Both use keypoints with conf > 0.1.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pose_box(const float* p, float* cent4, float* area) {
+    float lx = 1e9f, ly = 1e9f, hx = -1e9f, hy = -1e9f;
+    int valid = 0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        if (p[k * 3 + 2] > 0.1f) {
+            const float x = p[k * 3], y = p[k * 3 + 1];
+            lx = pb_min(lx, x); ly = pb_min(ly, y); hx = pb_max(hx, x); hy = pb_max(hy, y);
+            ++valid;
+        }
+    }
+    *area = (hx - lx) * (hy - ly);
+    if (valid < 2) { cent4[0] = 0.f; cent4[1] = 0.f; cent4[2] = 0.f; cent4[3] = 0.f; return; }
+    const float w = hx - lx, h = hy - ly;
+    cent4[0] = (lx + hx) * 0.5f; cent4[1] = (ly + hy) * 0.5f; cent4[2] = w; cent4[3] = h;
+}
+
+// kernelSpatialGate (:241-317) for one active row / one detection.
+__device__ __forceinline__ bool gate_cell(const float* tc, const float* dc, float av, bool lost,
+                                          float base, bool gating) {
+    const float tw = tc[2], th = tc[3], dw = dc[2], dh = dc[3];
+    if (tw < 1.0f || th < 1.0f || dw < 1.0f || dh < 1.0f) return true;
+    if (!gating) return true;
+    const float dx = tc[0] - dc[0], dy = tc[1] - dc[1];
+    const float dist = sqrtf(dx * dx + dy * dy);
+    const float size = (tw + th + dw + dh) * 0.25f;
+    const float ratio = dist / (size + 1e-6f);
+    const float vf = 1.0f + pb_min(av / (size + 1e-6f), 2.0f);
+    float thr = base * vf;
+    if (lost) thr *= 2.0f;
+    return ratio < thr;
+}
+
+// kernelOKSWithGating cell (:360-424).
+__device__ __forceinline__ float oks_cost(const float* tp, const float* dp, float ta, float da, float vis) {
+    const float scale_sq = pb_max((da + ta) * 0.5f, 1000.0f);
+    const float t2 = 2.0f * scale_sq;
+    float sum = 0.0f;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        if (dp[k * 3 + 2] > vis && tp[k * 3 + 2] > vis) {
+            const float dx = dp[k * 3] - tp[k * 3], dy = dp[k * 3 + 1] - tp[k * 3 + 1];
+            const float d2 = dx * dx + dy * dy;
+            const float sg = kSigmas[k] * 2.0f;
+            const float s2 = sg * sg;
+            sum += pb_expf(-d2 / (t2 * s2));
+            ++cnt;
+        }
+    }
+    const float oks = (cnt >= 3) ? (sum / (float)cnt) : 0.0f;
+    return 1.0f - oks;
+}
+
+// kernelTorsoOKS cell (:455-489).
+__device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
+    const int torso[4] = {5, 6, 11, 12};
+    const float scale_sq = 10000.0f;
+    float sum = 0.0f;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = torso[i];
+        if (dp[k * 3 + 2] > 0.1f && tp[k * 3 + 2] > 0.1f) {
+            const float dx = dp[k * 3] - tp[k * 3], dy = dp[k * 3 + 1] - tp[k * 3 + 1];
+            const float d2 = dx * dx + dy * dy;
+            const float sg = kSigmas[k] * 3.0f;
+            sum += pb_expf(-d2 / (2.0f * scale_sq * sg * sg));
+            ++cnt;
+        }
+    }
+    const float oks = (cnt >= 2) ? (sum / (float)cnt) : 0.0f;
+    return 1.0f - oks;
+}
+
+struct Ctx {
+    TkSmem s;
+    int T, D, Dw, tid, nthreads, lane, warp, nwarps;
+    float* cost;        // shared or global, flat [t*D + d]
+    const float* det;   // shared or global scratch [d*51]
+    float* pred;        // shared or global (persistent) [t*51]
+};
+
+// Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
+__device__ __forceinline__ void auction_solve(Ctx& c) {
+    TkSmem& s = c.s;
+    auction_solve_cta(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, s.colbid, &s.misc[8],
+                      c.tid, c.nthreads);
+}
+
+// kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.
+__device__ void lock_pairs(Ctx& c, unsigned* gate) {
+    TkSmem& s = c.s;
+    const int T = c.T, D = c.D, Dw = c.Dw;
+    for (int w = c.tid; w < Dw; w += c.nthreads) {
+        unsigned mk = 0u;
+        for (int bit = 0; bit < 32; ++bit) { const int d = w * 32 + bit; if (d < D && s.col[d] >= 0) mk |= 1u << bit; }
+        s.colmask[w] = mk;
+    }
+    __syncthreads();
+    for (int i = c.tid; i < T * D; i += c.nthreads) {
+        const int t = i / D, d = i - t * D;
+        if (s.row[t] >= 0 || s.col[d] >= 0) c.cost[i] = 1e9f;
+    }
+    for (int i = c.tid; i < T * Dw; i += c.nthreads) {
+        const int t = i / Dw, w = i - t * Dw;
+        gate[i] = (s.row[t] >= 0) ? 0u : (gate[i] & ~s.colmask[w]);
+    }
+    __syncthreads();
+}
+
+// cost <- 1.0 on inactive rows; cost <- f(cell) on gated cells of active rows (:351-358).
+template <bool TORSO>
+__device__ void cost_pass(Ctx& c, const unsigned* gate, int na) {
+    TkSmem& s = c.s;
+    const int T = c.T, D = c.D, Dw = c.Dw;
+    for (int i = c.tid; i < T * D; i += c.nthreads) {
+        const int t = i / D;
+        if (s.active[t] == 0) c.cost[i] = 1.0f;
+    }
+    for (int i = c.tid; i < na * D; i += c.nthreads) {
+        const int ai = i / D, d = i - ai * D;
+        const int t = s.act_list[ai];
+        if ((gate[t * Dw + (d >> 5)] >> (d & 31)) & 1u) {
+            const float* tp = c.pred + (size_t)t * POSE_F;
+            const float* dp = c.det + (size_t)d * POSE_F;
+            c.cost[(size_t)t * D + d] = TORSO ? torso_cost(tp, dp) : oks_cost(tp, dp, s.tarea[t], s.darea[d], 0.2f);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void backup_assign(Ctx& c) {
+    TkSmem& s = c.s;
+    for (int t = c.tid; t < c.T; t += c.nthreads) s.rowb[t] = s.row[t];
+    for (int d = c.tid; d < c.D; d += c.nthreads) s.colb[d] = s.col[d];
+    __syncthreads();
+}
+__device__ void merge_assign(Ctx& c) {   // kernelMergeAssignments :575-588
+    TkSmem& s = c.s;
+    for (int t = c.tid; t < c.T; t += c.nthreads) if (s.rowb[t] >= 0) s.row[t] = s.rowb[t];
+    for (int d = c.tid; d < c.D; d += c.nthreads) if (s.colb[d] >= 0) s.col[d] = s.colb[d];
+    __syncthreads();
+}
+
+__device__ __forceinline__ float center_iou(const float* a, const float* b) {   // kernelTrackIoU :825-854
+    const float cx1 = a[0], cy1 = a[1], w1 = a[2], h1 = a[3];
+    const float cx2 = b[0], cy2 = b[1], w2 = b[2], h2 = b[3];
+    const float x1a = cx1 - w1 * 0.5f, x1b = cx1 + w1 * 0.5f, y1a = cy1 - h1 * 0.5f, y1b = cy1 + h1 * 0.5f;
+    const float x2a = cx2 - w2 * 0.5f, x2b = cx2 + w2 * 0.5f, y2a = cy2 - h2 * 0.5f, y2b = cy2 + h2 * 0.5f;
+    const float ix1 = pb_max(x1a, x2a), iy1 = pb_max(y1a, y2a);
+    const float ix2 = pb_min(x1b, x2b), iy2 = pb_min(y1b, y2b);
+    const float iw = pb_max(0.0f, ix2 - ix1), ih = pb_max(0.0f, iy2 - iy1);
+    const float inter = iw * ih;
+    const float a1 = w1 * h1, a2 = w2 * h2;
+    const float uni = a1 + a2 - inter;
+    return (uni > 0) ? (inter / uni) : 0.0f;
+}
+
+template <int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS)
+pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx c;
+    tk_carve(smem_raw, P.T, P.Dm, P.cost_in_smem, P.det_in_smem, P.pred_in_smem, &c.s);
+    TkSmem& s = c.s;
+    const int b = blockIdx.x;
+    const int T = P.T, Dm = P.Dm;
+    c.T = T; c.tid = threadIdx.x; c.nthreads = NTHREADS; c.lane = threadIdx.x & 31;
+    c.warp = threadIdx.x >> 5; c.nwarps = NTHREADS >> 5;
+    const int tid = c.tid, NT = c.nthreads;
+
+    // per-stream slabs
+    float* g_poses = tb.poses + (size_t)b * T * POSE_F;
+    float* g_vel = tb.vel + (size_t)b * T * 34;
+    float* g_scores = tb.scores + (size_t)b * T;
+    float* g_pred = tb.predicted + (size_t)b * T * POSE_F;
+    float* g_tcent = tb.tcent + (size_t)b * T * 4;
+    float* g_cost = tb.cost + (size_t)b * T * Dm;
+    float* g_dscore = tb.det_scores + (size_t)b * Dm;
+    int* g_states = tb.states + (size_t)b * T; int* g_ids = tb.ids + (size_t)b * T;
+    int* g_hits = tb.hits + (size_t)b * T; int* g_ages = tb.ages + (size_t)b * T;
+    int* g_last = tb.last_frame + (size_t)b * T; int* g_active = tb.active + (size_t)b * T;
+    int* g_dirty = tb.pred_dirty + (size_t)b * T;
+    int* g_scal = tb.scalars + (size_t)b * 4;
+    unsigned long long* g_ns = tb.stage_ns + (size_t)b * 12;
+
+    unsigned long long t_stamp = 0;
+    if (tid == 0) t_stamp = globaltimer_ns();
+    const unsigned long long t_begin = t_stamp;
+    auto stamp = [&](int slot) {
+        if (tid == 0) { const unsigned long long now = globaltimer_ns(); g_ns[slot] += now - t_stamp; t_stamp = now; }
+    };
+
+    // ---------------- prologue (:1065-1088) ----------------
+    int n_in = src.num[b];
+    const int D = n_in < Dm ? (n_in < 0 ? 0 : n_in) : Dm;
+    c.D = D; c.Dw = (Dm + 31) / 32;
+    const int Dw = c.Dw;
+    const float* src_pose = src.poses + (size_t)b * src.stride * POSE_F;
+    const float* src_score = src.scores + (size_t)b * src.stride;
+    float* det_w = P.det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
+    for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
+    for (int d = tid; d < D; d += NT) { const float sc = src_score[d]; s.dscore[d] = sc; g_dscore[d] = sc; s.col[d] = -1; }
+    int na_local = 0;
+    for (int t = tid; t < T; t += NT) {
+        const int a = g_active[t];
+        s.active[t] = a; s.states[t] = g_states[t]; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
+        s.row[t] = -1;
+        na_local += (a == 1);
+    }
+    for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
+    c.det = det_w;
+    c.cost = P.cost_in_smem ? s.cost : g_cost;
+    c.pred = P.pred_in_smem ? s.pred : g_pred;
+    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
+    if (tid < 32) s.misc[tid] = 0;
+    __syncthreads();
+    {   // active count + ordered active list (ascending t)
+        for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
+            const int t = base + c.lane;
+            const bool a = (t < T) && (s.active[t] == 1);
+            const unsigned bm = __ballot_sync(FULLM, a);
+            int start = 0;
+            if (c.lane == 0 && bm) start = atomicAdd(&s.misc[0], __popc(bm));
+            start = __shfl_sync(FULLM, start, 0);
+            if (a) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
+        }
+    }
+    __syncthreads();
+    const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
+    (void)na_local;
+    stamp(0);
+
+    // ---------------- predict (:1160-1175, kernel :102-138) ----------------
+    if (na > 0) {
+        for (int i = tid; i < na * KP; i += NT) {
+            const int ai = i / KP, k = i - ai * KP;
+            const int t = s.act_list[ai];
+            const int po = t * POSE_F + k * 3, vo = t * 34 + k * 2;
+            const float x = g_poses[po], y = g_poses[po + 1], cf = g_poses[po + 2];
+            const float vx = g_vel[vo], vy = g_vel[vo + 1];
+            const float dt = 1.0f;
+            const float px = x + vx * dt, py = y + vy * dt;
+            g_pred[po] = px; g_pred[po + 1] = py; g_pred[po + 2] = cf;
+            if (P.pred_in_smem) { s.pred[po] = px; s.pred[po + 1] = py; s.pred[po + 2] = cf; }
+            if (s.states[t] == ST_LOST) { g_vel[vo] = vx * 0.95f; g_vel[vo + 1] = vy * 0.95f; }
+            if (k == 0) g_dirty[t] = 1;
+        }
+    }
+    __syncthreads();
+    stamp(1);
+
+    const bool assoc12 = (na > 0) && (D > 0);
+    // ---------------- centres + gates (:1177-1208, kernels :196-317) ----------------
+    if (assoc12) {
+        // track centres: every slot whose predicted pose changed since its centre was derived
+        // (== the reference recomputing all T slots: unchanged slots give unchanged centres)
+        for (int t = tid; t < T; t += NT) {
+            if (g_dirty[t]) {
+                const float* pp = (P.pred_in_smem && s.active[t] == 1) ? (s.pred + (size_t)t * POSE_F) : (g_pred + (size_t)t * POSE_F);
+                float area;
+                pose_box(pp, &s.tcent[t * 4], &area);
+                s.tarea[t] = area;
+                g_tcent[t * 4] = s.tcent[t * 4]; g_tcent[t * 4 + 1] = s.tcent[t * 4 + 1];
+                g_tcent[t * 4 + 2] = s.tcent[t * 4 + 2]; g_tcent[t * 4 + 3] = s.tcent[t * 4 + 3];
+                g_dirty[t] = 0;
+            }
+        }
+        for (int ai = tid; ai < na; ai += NT) {   // mean torso speed per active row (:287-298)
+            const int t = s.act_list[ai];
+            const int torso[4] = {5, 6, 11, 12};
+            float av = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float vx = g_vel[t * 34 + torso[i] * 2], vy = g_vel[t * 34 + torso[i] * 2 + 1];
+                av += sqrtf(vx * vx + vy * vy);
+            }
+            s.tav[t] = av * 0.25f;
+        }
+    }
+    if (D > 0) {
+        for (int d = tid; d < D; d += NT) {
+            float area;
+            pose_box(c.det + (size_t)d * POSE_F, &s.dcent[d * 4], &area);
+            s.darea[d] = area;
+        }
+        for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = 0u; s.lgate[i] = 0u; }
+    }
+    __syncthreads();
+    if (assoc12) {
+        // gate (base 3.0) minus LOST rows (tier 1 mask, :1231) and lost-tier gate (base 3.0*1.3,
+        // only LOST rows survive the two state masks, :1359-1387).  One warp per (row, 32 dets).
+        const int words = (D + 31) / 32;
+        for (int i = c.warp; i < na * words; i += c.nwarps) {
+            const int ai = i / words, w = i - ai * words;
+            const int t = s.act_list[ai];
+            const int d = w * 32 + c.lane;
+            const bool lost = (s.states[t] == ST_LOST);
+            const float base = lost ? (3.0f * 1.3f) : 3.0f;
+            bool g = false;
+            if (d < D) g = gate_cell(&s.tcent[t * 4], &s.dcent[d * 4], s.tav[t], lost, base, P.gating_enabled != 0);
+            const unsigned bm = __ballot_sync(FULLM, g);
+            if (c.lane == 0) { if (lost) s.lgate[t * Dw + w] = bm; else s.gate[t * Dw + w] = bm; }
+        }
+    }
+    __syncthreads();
+    stamp(2);
+
+    // ---------------- tier 1 (:1210-1274) ----------------
+    if (assoc12) {
+        cost_pass<false>(c, s.gate, na);
+        auction_solve(c);
+        lock_pairs(c, s.gate);
+    }
+    stamp(3);
+    // ---------------- tier 2 (:1276-1335) ----------------
+    if (assoc12) {
+        backup_assign(c);
+        cost_pass<true>(c, s.gate, na);
+        auction_solve(c);
+        merge_assign(c);
+        lock_pairs(c, s.gate);
+    }
+    stamp(4);
+    // ---------------- tier 3 (:1337-1436) ----------------
+    if (D > 0) {
+        backup_assign(c);
+        lock_pairs(c, s.lgate);
+        cost_pass<false>(c, s.lgate, na);
+        auction_solve(c);
+        merge_assign(c);
+    }
+    stamp(5);
+
+    // ---------------- update matched (:1438-1472, kernels :141-189, :612-648) -------------
+    if (D > 0) {
+        const float process_noise = 0.1f, measurement_noise = 0.3f;
+        const float K = measurement_noise / (measurement_noise + process_noise);
+        const float alpha = 0.3f;
+        for (int i = tid; i < na * KP; i += NT) {
+            const int ai = i / KP, k = i - ai * KP;
+            const int t = s.act_list[ai];
+            const int d = s.row[t];
+            if (d < 0) continue;
+            const int to = t * POSE_F + k * 3, vo = t * 34 + k * 2;
+            const float* dp = c.det + (size_t)d * POSE_F + k * 3;
+            const float ox = g_poses[to], oy = g_poses[to + 1];
+            const float zx = dp[0], zy = dp[1], zc = dp[2];
+            const float nx = ox + K * (zx - ox);
+            const float ny = oy + K * (zy - oy);
+            const float dx = zx - ox, dy = zy - oy;
+            g_vel[vo] = alpha * dx + (1 - alpha) * g_vel[vo];
+            g_vel[vo + 1] = alpha * dy + (1 - alpha) * g_vel[vo + 1];
+            g_poses[to] = nx; g_poses[to + 1] = ny; g_poses[to + 2] = zc;
+        }
+        for (int ai = tid; ai < na; ai += NT) {
+            const int t = s.act_list[ai];
+            const int d = s.row[t];
+            if (d < 0) continue;
+            g_scores[t] = s.dscore[d];
+            const int h = s.hits[t] + 1;
+            s.hits[t] = h;
+            s.ages[t] = 0;
+            g_last[t] = P.frame_id;
+            const int st = s.states[t];
+            if (st == ST_TENTATIVE && h >= P.min_hits) s.states[t] = ST_CONFIRMED;
+            else if (st == ST_LOST) s.states[t] = ST_CONFIRMED;
+        }
+    }
+    __syncthreads();
+    stamp(6);
+
+    // ---------------- age unmatched (:1474-1487, kernel :651-688) ----------------
+    for (int ai = tid; ai < na; ai += NT) {
+        const int t = s.act_list[ai];
+        if (s.row[t] >= 0) continue;
+        const int age = s.ages[t] + 1;
+        s.ages[t] = age;
+        const int st = s.states[t];
+        if (st == ST_TENTATIVE) { if (age > 2) s.active[t] = 0; }
+        else if (st == ST_CONFIRMED) { if (age > P.max_age) s.states[t] = ST_LOST; }
+        else if (st == ST_LOST) { if (age > P.max_age + 10) s.active[t] = 0; }
+    }
+    __syncthreads();
+    stamp(7);
+
+    // ---------------- new tracks (:1489-1526; R3/R4: ascending detection order) ------------
+    if (D > 0) {
+        if (tid == 0) {
+            int hint = g_scal[1], next_id = g_scal[0];
+            for (int d = 0; d < D; ++d) {
+                s.slot_for_det[d] = -1;
+                if (s.col[d] >= 0) continue;
+                if (s.dscore[d] < P.new_track_thresh) continue;
+                const int start = hint % T;
+                ++hint;
+                for (int i = 0; i < T; ++i) {
+                    int sl = start + i; if (sl >= T) sl -= T;
+                    if (s.active[sl] == 0) { s.active[sl] = 1; s.slot_for_det[d] = sl; break; }
+                }
+                const int sl = s.slot_for_det[d];
+                if (sl >= 0) {
+                    s.ids[sl] = next_id++;
+                    s.hits[sl] = 1; s.ages[sl] = 0; s.states[sl] = ST_TENTATIVE;
+                    g_scores[sl] = s.dscore[d];
+                    g_last[sl] = P.frame_id;
+                    s.col[d] = sl;
+                }
+            }
+            g_scal[1] = hint; g_scal[0] = next_id;
+        }
+        __syncthreads();
+        for (int i = tid; i < D * POSE_F; i += NT) {
+            const int d = i / POSE_F, e = i - d * POSE_F;
+            const int sl = s.slot_for_det[d];
+            if (sl >= 0) g_poses[sl * POSE_F + e] = c.det[(size_t)d * POSE_F + e];
+        }
+        for (int i = tid; i < D * 34; i += NT) {
+            const int d = i / 34, e = i - d * 34;
+            const int sl = s.slot_for_det[d];
+            if (sl >= 0) g_vel[sl * 34 + e] = 0.0f;
+        }
+    }
+    __syncthreads();
+    stamp(8);
+
+    // ---------------- de-duplication (:1528-1557; R5: sequential semantics) ----------------
+    {
+        if (tid == 0) { s.misc[1] = 0; s.misc[2] = 0; }
+        __syncthreads();
+        for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {   // eligible list, ascending
+            const int t = base + c.lane;
+            const bool e = (t < T) && s.active[t] == 1 && s.states[t] != ST_LOST && s.hits[t] >= P.min_hits;
+            const unsigned bm = __ballot_sync(FULLM, e);
+            if (bm) {
+                int start = 0;
+                if (c.lane == 0) start = atomicAdd(&s.misc[1], __popc(bm));
+                start = __shfl_sync(FULLM, start, 0);
+                if (e) s.elig_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
+            }
+        }
+        __syncthreads();
+        const int ne = s.misc[1];
+        for (int i = tid; i < ne * ne; i += NT) {
+            const int ia = i / ne, ib = i - ia * ne;
+            const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
+            if (t1 < t2 && center_iou(&s.tcent[t1 * 4], &s.tcent[t2 * 4]) > 0.7f) {
+                const int pos = atomicAdd(&s.misc[2], 1);
+                if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
+            }
+        }
+        __syncthreads();
+        const int ndup = s.misc[2];
+        if (tid == 0 && ndup > 0) {
+            auto resolve = [&](int t1, int t2) {
+                if (s.active[t1] == 0 || s.active[t2] == 0) return;      // LOST excluded by eligibility
+                if (s.hits[t1] < s.hits[t2] || (s.hits[t1] == s.hits[t2] && s.ids[t1] > s.ids[t2])) s.active[t1] = 0;
+                else s.active[t2] = 0;
+            };
+            if (ndup <= DUP_CAP) {
+                for (int i = 1; i < ndup; ++i) {                         // lexicographic (t1, t2)
+                    const int key = s.dup[i];
+                    int j = i - 1;
+                    while (j >= 0 && s.dup[j] > key) { s.dup[j + 1] = s.dup[j]; --j; }
+                    s.dup[j + 1] = key;
+                }
+                for (int i = 0; i < ndup; ++i) resolve(s.dup[i] >> 16, s.dup[i] & 0xffff);
+            } else {                                                     // overflow: recompute in order
+                for (int ia = 0; ia < ne; ++ia)
+                    for (int ib = 0; ib < ne; ++ib) {
+                        const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
+                        if (t1 < t2 && center_iou(&s.tcent[t1 * 4], &s.tcent[t2 * 4]) > 0.7f) resolve(t1, t2);
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    stamp(9);
+
+    // ---------------- outputs: getActiveTracks (:1594-1636) on the device ------------------
+    if (tid < 32) {
+        int count = 0;
+        for (int base = 0; base < D; base += 32) {
+            const int d = base + c.lane;
+            bool emit = false;
+            if (d < D) {
+                const int sl = s.col[d];
+                if (sl >= 0) {
+                    const int st = s.states[sl];
+                    emit = !(st == ST_TENTATIVE && s.hits[sl] < P.min_hits) && (st != ST_LOST);
+                }
+            }
+            const unsigned bm = __ballot_sync(FULLM, emit);
+            if (emit) s.out_list[count + __popc(bm & ((1u << c.lane) - 1u))] = d;
+            count += __popc(bm);
+        }
+        if (c.lane == 0) s.misc[3] = count;
+    }
+    __syncthreads();
+    const int n_out = s.misc[3];
+    {
+        float* outw = reinterpret_cast<float*>(tb.outputs) + (size_t)b * Dm * 57;
+        for (int o = c.warp; o < n_out; o += c.nwarps) {
+            const int d = s.out_list[o];
+            const int sl = s.col[d];
+            float* rec = outw + (size_t)o * 57;
+            float x = 0.f, y = 0.f, cf = 0.f;
+            float lx = 1e9f, ly = 1e9f, hx = -1e9f, hy = -1e9f;
+            if (c.lane < KP) {
+                x = g_poses[sl * POSE_F + c.lane * 3]; y = g_poses[sl * POSE_F + c.lane * 3 + 1]; cf = g_poses[sl * POSE_F + c.lane * 3 + 2];
+                rec[6 + c.lane * 3] = x; rec[7 + c.lane * 3] = y; rec[8 + c.lane * 3] = cf;
+                if (cf > 0.2f) { lx = x; ly = y; hx = x; hy = y; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                lx = pb_min(lx, __shfl_xor_sync(FULLM, lx, off)); ly = pb_min(ly, __shfl_xor_sync(FULLM, ly, off));
+                hx = pb_max(hx, __shfl_xor_sync(FULLM, hx, off)); hy = pb_max(hy, __shfl_xor_sync(FULLM, hy, off));
+            }
+            if (c.lane == 0) {
+                const float px = (hx - lx) * 0.1f, py = (hy - ly) * 0.1f;
+                reinterpret_cast<int*>(rec)[0] = s.ids[sl];
+                rec[1] = s.dscore[d];
+                rec[2] = lx - px; rec[3] = ly - py; rec[4] = hx + px; rec[5] = hy + py;
+            }
+        }
+    }
+
+    // ---------------- write back state ----------------
+    int cnt_local = 0;
+    for (int t = tid; t < T; t += NT) {
+        g_active[t] = s.active[t]; g_states[t] = s.states[t]; g_hits[t] = s.hits[t]; g_ids[t] = s.ids[t];
+        g_ages[t] = s.ages[t];
+        tb.row_assign[(size_t)b * T + t] = s.row[t];
+        cnt_local += (s.active[t] == 1);
+    }
+    for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
+    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
+    // block-wide sum of cnt_local (update()'s return value, :1130-1136)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt_local += __shfl_xor_sync(FULLM, cnt_local, off);
+    if (c.lane == 0 && cnt_local) atomicAdd(&s.misc[4], cnt_local);
+    __syncthreads();
+    if (tid == 0) {
+        g_scal[2] = D; g_scal[3] = s.misc[4];
+        tb.num_outputs[b] = n_out;
+        const unsigned long long now = globaltimer_ns();
+        g_ns[10] += now - t_begin;
+        g_ns[11] += 1;
+    }
+}
+
+__global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nT = (size_t)B * T, nD = (size_t)B * Dm;
+    if (i < nT * POSE_F) { tb.poses[i] = 0.f; tb.predicted[i] = 0.f; }
+    if (i < nT * 34) tb.vel[i] = 0.f;
+    if (i < nT * 4) tb.tcent[i] = 0.f;
+    if (i < nT * Dm) tb.cost[i] = 0.f;
+    if (i < nT) {
+        tb.scores[i] = 0.f; tb.states[i] = 0; tb.ids[i] = 0; tb.hits[i] = 0; tb.ages[i] = 0;
+        tb.last_frame[i] = 0; tb.active[i] = 0; tb.pred_dirty[i] = 0; tb.row_assign[i] = -1;
+    }
+    if (i < nD) { tb.det_scores[i] = 0.f; tb.col_assign[i] = -1; }
+    if (i < nD * 4) tb.dcent[i] = 0.f;
+    if (i < (size_t)B) {
+        tb.scalars[i * 4 + 0] = 1; tb.scalars[i * 4 + 1] = 0; tb.scalars[i * 4 + 2] = 0; tb.scalars[i * 4 + 3] = 0;
+        tb.num_outputs[i] = 0;
+    }
+    if (i < (size_t)B * 12) tb.stage_ns[i] = 0ull;
+}
+
+cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, cudaStream_t stream) {
+    size_t n = (size_t)B * T * (size_t)(Dm > POSE_F ? Dm : POSE_F);
+    if (n < (size_t)B * Dm * 4) n = (size_t)B * Dm * 4;
+    if (n < (size_t)B * 12) n = (size_t)B * 12;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    pb_tracker_reset_kernel<<<blocks, threads, 0, stream>>>(tb, B, T, Dm);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
+                           const TrackerPlan& plan, cudaStream_t stream) {
+    static size_t configured[3] = {0, 0, 0};
+    const int v = plan.threads == 256 ? 0 : (plan.threads == 512 ? 1 : 2);
+    if (plan.smem_bytes > configured[v]) {
+        cudaError_t e;
+        const int bytes = (int)plan.smem_bytes;
+        if (v == 0) e = cudaFuncSetAttribute(pb_tracker_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        else if (v == 1) e = cudaFuncSetAttribute(pb_tracker_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        else e = cudaFuncSetAttribute(pb_tracker_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        configured[v] = plan.smem_bytes;
+    }
+    p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
+    if (v == 0) pb_tracker_kernel<256><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
+    else if (v == 1) pb_tracker_kernel<512><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
+    else pb_tracker_kernel<1024><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace pb
