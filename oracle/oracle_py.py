@@ -68,6 +68,10 @@ def lib() -> C.CDLL:
         for f in (L.orc_kf3_initiate, L.orc_kf3_predict, L.orc_kf3_update, L.orc_kf3_extract,
                   L.orc_kf3_get_state, L.orc_kf3_get_diag):
             f.restype = None
+        L.orc_expf_array.argtypes = [vp, vp, ip]
+        L.orc_expf_array.restype = None
+        L.orc_nms_mask.argtypes = [vp, vp, ip, fp, vp]
+        L.orc_nms_mask.restype = None
         L.orc_run_streams.argtypes = [vp, ip, ip, ip, ip, fp, fp, ip, ip, C.POINTER(TrackerConfig), ip, vp, vp, vp]
         L.orc_run_streams.restype = C.c_double
         _lib = L
@@ -76,6 +80,21 @@ def lib() -> C.CDLL:
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def expf(x: np.ndarray) -> np.ndarray:
+    x = _f32(x).ravel()
+    y = np.empty_like(x)
+    lib().orc_expf_array(x.ctypes.data, y.ctypes.data, x.size)
+    return y
+
+
+def nms_mask(poses, bboxes, thr) -> np.ndarray:
+    poses = _f32(poses).reshape(-1, 51); bboxes = _f32(bboxes).reshape(-1, 4)
+    n = len(poses)
+    m = np.zeros((n, n), np.uint8)
+    lib().orc_nms_mask(poses.ctypes.data, bboxes.ctypes.data, n, thr, m.ctypes.data)
+    return m
 
 
 def decode(raw: np.ndarray, conf_thr: float, max_cand: int = 1024):

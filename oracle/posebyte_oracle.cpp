@@ -804,6 +804,18 @@ double now_s() {
 
 extern "C" {
 
+void orc_expf_array(const float* x, float* y, int n) {
+    for (int i = 0; i < n; ++i) y[i] = pb_expf(x[i]);
+}
+
+// Full symmetric NMS overlap matrix (the reference's kernelComputeNMSMask output, one byte
+// per bit) for tests that want to check the lazy sweep against the literal one.
+void orc_nms_mask(const float* poses, const float* bboxes, int C, float thr, unsigned char* mask) {
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j)
+            mask[(size_t)i * C + j] = (i != j && nms_overlap(poses, bboxes, i, j, thr, thr)) ? 1 : 0;
+}
+
 int orc_decode(const float* raw, int N, float thr, int max_cand, float* poses, float* bboxes,
                float* scores, int* anchors) {
     return decode(raw, N, thr, max_cand, poses, bboxes, scores, anchors);

@@ -33,6 +33,11 @@ typedef struct orc_tracker_config {
     int gating_enabled;      /* extension: 0 = all-ones spatial gate */
 } orc_tracker_config;
 
+/* pb_expf of include/pb_math.h over an array (accuracy tests). */
+void orc_expf_array(const float* x, float* y, int n);
+/* A2 literal: the full C x C overlap matrix, one byte per bit (gpu_postprocess.cu:88-172). */
+void orc_nms_mask(const float* poses, const float* bboxes, int C, float thr, unsigned char* mask);
+
 /* A1  gpu_postprocess.cu:30-81 (R1: ascending anchor order, first max_cand kept). */
 int orc_decode(const float* raw, int num_anchors, float conf_thr, int max_cand,
                float* poses, float* bboxes, float* scores, int* anchors);

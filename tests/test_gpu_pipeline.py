@@ -1,0 +1,81 @@
+"""Whole path at BASELINE config sizes: pb_step over many streams against the CPU checker's
+stream runner through size-independent properties (a checksum of every frame's kept anchors and
+TrackOutput records), shard invariance, and the host-buffer entry point."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_hashes(pb, torch, heads, **cfg):
+    F, B, _, N = heads.shape
+    pipe = pb.Pipeline(num_streams=B, num_anchors=N, **cfg)
+    h = [0] * B
+    pos = [0] * B
+    total = 0
+    for f in range(F):
+        pipe.step(torch.from_numpy(heads[f]).cuda(), f)
+        outs, counts = pipe.get_tracks_all()
+        for b in range(B):
+            k = pipe.get_kept(b)
+            words = np.concatenate([np.array([k["num_keep"], counts[b]], np.uint32), k["keep_anchors"].view(np.uint32),
+                                    np.frombuffer(outs[b, : counts[b]].tobytes(), np.uint32)])
+            h[b] = (h[b] + pb.words_checksum(words, pos[b])) % (1 << 64)
+            pos[b] += words.size
+            total += int(counts[b])
+    return np.array(h, np.uint64), total
+
+
+def test_config2_64_streams_checksum(pb, orc, cuda):
+    """Config 2 (64 concurrent 640x640 streams, 20 persons, max-age 10), 24 frames."""
+    cfg = pb.synth_config(canvas=640, persons=20, period=24)
+    heads = pb.synth_heads(cfg, 0, 64, 0, 24, frame_major=True)
+    got, total = gpu_hashes(pb, cuda, heads)
+    ref = orc.run_streams(heads, True, threads=8)
+    assert np.array_equal(got, ref["hashes"]) and total == ref["tracks_total"] > 10000
+
+
+def test_config4_max_age_30_with_occlusion_and_shard_invariance(pb, orc, cuda):
+    """Config 4 semantics (max-age 30, occlusion gaps) on one shard of 16 streams; a second handle
+    holding only streams 8..15 must reproduce their results (streams are independent)."""
+    cfg = pb.synth_config(canvas=640, persons=20, period=120, occlusion=1)
+    heads = pb.synth_heads(cfg, 0, 16, 0, 120, frame_major=True)
+    got, total = gpu_hashes(pb, cuda, heads, max_age=30)
+    ref = orc.run_streams(heads, True, threads=8, max_age=30)
+    assert np.array_equal(got, ref["hashes"]) and total == ref["tracks_total"]
+    shard, _ = gpu_hashes(pb, cuda, np.ascontiguousarray(heads[:, 8:]), max_age=30)
+    assert np.array_equal(shard, got[8:])
+
+
+def test_config3_crowd_checksum(pb, orc, cuda):
+    cfg = pb.synth_config(canvas=1280, persons=100, period=12, clumps=10, kp_drop_prob=0.15)
+    heads = pb.synth_heads(cfg, 0, 4, 0, 12, frame_major=True)
+    got, total = gpu_hashes(pb, cuda, heads, max_tracks=256, max_detections=128)
+    ref = orc.run_streams(heads, True, threads=4, max_tracks=256, max_detections=128)
+    assert np.array_equal(got, ref["hashes"]) and total == ref["tracks_total"] > 1000
+
+
+def test_step_host_equals_device_path(pb, orc, cuda):
+    torch = cuda
+    cfg = pb.synth_config(canvas=640, persons=10, period=16)
+    heads = pb.synth_heads(cfg, 0, 4, 0, 10, frame_major=True)
+    a, b = pb.Pipeline(num_streams=4), pb.Pipeline(num_streams=4)
+    for f in range(10):
+        out_h, cnt_h = a.step_host(heads[f], f)
+        b.step(torch.from_numpy(heads[f]).cuda(), f)
+        out_d, cnt_d = b.get_tracks_all()
+        assert np.array_equal(cnt_h, cnt_d)
+        for s in range(4):
+            assert out_h[s, : cnt_h[s]].tobytes() == out_d[s, : cnt_d[s]].tobytes()
+    assert cnt_h.sum() > 20
+
+
+def test_launch_counter_counts_real_kernels(pb, cuda):
+    torch = cuda
+    pipe = pb.Pipeline(num_streams=2)
+    heads = torch.zeros(2, 56, 8400, device="cuda")
+    before = pb.launch_count()
+    for f in range(5):
+        pipe.step(heads, f)
+    torch.cuda.synchronize()
+    assert pb.launch_count() - before == 10          # one decode+NMS and one tracker launch per step

@@ -1,0 +1,87 @@
+"""GPU decode + NMS (pb_postprocess, through the C ABI) against the CPU checker: bit-exact
+candidate counts, kept anchors / slots and kept poses, boxes, scores."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run_post(pb, torch, heads, conf=0.30, nms=0.65, **cfg):
+    B, _, N = heads.shape
+    pipe = pb.Pipeline(num_streams=B, num_anchors=N, **cfg)
+    d = torch.from_numpy(np.ascontiguousarray(heads)).cuda()
+    pipe.postprocess(d, conf, nms)
+    torch.cuda.synchronize()
+    return pipe, [pipe.get_kept(b) for b in range(B)]
+
+
+def assert_same(got, ref, tag=""):
+    assert got["num_cand"] == ref["num_cand"], tag
+    assert np.array_equal(got["keep_anchors"], ref["keep_anchors"]), tag
+    assert np.array_equal(got["keep_slots"], ref["keep_slots"]), tag
+    for k in ("poses", "bboxes", "scores"):
+        assert got[k].tobytes() == ref[k].tobytes(), (tag, k)
+
+
+@pytest.mark.parametrize("canvas,persons,clumps,B,frames", [(640, 20, 0, 8, 3), (1280, 100, 10, 4, 2), (640, 3, 0, 3, 1)])
+def test_postprocess_matches_checker(pb, orc, cuda, canvas, persons, clumps, B, frames):
+    cfg = pb.synth_config(canvas=canvas, persons=persons, period=16, clumps=clumps, kp_drop_prob=0.15 if clumps else 0.05)
+    heads = pb.synth_heads(cfg, 0, B, 0, frames, frame_major=True)
+    for f in range(frames):
+        _, got = run_post(pb, cuda, heads[f])
+        for b in range(B):
+            assert_same(got[b], orc.postprocess(heads[f, b]), f"f{f} b{b}")
+
+
+def test_empty_and_single(pb, orc, cuda):
+    heads = np.zeros((3, 56, 8400), np.float32)
+    heads[1, 4, 4242] = 0.9; heads[1, :4, 4242] = [100, 100, 40, 80]
+    heads[2, 4, 8399] = 0.31; heads[2, 4, 0] = 0.31                      # first and last anchor, equal score
+    _, got = run_post(pb, cuda, heads)
+    assert got[0]["num_keep"] == 0 and got[0]["num_cand"] == 0
+    for b in range(3):
+        assert_same(got[b], orc.postprocess(heads[b]), f"b{b}")
+    assert list(got[2]["keep_anchors"]) == [0, 8399]
+
+
+def test_candidate_overflow_and_keep_cap(pb, orc, cuda):
+    rng = np.random.default_rng(0)
+    heads = rng.uniform(0, 640, (2, 56, 8400)).astype(np.float32)
+    heads[0, 4] = rng.uniform(0.25, 0.35, 8400)                          # ~4000 above threshold -> first 1024
+    n = 700
+    heads[1, 4] = 0.0
+    idx = rng.choice(8400, n, replace=False)
+    heads[1, 4, idx] = rng.uniform(0.4, 0.9, n)
+    heads[1, 0, idx] = rng.uniform(0, 1e5, n); heads[1, 1, idx] = rng.uniform(0, 1e5, n)
+    heads[1, 2, idx] = 10; heads[1, 3, idx] = 10                         # disjoint boxes: nothing suppressed
+    _, got = run_post(pb, cuda, heads)
+    ref0, ref1 = orc.postprocess(heads[0]), orc.postprocess(heads[1])
+    assert got[0]["num_cand"] == 1024 and got[1]["num_keep"] == 256
+    assert_same(got[0], ref0, "overflow"); assert_same(got[1], ref1, "cap")
+
+
+def test_threshold_sweep_and_small_capacities(pb, orc, cuda):
+    cfg = pb.synth_config(canvas=640, persons=15, period=16)
+    heads = pb.synth_heads(cfg, 7, 2, 4, 1)[0]
+    for conf, nms in [(0.05, 0.65), (0.5, 0.3), (0.30, 0.95), (0.30, 0.05)]:
+        cap = 1024 if conf > 0.1 else 1024
+        _, got = run_post(pb, cuda, heads, conf, nms)
+        for b in range(2):
+            assert_same(got[b], orc.postprocess(heads[b], conf, nms), f"conf{conf} nms{nms} b{b}")
+    _, got = run_post(pb, cuda, heads, max_candidates=64, max_keep=8)
+    for b in range(2):
+        assert_same(got[b], orc.postprocess(heads[b], max_cand=64, max_keep=8), f"small b{b}")
+
+
+def test_unaligned_anchor_count(pb, orc, cuda):
+    """N not a multiple of 4: the scalar scan path."""
+    rng = np.random.default_rng(5)
+    N = 8403
+    heads = rng.uniform(0, 640, (2, 56, N)).astype(np.float32)
+    heads[:, 4] = rng.uniform(0, 0.2, (2, N))
+    hit = rng.choice(N, 90, replace=False)
+    heads[:, 4, hit] = rng.uniform(0.35, 0.9, (2, 90))
+    heads[0, 4, N - 1] = 0.8
+    _, got = run_post(pb, cuda, heads)
+    for b in range(2):
+        assert_same(got[b], orc.postprocess(heads[b]), f"b{b}")

@@ -1,0 +1,128 @@
+"""GPU tracker update (pb_tracker_update / pb_step through the C ABI) against the CPU checker:
+track ids, assignments, lifecycle state bit-exact; poses, velocities, costs bit-exact too
+(both sides evaluate the same IEEE operations, include/pb_math.h), which is stricter than the
+1e-4 relative tolerance the contract states for floating point."""
+import numpy as np
+import pytest
+
+from helpers import compare_state
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sequence(pb, orc, torch, B, F, canvas=640, persons=20, period=64, occlusion=0, clumps=0, T=128, Dm=64,
+                 max_age=10, min_hits=3, gating=1, stream0=0, check_state_every=1):
+    cfg = pb.synth_config(canvas=canvas, persons=persons, period=period, occlusion=occlusion, clumps=clumps,
+                          kp_drop_prob=0.15 if clumps else 0.05)
+    heads = pb.synth_heads(cfg, stream0, B, 0, F, frame_major=True)
+    pipe = pb.Pipeline(num_streams=B, num_anchors=cfg.num_anchors, max_tracks=T, max_detections=Dm, max_age=max_age,
+                       min_hits=min_hits, gating_enabled=gating)
+    trk = [orc.Tracker(max_tracks=T, max_detections=Dm, max_age=max_age, min_hits=min_hits, gating_enabled=gating)
+           for _ in range(B)]
+    d = torch.from_numpy(heads).cuda()
+    n_out = 0
+    for f in range(F):
+        pipe.step(d[f], f)
+        torch.cuda.synchronize()
+        na = pipe.get_num_active()
+        for b in range(B):
+            ref = orc.postprocess(heads[f, b])
+            ra = trk[b].update(ref["poses"], ref["scores"], f)
+            assert na[b] == ra, (f, b)
+            rt, gt = trk[b].get_tracks(), pipe.get_tracks(b)
+            assert gt.tobytes() == rt.tobytes(), (f, b, gt["track_id"], rt["track_id"])
+            n_out += len(gt)
+            if f % check_state_every == 0:
+                rs = trk[b].get_state()
+                bad = compare_state(pipe.get_state(b), rs, int(rs["scalars"][2]), T, f"f{f} b{b}")
+                assert not bad, bad
+    return n_out
+
+
+def test_config1_like_sequence(pb, orc, cuda):
+    assert run_sequence(pb, orc, cuda, B=3, F=48) > 1000
+
+
+def test_occlusion_lost_and_recovery(pb, orc, cuda):
+    assert run_sequence(pb, orc, cuda, B=4, F=90, period=90, occlusion=1, max_age=5) > 1000
+
+
+def test_dense_crowd_1280(pb, orc, cuda):
+    assert run_sequence(pb, orc, cuda, B=2, F=10, canvas=1280, persons=100, period=32, clumps=10, T=256, Dm=128) > 500
+
+
+def test_small_tables_force_truncation_and_slot_reuse(pb, orc, cuda):
+    assert run_sequence(pb, orc, cuda, B=2, F=40, persons=20, T=16, Dm=12, max_age=2, occlusion=1, period=40) > 50
+
+
+def test_min_hits_one_and_gating_off(pb, orc, cuda):
+    assert run_sequence(pb, orc, cuda, B=2, F=24, persons=10, min_hits=1, gating=0) > 100
+
+
+def test_direct_detections_with_empty_and_varying_frames(pb, orc, cuda):
+    """pb_tracker_update with caller-owned detection buffers (the GPUTracker::update signature),
+    including frames with zero detections and a changing detection count (cost stride re-aliasing)."""
+    torch = cuda
+    B, T, Dm, F = 3, 64, 32, 40
+    cfg = pb.synth_config(canvas=640, persons=24, period=40, occlusion=1)
+    pipe = pb.Pipeline(num_streams=B, max_tracks=T, max_detections=Dm, max_age=3)
+    trk = [orc.Tracker(max_tracks=T, max_detections=Dm, max_age=3) for _ in range(B)]
+    stride = 40
+    for f in range(F):
+        poses = np.zeros((B, stride, 51), np.float32); scores = np.zeros((B, stride), np.float32)
+        num = np.zeros(B, np.int32)
+        for b in range(B):
+            p, s = pb.synth_dets(cfg, b, f)
+            if f % 7 == 3 and b == 1:
+                p, s = p[:0], s[:0]                                   # empty frame
+            if f % 5 == 0:
+                p, s = p[: len(s) // 2], s[: len(s) // 2]
+            poses[b, : len(s)] = p; scores[b, : len(s)] = s; num[b] = len(s)
+        pipe.tracker_update(f, torch.from_numpy(poses).cuda(), torch.from_numpy(scores).cuda(),
+                            torch.from_numpy(num).cuda(), stride)
+        torch.cuda.synchronize()
+        for b in range(B):
+            trk[b].update(poses[b, : num[b]], scores[b, : num[b]], f)
+            rs = trk[b].get_state()
+            bad = compare_state(pipe.get_state(b), rs, int(rs["scalars"][2]), T, f"f{f} b{b}")
+            assert not bad, bad
+            assert pipe.get_tracks(b).tobytes() == trk[b].get_tracks().tobytes()
+
+
+def test_tracker_stress_tables_in_global_memory(pb, orc, cuda):
+    """Config 5 shape (512 x 512): the cost matrix does not fit in shared memory and is streamed
+    from L2; three frames so that tracks exist and all three tiers run."""
+    torch = cuda
+    T = Dm = 512
+    cfg = pb.synth_config(canvas=4096, persons=512, period=50)
+    pipe = pb.Pipeline(num_streams=1, max_tracks=T, max_detections=Dm)
+    trk = orc.Tracker(max_tracks=T, max_detections=Dm)
+    for f in range(4):
+        p, s = pb.synth_dets(cfg, 0, f)
+        n = np.array([len(s)], np.int32)
+        pipe.tracker_update(f, torch.from_numpy(p[None].copy()).cuda(), torch.from_numpy(s[None].copy()).cuda(),
+                            torch.from_numpy(n).cuda(), len(s))
+        torch.cuda.synchronize()
+        trk.update(p, s, f)
+        rs = trk.get_state()
+        bad = compare_state(pipe.get_state(0), rs, int(rs["scalars"][2]), T, f"f{f}")
+        assert not bad, bad
+    assert len(pipe.get_tracks(0)) > 300
+
+
+def test_reset_and_determinism(pb, orc, cuda):
+    torch = cuda
+    cfg = pb.synth_config(canvas=640, persons=12, period=16)
+    heads = pb.synth_heads(cfg, 0, 2, 0, 12, frame_major=True)
+    d = torch.from_numpy(heads).cuda()
+    pipe = pb.Pipeline(num_streams=2)
+    outs = []
+    for rep in range(2):
+        pipe.reset()
+        acc = []
+        for f in range(12):
+            pipe.step(d[f], f)
+            o, c = pipe.get_tracks_all()
+            acc.append(c.tobytes() + b"".join(o[b, : c[b]].tobytes() for b in range(2)))
+        outs.append(b"".join(acc))
+    assert outs[0] == outs[1]
