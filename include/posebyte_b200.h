@@ -142,6 +142,16 @@ int pb_get_device_views(pb_handle_t h, pb_device_views* out);
 int pb_get_timing(pb_handle_t h, pb_timing* out);
 /* Number of kernels this library has launched since process start (bench bookkeeping). */
 long long pb_launch_count(void);
+/* Per-kernel device timing for benchmarks: when enabled, every pb_postprocess /
+ * pb_tracker_update launch is bracketed by CUDA events on its stream.  pb_get_kernel_ms
+ * synchronises, returns the summed milliseconds and launch counts since the last call and
+ * clears the record.  Off by default (TrackerTiming's per-stage numbers come from in-kernel
+ * timestamps and are always on). */
+int pb_set_profiling(pb_handle_t h, int enabled);
+/* Mean microseconds per launch and stream of the decode+NMS kernel's stages since creation
+ * (in-kernel timestamps): scan+compaction, ranking, gather, suppression, output. */
+int pb_get_post_stage_us(pb_handle_t h, double* out5);
+int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_launches, double* track_ms, int* track_launches);
 
 /* ---- stage-level entry points ------------------------------------------------------ */
 

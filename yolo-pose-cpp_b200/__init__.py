@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
     "pb_postprocess", "pb_tracker_update", "pb_step", "pb_step_host", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
-    "pb_get_timing", "pb_launch_count", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
+    "pb_get_timing", "pb_launch_count", "pb_set_profiling", "pb_get_kernel_ms", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
 ]
 
@@ -105,6 +105,9 @@ def lib() -> C.CDLL:
         L.pb_get_state.argtypes = [vp, ip] + [vp] * 15
         L.pb_get_device_views.argtypes = [vp, C.POINTER(PbDeviceViews)]
         L.pb_get_timing.argtypes = [vp, C.POINTER(PbTiming)]
+        L.pb_get_post_stage_us.argtypes = [vp, C.POINTER(C.c_double * 5)]
+        L.pb_set_profiling.argtypes = [vp, ip]
+        L.pb_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip), C.POINTER(C.c_double), C.POINTER(ip)]
         L.launchPoseNMS.argtypes = [vp, vp, vp, vp, ip, ip, fp, fp, vp]
         L.pb_nms_legacy.argtypes = [vp, vp, ip, ip, fp, fp, vp, vp, vp]
         L.pb_auction_solve.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp]
@@ -237,6 +240,25 @@ class Pipeline:
         v = PbDeviceViews()
         check(lib().pb_get_device_views(self._h, C.byref(v)))
         return v
+
+    def post_stage_us(self) -> dict:
+        a = (C.c_double * 5)()
+        check(lib().pb_get_post_stage_us(self._h, C.byref(a)))
+        return dict(zip(("scan", "rank", "gather", "nms", "output"), [round(x, 2) for x in a]))
+
+    def tracker_stage_us(self) -> dict:
+        t = self.timing()
+        n = max(t.frame_count, 1)
+        return {k: round(getattr(t, k) / n, 2) for k, _ in t._fields_ if k != "frame_count"}
+
+    def set_profiling(self, on: bool):
+        check(lib().pb_set_profiling(self._h, int(on)))
+
+    def kernel_ms(self) -> dict:
+        """Summed per-kernel device milliseconds since the last call (needs set_profiling(True))."""
+        pm, tm, pn, tn = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
+        check(lib().pb_get_kernel_ms(self._h, C.byref(pm), C.byref(pn), C.byref(tm), C.byref(tn)))
+        return dict(post_ms=pm.value, post_launches=pn.value, track_ms=tm.value, track_launches=tn.value)
 
     def timing(self) -> PbTiming:
         t = PbTiming()

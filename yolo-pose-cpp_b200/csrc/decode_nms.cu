@@ -27,6 +27,8 @@ constexpr int DN_THREADS = 512;
 constexpr int DN_WARPS = DN_THREADS / 32;
 constexpr int DN_MAX_CHUNKS = 32;            // N <= 32 * 512 * 4 = 65536 anchors
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int DN_LIST = 2048;                // undecided pairs per round (>= 64*63/2)
+constexpr int DN_TERM_PAIRS = 128;           // pairs whose 17 terms are evaluated at once
 
 struct DnSmem {
     float* score;      // [Ccap] by slot
@@ -37,12 +39,18 @@ struct DnSmem {
     unsigned* vis;     // [Ccap] bit k: conf_k > 0.2
     float* box;        // [4][Ccap] cx,cy,w,h then x1,y1,x2,y2
     float* area;       // [Ccap]
+    float* ext;        // [4][Ccap] keypoint extents lx, hx, ly, hy over all 17 keypoints
     unsigned* sup;     // [Ccap/32]
     int* keep;         // [Kcap] kept ranks
     unsigned long long* tmask;  // [64]
     int* cnt;          // [DN_MAX_CHUNKS * DN_WARPS]
     int* tk;           // [64] ranks kept in the current tile
-    int* misc;         // [8]: 0 total, 1 nkeep, 2 ntk
+    int* misc;         // [8]: 0 total, 1 nkeep, 2 ntk, 3 list length
+    unsigned* list_key; // [DN_LIST] undecided pairs (rank_i << 16 | rank_j)
+    float* list_iou;    // [DN_LIST]
+    float* terms;       // [DN_TERM_PAIRS * 17] per-keypoint OKS terms of the pairs being resolved
+    float* sig;         // [17] COCO sigmas (shared copy: indexed per lane)
+    unsigned long long* acc;  // [16] stage telemetry accumulators
 };
 
 __host__ __device__ inline size_t dn_align(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -50,28 +58,38 @@ __host__ __device__ inline size_t dn_align(size_t x) { return (x + 15) & ~(size_
 __host__ __device__ inline size_t dn_carve(unsigned char* base, int Ccap, int Kcap, DnSmem* s) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = dn_align(off + bytes); return o; };
-    size_t o_tmask = take(64 * 8);
+    size_t o_tmask = take(64 * 8), o_acc = take(16 * 8);
     size_t o_score = take((size_t)Ccap * 4), o_anchor = take((size_t)Ccap * 4), o_order = take((size_t)Ccap * 4);
     size_t o_kx = take((size_t)KP * Ccap * 4), o_ky = take((size_t)KP * Ccap * 4);
     size_t o_vis = take((size_t)Ccap * 4), o_box = take((size_t)4 * Ccap * 4), o_area = take((size_t)Ccap * 4);
+    size_t o_ext = take((size_t)4 * Ccap * 4);
     size_t o_sup = take((size_t)((Ccap + 31) / 32) * 4 + 8), o_keep = take((size_t)Kcap * 4);
     size_t o_cnt = take((size_t)DN_MAX_CHUNKS * DN_WARPS * 4), o_tk = take(64 * 4), o_misc = take(8 * 4);
+    size_t o_lk = take((size_t)DN_LIST * 4), o_li = take((size_t)DN_LIST * 4);
+    size_t o_terms = take((size_t)DN_TERM_PAIRS * KP * 4), o_sig = take(KP * 4);
     if (s) {
         s->tmask = (unsigned long long*)(base + o_tmask);
+        s->acc = (unsigned long long*)(base + o_acc);
         s->score = (float*)(base + o_score); s->anchor = (int*)(base + o_anchor); s->order = (int*)(base + o_order);
         s->kx = (float*)(base + o_kx); s->ky = (float*)(base + o_ky);
         s->vis = (unsigned*)(base + o_vis); s->box = (float*)(base + o_box); s->area = (float*)(base + o_area);
+        s->ext = (float*)(base + o_ext);
         s->sup = (unsigned*)(base + o_sup); s->keep = (int*)(base + o_keep);
         s->cnt = (int*)(base + o_cnt); s->tk = (int*)(base + o_tk); s->misc = (int*)(base + o_misc);
+        s->list_key = (unsigned*)(base + o_lk); s->list_iou = (float*)(base + o_li);
+        s->terms = (float*)(base + o_terms); s->sig = (float*)(base + o_sig);
     }
     return off;
 }
 
 size_t decode_nms_smem_bytes(int max_cand, int max_keep) { return dn_carve(nullptr, max_cand, max_keep, nullptr); }
 
-// The reference's pair test (gpu_postprocess.cu:113-168) on shared-memory SoA data.
-// i, j are ranks.  Symmetric in (i, j) bit for bit.
-__device__ __forceinline__ bool nms_pair(const DnSmem& s, int Ccap, int i, int j, float thr) {
+// The reference's pair test (gpu_postprocess.cu:113-168) on shared-memory SoA data, split in
+// two so that the rare expensive part can be compacted and run with full lanes:
+//   nms_quick  -> 1 overlap (IoU alone decides), 0 no overlap (exact upper bounds decide),
+//                 2 undecided: the 17-exponential OKS has to be evaluated (nms_exact).
+// i, j are ranks.  Both functions are symmetric in (i, j) bit for bit.
+__device__ __forceinline__ int nms_quick(const DnSmem& s, int Ccap, int i, int j, float thr, float* iou_out) {
     const float xi1 = s.box[0 * Ccap + i], yi1 = s.box[1 * Ccap + i], xi2 = s.box[2 * Ccap + i], yi2 = s.box[3 * Ccap + i];
     const float xj1 = s.box[0 * Ccap + j], yj1 = s.box[1 * Ccap + j], xj2 = s.box[2 * Ccap + j], yj2 = s.box[3 * Ccap + j];
     const float ix1 = pb_max(xi1, xj1), iy1 = pb_max(yi1, yj1);
@@ -80,21 +98,31 @@ __device__ __forceinline__ bool nms_pair(const DnSmem& s, int Ccap, int i, int j
     const float inter = iw * ih;
     const float area_i = s.area[i], area_j = s.area[j];
     const float uni = area_i + area_j - inter;
-    const float iou = (uni > 0) ? (inter / uni) : 0.0f;
-    if (iou > thr) return true;
+    // inter == +0 gives iou == +0 whenever uni > 0 (and 0 otherwise): skip the division then.
+    const float iou = (uni > 0 && inter > 0.0f) ? (inter / uni) : 0.0f;
+    *iou_out = iou;
+    if (iou > thr) return 1;
 
     const unsigned vis = s.vis[i] & s.vis[j];
     const int cnt = __popc(vis);
-    if (cnt < 3) return false;
+    if (cnt < 3) return 0;
     float scale_sq = pb_max(area_i, area_j);
     if (scale_sq < 32.0f * 32.0f) scale_sq = 32.0f * 32.0f;
     const float t8 = 2.0f * scale_sq * 4.0f;
-
-    // Exact filter: a keypoint with d2 >= 3.003*den contributes exp(-d2/den) < 0.05, any
-    // other at most 1, so oks <= (m + 0.05*(cnt-m))/cnt.  If that bound is below the
-    // smallest threshold that could fire (minus a margin far above fp32 rounding), the
-    // reference's test is false without evaluating a single exponential.
     const float need = (iou > 0.2f) ? pb_min(thr, 0.4f) : thr;
+
+    // Bound 1.  If the keypoint extents of i and j are separated by more than
+    // r = sqrt(3.1 * t8 * sigma_max^2) along x or y, every keypoint pair has
+    // d2 > 3.003 * t8 * sigma_k^2, i.e. contributes < 0.05: oks < 0.05 <= need - 0.002.
+    if (need > 0.06f) {
+        const float r2 = 3.1f * t8 * (0.107f * 0.107f);
+        const float gx = pb_max(s.ext[0 * Ccap + i] - s.ext[1 * Ccap + j], s.ext[0 * Ccap + j] - s.ext[1 * Ccap + i]);
+        const float gy = pb_max(s.ext[2 * Ccap + i] - s.ext[3 * Ccap + j], s.ext[2 * Ccap + j] - s.ext[3 * Ccap + i]);
+        if ((gx > 0.0f && gx * gx > r2) || (gy > 0.0f && gy * gy > r2)) return 0;
+    }
+    // Bound 2.  A keypoint with d2 >= 3.003*den contributes exp(-d2/den) < 0.05, any other at
+    // most 1, so oks <= (m + 0.05*(cnt-m))/cnt.  If that is below the smallest threshold that
+    // could fire (minus a margin far above fp32 rounding) the reference's test is false.
     int m = 0;
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -106,20 +134,69 @@ __device__ __forceinline__ bool nms_pair(const DnSmem& s, int Ccap, int i, int j
             m += (d2 < 3.003f * (t8 * sg * sg)) ? 1 : 0;
         }
     }
-    if ((float)m + 0.05f * (float)(cnt - m) < (need - 0.002f) * (float)cnt) return false;
+    if ((float)m + 0.05f * (float)(cnt - m) < (need - 0.002f) * (float)cnt) return 0;
+    return 2;
+}
 
-    float sum = 0.0f;
-    for (int k = 0; k < KP; ++k) {
-        if (vis & (1u << k)) {
-            const float dx = s.kx[k * Ccap + i] - s.kx[k * Ccap + j];
-            const float dy = s.ky[k * Ccap + i] - s.ky[k * Ccap + j];
-            const float d2 = dx * dx + dy * dy;
-            const float sg = kSigmas[k];
-            sum += pb_expf(-d2 / (t8 * sg * sg));
+// The undecided pairs are resolved with the exponentials spread over threads: one thread per
+// (pair, keypoint) evaluates exp(-d2 / (2*scale*4*sigma^2)) (gpu_postprocess.cu:151-157), then one
+// thread per pair adds the 17 terms in keypoint order (the reference's summation order; a
+// keypoint that is not visible on both sides contributes an exact +0) and applies :162-167.
+// MODE 0: pairs inside the tile -> tile mask; MODE 1: survivor x later rank -> suppressed bitmap.
+template <int MODE>
+__device__ __forceinline__ void exact_phase(const DnSmem& s, int Ccap, int t0, float thr, int tid) {
+    const int nlist = s.misc[3];
+    for (int cbase = 0; cbase < nlist; cbase += DN_TERM_PAIRS) {
+        const int ncur = (nlist - cbase) < DN_TERM_PAIRS ? (nlist - cbase) : DN_TERM_PAIRS;
+        for (int idx = tid; idx < ncur * KP; idx += DN_THREADS) {
+            const int e = idx / KP, k = idx - e * KP;
+            const unsigned key = s.list_key[cbase + e];
+            const int i = (int)(key >> 16), j = (int)(key & 0xffffu);
+            float term = 0.0f;
+            if ((s.vis[i] & s.vis[j]) & (1u << k)) {
+                float scale_sq = pb_max(s.area[i], s.area[j]);
+                if (scale_sq < 32.0f * 32.0f) scale_sq = 32.0f * 32.0f;
+                const float t8 = 2.0f * scale_sq * 4.0f;
+                const float dx = s.kx[k * Ccap + i] - s.kx[k * Ccap + j];
+                const float dy = s.ky[k * Ccap + i] - s.ky[k * Ccap + j];
+                const float d2 = dx * dx + dy * dy;
+                const float sg = s.sig[k];
+                term = pb_expf(-d2 / (t8 * sg * sg));
+            }
+            s.terms[idx] = term;
         }
+        __syncthreads();
+        for (int e = tid; e < ncur; e += DN_THREADS) {
+            const unsigned key = s.list_key[cbase + e];
+            const int i = (int)(key >> 16), j = (int)(key & 0xffffu);
+            const int cnt = __popc(s.vis[i] & s.vis[j]);
+            float sum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) sum += s.terms[e * KP + k];
+            const float oks = sum / (float)cnt;
+            const float iou = s.list_iou[cbase + e];
+            if ((oks > thr) || (oks > 0.4f && iou > 0.2f)) {
+                if (MODE == 0) atomicOr(&s.tmask[i - t0], 1ull << (j - t0));
+                else atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+            }
+        }
+        __syncthreads();
     }
-    const float oks = sum / (float)cnt;
-    return (oks > thr) || (oks > 0.4f && iou > 0.2f);
+}
+
+// Warp-aggregated append of an undecided pair to the work list.
+__device__ __forceinline__ void list_push(const DnSmem& s, bool want, unsigned key, float iou) {
+    const unsigned bm = __ballot_sync(FULL, want);
+    if (bm == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(bm) - 1) base = atomicAdd(&s.misc[3], __popc(bm));
+    base = __shfl_sync(FULL, base, __ffs(bm) - 1);
+    if (want) {
+        const int pos = base + __popc(bm & ((1u << lane) - 1u));
+        s.list_key[pos] = key;
+        s.list_iou[pos] = iou;
+    }
 }
 
 __device__ __forceinline__ bool is_sup(const unsigned* sup, int r) { return (sup[r >> 5] >> (r & 31)) & 1u; }
@@ -135,16 +212,24 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* head = heads + (size_t)b * HEAD_ROWS * N;
     const float* conf_row = head + 4 * (size_t)N;
+    unsigned long long t_stamp = 0;
+    if (tid == 0) t_stamp = globaltimer_ns();
+    // stage telemetry: thread 0 accumulates globaltimer deltas in shared memory (cheap) and
+    // flushes them once at the end of the kernel
+    auto stamp = [&](int slot) {
+        if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
+    };
 
     // ---------------- 1. confidence scan + ordered compaction (A1, R1) ----------------
     const bool vec_ok = ((N & 3) == 0) && ((((uintptr_t)conf_row) & 15) == 0);
     const int ngroups = (N + 3) >> 2;
     const int chunks = (ngroups + DN_THREADS - 1) / DN_THREADS;
     unsigned m[4] = {0u, 0u, 0u, 0u};
-    for (int c0 = 0; c0 < chunks; c0 += 4) {
-        float4 v[4];
+    constexpr int SU = 8;                      // independent 128-bit loads in flight per thread
+    for (int c0 = 0; c0 < chunks; c0 += SU) {
+        float4 v[SU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SU; ++u) {
             const int g = (c0 + u) * DN_THREADS + tid;
             const float ninf = -__int_as_float(0x7f800000);
             v[u] = make_float4(ninf, ninf, ninf, ninf);
@@ -161,7 +246,7 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SU; ++u) {
             const int c = c0 + u;
             if (c < chunks) {
                 // keep iff !(conf < thr)  (gpu_postprocess.cu:51)
@@ -174,6 +259,8 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
         }
     }
     if (tid < 8) s.misc[tid] = 0;
+    if (tid < 16) s.acc[tid] = 0ull;
+    if (tid < KP) s.sig[tid] = kSigmas[tid];
     for (int i = tid; i < (Ccap + 31) / 32 + 2; i += DN_THREADS) s.sup[i] = 0u;
     for (int i = tid; i < Ccap; i += DN_THREADS) s.vis[i] = 0u;
     __syncthreads();
@@ -213,6 +300,7 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
     __syncthreads();
     const int total = s.misc[0];
     const int C = total < Ccap ? total : Ccap;
+    stamp(0);
 
     // ---------------- 2. rank by (score desc, slot asc)  (A3 sort, R2) ----------------
     for (int i = tid; i < C; i += DN_THREADS) {
@@ -225,15 +313,17 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
         s.order[rank] = i;
     }
     __syncthreads();
+    stamp(1);
 
     // ---------------- 3. gather the other head rows at the candidate anchors ----------
     {
         const int items = 55 * C;
-        for (int it0 = tid; it0 < items; it0 += DN_THREADS * 4) {
-            float v[4];
-            int rr[4], rw[4];
+        constexpr int GU = 8;                  // independent sector loads in flight per thread
+        for (int it0 = tid; it0 < items; it0 += DN_THREADS * GU) {
+            float v[GU];
+            int rr[GU], rw[GU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GU; ++u) {
                 const int it = it0 + u * DN_THREADS;
                 rr[u] = -1;
                 if (it < items) {
@@ -246,7 +336,7 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GU; ++u) {
                 if (rr[u] < 0) continue;
                 const int r = rr[u], row = rw[u];
                 if (row < 4) {
@@ -266,51 +356,99 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
         const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f, x2 = cx + w * 0.5f, y2 = cy + h * 0.5f;
         s.box[0 * Ccap + r] = x1; s.box[1 * Ccap + r] = y1; s.box[2 * Ccap + r] = x2; s.box[3 * Ccap + r] = y2;
         s.area[r] = (x2 - x1) * (y2 - y1);
+        float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
+#pragma unroll
+        for (int k = 1; k < KP; ++k) {
+            const float x = s.kx[k * Ccap + r], y = s.ky[k * Ccap + r];
+            lx = fminf(lx, x); hx = fmaxf(hx, x); ly = fminf(ly, y); hy = fmaxf(hy, y);
+        }
+        s.ext[0 * Ccap + r] = lx; s.ext[1 * Ccap + r] = hx; s.ext[2 * Ccap + r] = ly; s.ext[3 * Ccap + r] = hy;
     }
 
+    stamp(2);
     // ---------------- 4. greedy suppression in rank order (A2 + A3 sweep) --------------
     int nkeep = 0;
     for (int t0 = 0; t0 < C; t0 += 64) {
         const int tl = (C - t0) < 64 ? (C - t0) : 64;
         if (tid < 64) s.tmask[tid] = 0ull;
+        if (tid == 0) s.misc[3] = 0;
         __syncthreads();
+        // (a) pairs inside the tile: decide cheaply, queue the undecided ones
         for (int p = tid; p < 64 * 64; p += DN_THREADS) {
             const int a = p >> 6, bb = p & 63;
-            if (a < bb && bb < tl && !is_sup(s.sup, t0 + a) && !is_sup(s.sup, t0 + bb) &&
-                nms_pair(s, Ccap, t0 + a, t0 + bb, nms_thr))
-                atomicOr(&s.tmask[a], 1ull << bb);
+            int q = 0;
+            float iou = 0.0f;
+            if (a < bb && bb < tl && !is_sup(s.sup, t0 + a) && !is_sup(s.sup, t0 + bb))
+                q = nms_quick(s, Ccap, t0 + a, t0 + bb, nms_thr, &iou);
+            if (q == 1) atomicOr(&s.tmask[a], 1ull << bb);
+            list_push(s, q == 2, ((unsigned)(t0 + a) << 16) | (unsigned)(t0 + bb), iou);
         }
         __syncthreads();
-        if (tid == 0) {
+        stamp(8);
+        exact_phase<0>(s, Ccap, t0, nms_thr, tid);
+        stamp(9);
+        if (warp == 0) {
+            // serial greedy over the tile with the 64 mask rows held in registers (2 per lane)
+            const unsigned long long row_lo = s.tmask[lane], row_hi = s.tmask[lane + 32];
             unsigned long long supt = (unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32);
-            int ntk = 0, nk = s.misc[1];
+            unsigned long long kept = 0ull;
+            int nk = s.misc[1];
+            const int nk0 = nk;
             for (int a = 0; a < tl && nk < Kcap; ++a) {          // :224 "num_keep < 256"
+                const unsigned long long ra = __shfl_sync(FULL, a < 32 ? row_lo : row_hi, a & 31);
                 if ((supt >> a) & 1ull) continue;
-                s.keep[nk++] = t0 + a;
-                s.tk[ntk++] = t0 + a;
-                supt |= s.tmask[a];
+                kept |= 1ull << a;
+                ++nk;
+                supt |= ra;
             }
-            s.sup[t0 >> 5] = (unsigned)supt;
-            s.sup[(t0 >> 5) + 1] = (unsigned)(supt >> 32);
-            s.misc[1] = nk; s.misc[2] = ntk;
+            for (int half = 0; half < 2; ++half) {               // lanes write the kept ranks in order
+                const int a = half * 32 + lane;
+                if ((kept >> a) & 1ull) {
+                    const int pos = __popcll(kept & ((1ull << a) - 1ull));
+                    s.keep[nk0 + pos] = t0 + a;
+                    s.tk[pos] = t0 + a;
+                }
+            }
+            if (lane == 0) {
+                s.sup[t0 >> 5] = (unsigned)supt;
+                s.sup[(t0 >> 5) + 1] = (unsigned)(supt >> 32);
+                s.misc[1] = nk; s.misc[2] = nk - nk0; s.misc[3] = 0;
+            }
         }
         __syncthreads();
+        stamp(10);
         nkeep = s.misc[1];
         const int ntk = s.misc[2];
         if (nkeep >= Kcap) break;
+        // (c) the tile's survivors strike the remaining ranks, DN_LIST candidate pairs per round
         const int j0 = t0 + 64, rem = C - j0;
         if (rem > 0 && ntk > 0) {
             const int pairs = ntk * rem;
-            for (int p = tid; p < pairs; p += DN_THREADS) {
-                const int ai = p / rem;
-                const int j = j0 + (p - ai * rem);
-                if (!is_sup(s.sup, j) && nms_pair(s, Ccap, s.tk[ai], j, nms_thr))
-                    atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+            for (int pbase = 0; pbase < pairs; pbase += DN_LIST) {
+                const int pend = (pairs - pbase) < DN_LIST ? (pairs - pbase) : DN_LIST;
+                for (int p0 = 0; p0 < pend; p0 += DN_THREADS) {   // uniform trip count: list_push uses ballots
+                    const int p = pbase + p0 + tid;
+                    int q = 0, ai = 0, j = 0;
+                    float iou = 0.0f;
+                    if (p0 + tid < pend) {
+                        ai = p / rem;
+                        j = j0 + (p - ai * rem);
+                        if (!is_sup(s.sup, j)) q = nms_quick(s, Ccap, s.tk[ai], j, nms_thr, &iou);
+                    }
+                    if (q == 1) atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+                    list_push(s, q == 2, ((unsigned)s.tk[ai] << 16) | (unsigned)j, iou);
+                }
+                __syncthreads();
+                exact_phase<1>(s, Ccap, t0, nms_thr, tid);
+                if (tid == 0) s.misc[3] = 0;
+                __syncthreads();
             }
         }
+        stamp(11);
     }
     __syncthreads();
     nkeep = s.misc[1];
+    stamp(3);
 
     // ---------------- 5. kept detections in score order -------------------------------
     float* o_pose = out.det_poses + (size_t)b * Kcap * POSE_F;
@@ -338,7 +476,9 @@ pb_decode_nms_kernel(const float* __restrict__ heads, int N, int Ccap, int Kcap,
         o_slot[k] = slot;
         o_anchor[k] = s.anchor[slot];
     }
-    if (tid == 0) { out.num_keep[b] = nkeep; out.num_cand[b] = C; }
+    stamp(4);
+    if (tid == 0) { out.num_keep[b] = nkeep; out.num_cand[b] = C; s.acc[7] = 1ull; }
+    if (tid < 16 && s.acc[tid] != 0ull) out.stage_ns[(size_t)b * 16 + tid] += s.acc[tid];
 }
 
 cudaError_t launch_decode_nms(const float* d_heads, int B, int N, int max_cand, int max_keep,

@@ -7,8 +7,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "pb_common.cuh"
@@ -40,7 +42,21 @@ struct pb_handle_st {
     int* h_cnt_pinned = nullptr;   // [B]
     cudaStream_t own_stream = nullptr;
     int frames = 0;
+    // optional per-kernel event timing (pb_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_post, ev_track;   // indices into ev_pool (begin, end)
+    size_t ev_used = 0;
 };
+
+static int prof_event(pb_handle_st* h) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        h->ev_pool.push_back(e);
+    }
+    return (int)h->ev_used++;
+}
 
 #define PB_CUDA(call)                                                                         \
     do { cudaError_t e_ = (call);                                                             \
@@ -94,6 +110,7 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &h->post.keep_anchors, B * K));
     PB_TRY(dev_alloc(h, &h->post.num_keep, B));
     PB_TRY(dev_alloc(h, &h->post.num_cand, B));
+    PB_TRY(dev_alloc(h, &h->post.stage_ns, B * 16));
     TrackBuffers& t = h->trk;
     PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
     PB_TRY(dev_alloc(h, &t.vel, B * T * 34));
@@ -115,7 +132,7 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &t.scalars, B * 4));
     PB_TRY(dev_alloc(h, &t.num_outputs, B));
     PB_TRY(dev_alloc(h, &t.det_poses_scratch, B * Dm * POSE_F));
-    PB_TRY(dev_alloc(h, &t.stage_ns, B * 12));
+    PB_TRY(dev_alloc(h, &t.stage_ns, B * 20));
     unsigned char* outp = nullptr;
     PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
     t.outputs = outp;
@@ -150,6 +167,9 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
                      decode_nms_smem_bytes(c.max_candidates, c.max_keep), (size_t)prop.sharedMemPerBlockOptin);
         return PB_ERR_UNSUPPORTED;
     }
+    if (const char* g = getenv("PB_L2_FETCH")) {       // experiment: 32 / 64 / 128 byte L2 fetch granularity
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    }
     pb_handle_st* h = new (std::nothrow) pb_handle_st();
     if (!h) { pb_set_error("pb_create: out of host memory"); return PB_ERR_INVALID; }
     h->cfg = c;
@@ -167,6 +187,7 @@ int pb_destroy(pb_handle_t h) {
     if (h->h_out_pinned) cudaFreeHost(h->h_out_pinned);
     if (h->h_cnt_pinned) cudaFreeHost(h->h_cnt_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return PB_OK;
 }
@@ -181,8 +202,14 @@ int pb_reset(pb_handle_t h, pb_stream_t stream) {
 int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, pb_stream_t stream) {
     if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
     const pb_config& c = h->cfg;
+    int e0 = -1, e1 = -1;
+    if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_decode_nms(d_heads, c.num_streams, c.num_anchors, c.max_candidates, c.max_keep, conf, nms,
                               h->post, (cudaStream_t)stream));
+    if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
+        cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
+        h->ev_post.push_back({e0, e1});
+    }
     return PB_OK;
 }
 
@@ -204,7 +231,13 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
+    int e0 = -1, e1 = -1;
+    if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_tracker(h->trk, p, src, h->plan, (cudaStream_t)stream));
+    if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
+        cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
+        h->ev_track.push_back({e0, e1});
+    }
     h->frames++;
     return PB_OK;
 }
@@ -325,14 +358,55 @@ int pb_get_device_views(pb_handle_t h, pb_device_views* v) {
     return PB_OK;
 }
 
+int pb_get_post_stage_us(pb_handle_t h, double* out5) {
+    if (!h || !out5) { pb_set_error("pb_get_post_stage_us: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    const int B = h->cfg.num_streams;
+    std::vector<unsigned long long> ns((size_t)B * 16);
+    PB_CUDA(cudaMemcpy(ns.data(), h->post.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
+    double acc[16] = {0};
+    for (int b = 0; b < B; ++b) for (int i = 0; i < 16; ++i) acc[i] += (double)ns[(size_t)b * 16 + i];
+    if (getenv("PB_DEBUG_STAGES") && acc[7] > 0)
+        fprintf(stderr, "[pb] nms us/launch: intra-classify %.2f intra-exact %.2f resolve %.2f cross %.2f\n",
+                acc[8] / acc[7] / 1e3, acc[9] / acc[7] / 1e3, acc[10] / acc[7] / 1e3, acc[11] / acc[7] / 1e3);
+    for (int i = 0; i < 5; ++i) out5[i] = acc[7] > 0 ? acc[i] / acc[7] / 1e3 : 0.0;
+    return PB_OK;
+}
+
+int pb_set_profiling(pb_handle_t h, int enabled) {
+    if (!h) { pb_set_error("pb_set_profiling: null handle"); return PB_ERR_INVALID; }
+    h->profiling = enabled != 0;
+    return PB_OK;
+}
+
+int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_n, double* track_ms, int* track_n) {
+    if (!h) { pb_set_error("pb_get_kernel_ms: null handle"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    auto sum = [&](std::vector<std::pair<int, int>>& v, double* ms, int* n) {
+        double acc = 0;
+        for (auto& pr : v) { float t = 0; if (cudaEventElapsedTime(&t, h->ev_pool[pr.first], h->ev_pool[pr.second]) == cudaSuccess) acc += t; }
+        if (ms) *ms = acc;
+        if (n) *n = (int)v.size();
+        v.clear();
+    };
+    sum(h->ev_post, post_ms, post_n);
+    sum(h->ev_track, track_ms, track_n);
+    h->ev_used = 0;
+    return PB_OK;
+}
+
 int pb_get_timing(pb_handle_t h, pb_timing* out) {
     if (!h || !out) { pb_set_error("pb_get_timing: bad argument"); return PB_ERR_INVALID; }
     PB_CUDA(cudaDeviceSynchronize());
     const int B = h->cfg.num_streams;
-    std::vector<unsigned long long> ns((size_t)B * 12);
+    std::vector<unsigned long long> ns((size_t)B * 20);
     PB_CUDA(cudaMemcpy(ns.data(), h->trk.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
-    unsigned long long acc[12] = {0};
-    for (int b = 0; b < B; ++b) for (int i = 0; i < 12; ++i) acc[i] += ns[(size_t)b * 12 + i];
+    unsigned long long acc[20] = {0};
+    for (int b = 0; b < B; ++b) for (int i = 0; i < 20; ++i) acc[i] += ns[(size_t)b * 20 + i];
+    if (getenv("PB_DEBUG_STAGES"))
+        fprintf(stderr, "[pb] tier1 us/frame: cost %.2f auction %.2f lock %.2f | prologue %.2f\n",
+                acc[12] / 1e3 / B / (double)(acc[11] / B), acc[13] / 1e3 / B / (double)(acc[11] / B),
+                acc[14] / 1e3 / B / (double)(acc[11] / B), acc[0] / 1e3 / B / (double)(acc[11] / B));
     auto us = [&](int i) { return (long long)(acc[i] / 1000ull / (unsigned long long)B); };   // mean over streams
     out->predict_us = us(1); out->gate_us = us(2); out->high_assoc_us = us(3); out->low_assoc_us = us(4);
     out->lost_assoc_us = us(5); out->update_us = us(6); out->age_us = us(7); out->new_track_us = us(8);

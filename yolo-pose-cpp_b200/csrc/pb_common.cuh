@@ -27,6 +27,7 @@ struct PostBuffers {
     int* keep_anchors;   // [B, Kcap]  anchor index
     int* num_keep;       // [B]
     int* num_cand;       // [B]
+    unsigned long long* stage_ns;  // [B, 8] scan, rank, gather, nms, output (ns sums), [7] = launches
 };
 
 // ---- tracker state, struct-of-arrays over streams (all persistent across frames) ------

@@ -26,7 +26,7 @@ constexpr unsigned FULLM = 0xffffffffu;
 constexpr int DUP_CAP = 256;
 
 struct TkSmem {
-    int *active, *states, *hits, *ids, *ages, *row, *rowb, *act_list, *elig_list;   // [T]
+    int *active, *states, *hits, *ids, *ages, *row, *rowb, *act_list, *elig_list, *rowbc, *rowbid;   // [T]
     int *col, *colb, *slot_for_det, *out_list;                                        // [Dm]
     float *price, *dscore, *darea;                                                    // [Dm]
     unsigned long long* colbid;                                                       // [Dm]
@@ -36,6 +36,7 @@ struct TkSmem {
     unsigned* colmask;                                                                // [Dw]
     int* dup;                                                                         // [DUP_CAP]
     int* misc;                                                                        // [32]
+    unsigned long long* acc;                                                          // [20] telemetry
     float *cost, *det, *pred;                                                         // optional
 };
 
@@ -46,8 +47,8 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
     const int Dw = (Dm + 31) / 32;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = tk_align(off + bytes); return o; };
-    size_t o_colbid = take((size_t)Dm * 8);
-    size_t o_i[9]; for (int i = 0; i < 9; ++i) o_i[i] = take((size_t)T * 4);
+    size_t o_colbid = take((size_t)Dm * 8), o_acc = take(20 * 8);
+    size_t o_i[11]; for (int i = 0; i < 11; ++i) o_i[i] = take((size_t)T * 4);
     size_t o_d[4]; for (int i = 0; i < 4; ++i) o_d[i] = take((size_t)Dm * 4);
     size_t o_f[3]; for (int i = 0; i < 3; ++i) o_f[i] = take((size_t)Dm * 4);
     size_t o_tcent = take((size_t)T * 16), o_tarea = take((size_t)T * 4), o_tav = take((size_t)T * 4);
@@ -59,8 +60,10 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
     size_t o_pred = pred_s ? take((size_t)T * POSE_F * 4) : 0;
     if (s) {
         s->colbid = (unsigned long long*)(base + o_colbid);
-        int** ip[9] = {&s->active, &s->states, &s->hits, &s->ids, &s->ages, &s->row, &s->rowb, &s->act_list, &s->elig_list};
-        for (int i = 0; i < 9; ++i) *ip[i] = (int*)(base + o_i[i]);
+        s->acc = (unsigned long long*)(base + o_acc);
+        int** ip[11] = {&s->active, &s->states, &s->hits, &s->ids, &s->ages, &s->row, &s->rowb, &s->act_list, &s->elig_list,
+                        &s->rowbc, &s->rowbid};
+        for (int i = 0; i < 11; ++i) *ip[i] = (int*)(base + o_i[i]);
         int** dp[4] = {&s->col, &s->colb, &s->slot_for_det, &s->out_list};
         for (int i = 0; i < 4; ++i) *dp[i] = (int*)(base + o_d[i]);
         float** fp[3] = {&s->price, &s->dscore, &s->darea};
@@ -176,6 +179,7 @@ __device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
 struct Ctx {
     TkSmem s;
     int T, D, Dw, tid, nthreads, lane, warp, nwarps;
+    bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
     float* cost;        // shared or global, flat [t*D + d]
     const float* det;   // shared or global scratch [d*51]
     float* pred;        // shared or global (persistent) [t*51]
@@ -184,18 +188,30 @@ struct Ctx {
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
 __device__ __forceinline__ void auction_solve(Ctx& c) {
     TkSmem& s = c.s;
-    auction_solve_cta(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, s.colbid, &s.misc[8],
-                      c.tid, c.nthreads);
+    if (c.warp_auction && c.T <= 128 && c.D <= 32) {
+        auction_solve_regs<1>(c.cost, c.T, c.D, s.active, s.row, s.col, c.tid);
+    } else if (c.warp_auction && c.T <= 128 && c.D <= 64) {
+        auction_solve_regs<2>(c.cost, c.T, c.D, s.active, s.row, s.col, c.tid);
+    } else if (c.warp_auction) {
+        // colbid (8 B per column) doubles as the 32-bit bid array + the lowest-row array
+        unsigned* colbid32 = reinterpret_cast<unsigned*>(s.colbid);
+        int* colrow = reinterpret_cast<int*>(s.colbid) + c.D;
+        auction_solve_warp(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, colbid32, colrow, s.rowbc,
+                           reinterpret_cast<unsigned*>(s.rowbid), c.tid);
+    } else {
+        auction_solve_cta(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, s.colbid, &s.misc[8],
+                          c.tid, c.nthreads);
+    }
 }
 
 // kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.
 __device__ void lock_pairs(Ctx& c, unsigned* gate) {
     TkSmem& s = c.s;
     const int T = c.T, D = c.D, Dw = c.Dw;
-    for (int w = c.tid; w < Dw; w += c.nthreads) {
-        unsigned mk = 0u;
-        for (int bit = 0; bit < 32; ++bit) { const int d = w * 32 + bit; if (d < D && s.col[d] >= 0) mk |= 1u << bit; }
-        s.colmask[w] = mk;
+    for (int w = c.warp; w < Dw; w += c.nwarps) {
+        const int d = w * 32 + c.lane;
+        const unsigned mk = __ballot_sync(FULLM, d < D && s.col[d] >= 0);
+        if (c.lane == 0) s.colmask[w] = mk;
     }
     __syncthreads();
     for (int i = c.tid; i < T * D; i += c.nthreads) {
@@ -283,13 +299,15 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     int* g_last = tb.last_frame + (size_t)b * T; int* g_active = tb.active + (size_t)b * T;
     int* g_dirty = tb.pred_dirty + (size_t)b * T;
     int* g_scal = tb.scalars + (size_t)b * 4;
-    unsigned long long* g_ns = tb.stage_ns + (size_t)b * 12;
+    unsigned long long* g_ns = tb.stage_ns + (size_t)b * 20;
 
     unsigned long long t_stamp = 0;
     if (tid == 0) t_stamp = globaltimer_ns();
     const unsigned long long t_begin = t_stamp;
+    // stage telemetry (TrackerTiming): thread 0 accumulates globaltimer deltas in shared memory
+    // and flushes them once at the end of the kernel
     auto stamp = [&](int slot) {
-        if (tid == 0) { const unsigned long long now = globaltimer_ns(); g_ns[slot] += now - t_stamp; t_stamp = now; }
+        if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
     };
 
     // ---------------- prologue (:1065-1088) ----------------
@@ -312,9 +330,11 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
     c.det = det_w;
     c.cost = P.cost_in_smem ? s.cost : g_cost;
+    c.warp_auction = P.cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
     c.pred = P.pred_in_smem ? s.pred : g_pred;
     if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
     if (tid < 32) s.misc[tid] = 0;
+    if (tid < 20) s.acc[tid] = 0ull;
     __syncthreads();
     {   // active count + ordered active list (ascending t)
         for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
@@ -410,8 +430,11 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     // ---------------- tier 1 (:1210-1274) ----------------
     if (assoc12) {
         cost_pass<false>(c, s.gate, na);
+        stamp(12);
         auction_solve(c);
+        stamp(13);
         lock_pairs(c, s.gate);
+        stamp(14);
     }
     stamp(3);
     // ---------------- tier 2 (:1276-1335) ----------------
@@ -645,9 +668,11 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         g_scal[2] = D; g_scal[3] = s.misc[4];
         tb.num_outputs[b] = n_out;
         const unsigned long long now = globaltimer_ns();
-        g_ns[10] += now - t_begin;
-        g_ns[11] += 1;
+        s.acc[10] = now - t_begin;
+        s.acc[11] = 1ull;
     }
+    __syncthreads();
+    if (tid < 20 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
 }
 
 __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm) {
@@ -667,13 +692,13 @@ __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm) {
         tb.scalars[i * 4 + 0] = 1; tb.scalars[i * 4 + 1] = 0; tb.scalars[i * 4 + 2] = 0; tb.scalars[i * 4 + 3] = 0;
         tb.num_outputs[i] = 0;
     }
-    if (i < (size_t)B * 12) tb.stage_ns[i] = 0ull;
+    if (i < (size_t)B * 20) tb.stage_ns[i] = 0ull;
 }
 
 cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, cudaStream_t stream) {
     size_t n = (size_t)B * T * (size_t)(Dm > POSE_F ? Dm : POSE_F);
     if (n < (size_t)B * Dm * 4) n = (size_t)B * Dm * 4;
-    if (n < (size_t)B * 12) n = (size_t)B * 12;
+    if (n < (size_t)B * 20) n = (size_t)B * 20;
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     pb_tracker_reset_kernel<<<blocks, threads, 0, stream>>>(tb, B, T, Dm);
