@@ -78,4 +78,4 @@ def test_launch_counter_counts_real_kernels(pb, cuda):
     for f in range(5):
         pipe.step(heads, f)
     torch.cuda.synchronize()
-    assert pb.launch_count() - before == 10          # one decode+NMS and one tracker launch per step
+    assert pb.launch_count() - before == 15          # decode+gather, NMS and tracker: three launches per step

@@ -244,7 +244,7 @@ class Pipeline:
     def post_stage_us(self) -> dict:
         a = (C.c_double * 5)()
         check(lib().pb_get_post_stage_us(self._h, C.byref(a)))
-        return dict(zip(("scan", "rank", "gather", "nms", "output"), [round(x, 2) for x in a]))
+        return dict(zip(("list", "rank", "load", "nms", "output"), [round(x, 2) for x in a]))
 
     def tracker_stage_us(self) -> dict:
         t = self.timing()

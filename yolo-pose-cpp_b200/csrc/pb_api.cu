@@ -33,6 +33,8 @@ using namespace pb;
 struct pb_handle_st {
     pb_config cfg;
     PostBuffers post{};
+    CandScratch cand{};
+    DecodePlan dplan{};
     TrackBuffers trk{};
     TrackerPlan plan{};
     std::vector<void*> allocs;
@@ -111,6 +113,11 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &h->post.num_keep, B));
     PB_TRY(dev_alloc(h, &h->post.num_cand, B));
     PB_TRY(dev_alloc(h, &h->post.stage_ns, B * 16));
+    h->dplan = decode_plan(c.num_streams, c.num_anchors, c.max_candidates);
+    const size_t nsc = B * (size_t)h->dplan.nseg * (size_t)h->dplan.segcap;
+    PB_TRY(dev_alloc(h, &h->cand.records, nsc * HEAD_ROWS));
+    PB_TRY(dev_alloc(h, &h->cand.anchors, nsc));
+    PB_TRY(dev_alloc(h, &h->cand.counts, B * (size_t)h->dplan.nseg));
     TrackBuffers& t = h->trk;
     PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
     PB_TRY(dev_alloc(h, &t.vel, B * T * 34));
@@ -204,8 +211,8 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
     const pb_config& c = h->cfg;
     int e0 = -1, e1 = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
-    PB_CUDA(launch_decode_nms(d_heads, c.num_streams, c.num_anchors, c.max_candidates, c.max_keep, conf, nms,
-                              h->post, (cudaStream_t)stream));
+    PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->dplan, h->cand, (cudaStream_t)stream));
+    PB_CUDA(launch_nms(c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
         h->ev_post.push_back({e0, e1});
@@ -367,7 +374,7 @@ int pb_get_post_stage_us(pb_handle_t h, double* out5) {
     double acc[16] = {0};
     for (int b = 0; b < B; ++b) for (int i = 0; i < 16; ++i) acc[i] += (double)ns[(size_t)b * 16 + i];
     if (getenv("PB_DEBUG_STAGES") && acc[7] > 0)
-        fprintf(stderr, "[pb] nms us/launch: intra-classify %.2f intra-exact %.2f resolve %.2f cross %.2f\n",
+        fprintf(stderr, "[pb] nms us/launch: (unused) %.2f %.2f %.2f %.2f\n",
                 acc[8] / acc[7] / 1e3, acc[9] / acc[7] / 1e3, acc[10] / acc[7] / 1e3, acc[11] / acc[7] / 1e3);
     for (int i = 0; i < 5; ++i) out5[i] = acc[7] > 0 ? acc[i] / acc[7] / 1e3 : 0.0;
     return PB_OK;
@@ -403,6 +410,20 @@ int pb_get_timing(pb_handle_t h, pb_timing* out) {
     PB_CUDA(cudaMemcpy(ns.data(), h->trk.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
     unsigned long long acc[20] = {0};
     for (int b = 0; b < B; ++b) for (int i = 0; i < 20; ++i) acc[i] += ns[(size_t)b * 20 + i];
+    if (getenv("PB_DEBUG_STAGES")) {
+        const char* names[20] = {"prologue", "predict", "gate", "t1rest", "tier2", "tier3", "update", "age", "new", "dedup",
+                                 "total", "frames", "t1cost", "t1auction", "t1lock", "", "", "", "", ""};
+        for (int i = 0; i < 15; ++i) {
+            if (i == 11) continue;
+            double mn = 1e30, mx = 0, sm = 0;
+            for (int b = 0; b < B; ++b) {
+                const double f = (double)ns[(size_t)b * 20 + 11];
+                const double v = f > 0 ? ns[(size_t)b * 20 + i] / 1e3 / f : 0;
+                mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v;
+            }
+            fprintf(stderr, "[pb] %-10s us/frame over streams: min %7.2f mean %7.2f max %7.2f\n", names[i], mn, sm / B, mx);
+        }
+    }
     if (getenv("PB_DEBUG_STAGES"))
         fprintf(stderr, "[pb] tier1 us/frame: cost %.2f auction %.2f lock %.2f | prologue %.2f\n",
                 acc[12] / 1e3 / B / (double)(acc[11] / B), acc[13] / 1e3 / B / (double)(acc[11] / B),

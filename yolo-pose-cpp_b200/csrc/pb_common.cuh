@@ -27,8 +27,16 @@ struct PostBuffers {
     int* keep_anchors;   // [B, Kcap]  anchor index
     int* num_keep;       // [B]
     int* num_cand;       // [B]
-    unsigned long long* stage_ns;  // [B, 8] scan, rank, gather, nms, output (ns sums), [7] = launches
+    unsigned long long* stage_ns;  // [B, 16] list, rank, load, nms, output (ns sums), [7] = launches
 };
+
+// ---- candidate scratch between the decode+gather kernel and the NMS kernel (L2 resident) ----
+struct CandScratch {
+    float* records;      // [B, nseg, segcap, 56]  one contiguous head column per candidate
+    int* anchors;        // [B, nseg, segcap]
+    int* counts;         // [B, nseg]
+};
+struct DecodePlan { int nseg, groups_per_seg, segcap; };
 
 // ---- tracker state, struct-of-arrays over streams (all persistent across frames) ------
 struct TrackBuffers {
@@ -62,7 +70,7 @@ struct TrackParams {
     int max_age, min_hits, gating_enabled;
     int frame_id;
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
-    int cost_in_smem, det_in_smem, pred_in_smem;
+    int cost_in_smem, det_in_smem, pred_in_smem, term_floats;
 };
 
 struct DetSource {
@@ -95,11 +103,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // host-side launchers (defined in the .cu files, called from pb_api.cu)
 size_t decode_nms_smem_bytes(int max_cand, int max_keep);
-cudaError_t launch_decode_nms(const float* d_heads, int B, int N, int max_cand, int max_keep,
-                              float conf_thr, float nms_thr, const PostBuffers& out,
-                              cudaStream_t stream);
+DecodePlan decode_plan(int B, int N, int max_cand);
+cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, const DecodePlan& plan,
+                                 const CandScratch& cs, cudaStream_t stream);
+cudaError_t launch_nms(int B, int max_cand, int max_keep, float nms_thr, const DecodePlan& plan, const CandScratch& cs,
+                       const PostBuffers& out, cudaStream_t stream);
 
-struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem; };
+struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats; };
 TrackerPlan tracker_plan(int T, int Dm);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);

@@ -24,6 +24,7 @@ namespace pb {
 
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr int DUP_CAP = 256;
+constexpr int CELL_LIST_CAP = 4096;       // gated cells compacted per chunk of active rows
 
 struct TkSmem {
     int *active, *states, *hits, *ids, *ages, *row, *rowb, *act_list, *elig_list, *rowbc, *rowbid;   // [T]
@@ -37,13 +38,16 @@ struct TkSmem {
     int* dup;                                                                         // [DUP_CAP]
     int* misc;                                                                        // [32]
     unsigned long long* acc;                                                          // [20] telemetry
+    float* terms;                                                                     // [term_floats]
+    float* sig;                                                                       // [17]
+    int* cell_list;                                                                   // [CELL_LIST_CAP]
     float *cost, *det, *pred;                                                         // optional
 };
 
 __host__ __device__ inline size_t tk_align(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, int cost_s, int det_s,
-                                           int pred_s, TkSmem* s) {
+                                           int pred_s, int term_floats, TkSmem* s) {
     const int Dw = (Dm + 31) / 32;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = tk_align(off + bytes); return o; };
@@ -55,6 +59,7 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
     size_t o_dcent = take((size_t)Dm * 16);
     size_t o_gate = take((size_t)T * Dw * 4), o_lgate = take((size_t)T * Dw * 4), o_colmask = take((size_t)Dw * 4);
     size_t o_dup = take(DUP_CAP * 4), o_misc = take(32 * 4);
+    size_t o_terms = take((size_t)term_floats * 4), o_sig = take(KP * 4), o_cl = take(CELL_LIST_CAP * 4);
     size_t o_cost = cost_s ? take((size_t)T * Dm * 4) : 0;
     size_t o_det = det_s ? take((size_t)Dm * POSE_F * 4) : 0;
     size_t o_pred = pred_s ? take((size_t)T * POSE_F * 4) : 0;
@@ -73,6 +78,7 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
         s->gate = (unsigned*)(base + o_gate); s->lgate = (unsigned*)(base + o_lgate);
         s->colmask = (unsigned*)(base + o_colmask);
         s->dup = (int*)(base + o_dup); s->misc = (int*)(base + o_misc);
+        s->terms = (float*)(base + o_terms); s->sig = (float*)(base + o_sig); s->cell_list = (int*)(base + o_cl);
         s->cost = cost_s ? (float*)(base + o_cost) : nullptr;
         s->det = det_s ? (float*)(base + o_det) : nullptr;
         s->pred = pred_s ? (float*)(base + o_pred) : nullptr;
@@ -84,13 +90,17 @@ TrackerPlan tracker_plan(int T, int Dm) {
     TrackerPlan p{};
     const size_t budget = 200 * 1024;
     p.cost_in_smem = p.det_in_smem = p.pred_in_smem = 0;
-    size_t base = tk_carve(nullptr, T, Dm, 0, 0, 0, nullptr);
+    // term buffer: at least one active row (Dm * 17 floats), 32 KB when it fits
+    int term_floats = Dm * KP;
+    if (term_floats < 8192) term_floats = 8192;
+    p.term_floats = term_floats;
+    size_t base = tk_carve(nullptr, T, Dm, 0, 0, 0, term_floats, nullptr);
     size_t cost_b = tk_align((size_t)T * Dm * 4), det_b = tk_align((size_t)Dm * POSE_F * 4), pred_b = tk_align((size_t)T * POSE_F * 4);
     size_t used = base;
     if (used + cost_b <= budget) { p.cost_in_smem = 1; used += cost_b; }
     if (used + det_b <= budget) { p.det_in_smem = 1; used += det_b; }
     if (used + pred_b <= budget) { p.pred_in_smem = 1; used += pred_b; }
-    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, nullptr);
+    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, nullptr);
     const long cells = (long)T * Dm;
     p.threads = cells <= 16384 ? 256 : (cells <= 65536 ? 512 : 1024);
     return p;
@@ -180,6 +190,7 @@ struct Ctx {
     TkSmem s;
     int T, D, Dw, tid, nthreads, lane, warp, nwarps;
     bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
+    int term_floats;
     float* cost;        // shared or global, flat [t*D + d]
     const float* det;   // shared or global scratch [d*51]
     float* pred;        // shared or global (persistent) [t*51]
@@ -204,53 +215,124 @@ __device__ __forceinline__ void auction_solve(Ctx& c) {
     }
 }
 
-// kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.
-__device__ void lock_pairs(Ctx& c, unsigned* gate) {
+// kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.  Only rows that were active at
+// frame start are touched: the cells of inactive rows are never read by the auction (inactive
+// rows do not bid) and are overwritten with 1.0 by the last cost pass of the frame anyway.
+__device__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
     TkSmem& s = c.s;
-    const int T = c.T, D = c.D, Dw = c.Dw;
-    for (int w = c.warp; w < Dw; w += c.nwarps) {
-        const int d = w * 32 + c.lane;
-        const unsigned mk = __ballot_sync(FULLM, d < D && s.col[d] >= 0);
-        if (c.lane == 0) s.colmask[w] = mk;
-    }
-    __syncthreads();
-    for (int i = c.tid; i < T * D; i += c.nthreads) {
-        const int t = i / D, d = i - t * D;
-        if (s.row[t] >= 0 || s.col[d] >= 0) c.cost[i] = 1e9f;
-    }
-    for (int i = c.tid; i < T * Dw; i += c.nthreads) {
-        const int t = i / Dw, w = i - t * Dw;
-        gate[i] = (s.row[t] >= 0) ? 0u : (gate[i] & ~s.colmask[w]);
-    }
-    __syncthreads();
-}
-
-// cost <- 1.0 on inactive rows; cost <- f(cell) on gated cells of active rows (:351-358).
-template <bool TORSO>
-__device__ void cost_pass(Ctx& c, const unsigned* gate, int na) {
-    TkSmem& s = c.s;
-    const int T = c.T, D = c.D, Dw = c.Dw;
-    for (int i = c.tid; i < T * D; i += c.nthreads) {
-        const int t = i / D;
-        if (s.active[t] == 0) c.cost[i] = 1.0f;
-    }
-    for (int i = c.tid; i < na * D; i += c.nthreads) {
-        const int ai = i / D, d = i - ai * D;
+    const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
+    for (int ai = c.warp; ai < na; ai += c.nwarps) {
         const int t = s.act_list[ai];
-        if ((gate[t * Dw + (d >> 5)] >> (d & 31)) & 1u) {
-            const float* tp = c.pred + (size_t)t * POSE_F;
-            const float* dp = c.det + (size_t)d * POSE_F;
-            c.cost[(size_t)t * D + d] = TORSO ? torso_cost(tp, dp) : oks_cost(tp, dp, s.tarea[t], s.darea[d], 0.2f);
+        const bool rowm = s.row[t] >= 0;
+        for (int w = 0; w < words; ++w) {
+            const int d = w * 32 + c.lane;
+            const bool colm = (d < D) && (s.col[d] >= 0);
+            const unsigned bm = __ballot_sync(FULLM, colm);
+            if (d < D && (rowm || colm)) c.cost[(size_t)t * D + d] = 1e9f;
+            if (c.lane == 0) gate[t * Dw + w] = rowm ? 0u : (gate[t * Dw + w] & ~bm);
         }
     }
     __syncthreads();
 }
 
-__device__ void backup_assign(Ctx& c) {
+// cost <- 1.0 on inactive rows (:351-354): warp per row.  Only the last writer of a frame matters
+// for these rows (see lock_pairs), so this runs once per frame, in the lost-track tier.
+__device__ void cost_inactive_rows(Ctx& c) {
+    TkSmem& s = c.s;
+    for (int t = c.warp; t < c.T; t += c.nwarps)
+        if (s.active[t] == 0)
+            for (int d = c.lane; d < c.D; d += 32) c.cost[(size_t)t * c.D + d] = 1.0f;
+}
+
+// Visibility-masked OKS cost on the gated cells of the active rows (kernelOKSWithGating :360-424).
+// The gated cells are first compacted into a list (warp per row, ballot append); then the
+// exponentials are spread over threads: one thread per (cell, keypoint) evaluates a term into
+// shared memory and one thread per cell adds the terms of its visible keypoints in keypoint
+// order (the reference's summation order) and finishes the cell.
+__device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
+    TkSmem& s = c.s;
+    const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
+    int rows_per_chunk = CELL_LIST_CAP / D;            // worst case: every cell of the chunk is gated
+    if (rows_per_chunk < 1) rows_per_chunk = 1;
+    const int cells_per_round = c.term_floats / KP;
+    for (int a0 = 0; a0 < na; a0 += rows_per_chunk) {
+        const int a1 = (a0 + rows_per_chunk < na) ? a0 + rows_per_chunk : na;
+        if (c.tid == 0) s.misc[5] = 0;
+        __syncthreads();
+        for (int ai = a0 + c.warp; ai < a1; ai += c.nwarps) {
+            const int t = s.act_list[ai];
+            for (int w = 0; w < words; ++w) {
+                const int d = w * 32 + c.lane;
+                const unsigned gw = gate[t * Dw + w];
+                if (gw == 0u) continue;
+                const int n = __popc(gw);
+                int base = 0;
+                if (c.lane == 0) base = atomicAdd(&s.misc[5], n);
+                base = __shfl_sync(FULLM, base, 0);
+                if ((gw >> c.lane) & 1u) {
+                    const int pos = base + __popc(gw & ((1u << c.lane) - 1u));
+                    if (pos < CELL_LIST_CAP) s.cell_list[pos] = (t << 16) | d;
+                }
+            }
+        }
+        __syncthreads();
+        const int ncell = s.misc[5] < CELL_LIST_CAP ? s.misc[5] : CELL_LIST_CAP;
+        for (int cb = 0; cb < ncell; cb += cells_per_round) {
+            const int ncur = (ncell - cb) < cells_per_round ? (ncell - cb) : cells_per_round;
+            for (int idx = c.tid; idx < ncur * KP; idx += c.nthreads) {
+                const int e = idx / KP, k = idx - e * KP;
+                const int key = s.cell_list[cb + e];
+                const int t = key >> 16, d = key & 0xffff;
+                const float* tp = c.pred + (size_t)t * POSE_F + k * 3;
+                const float* dp = c.det + (size_t)d * POSE_F + k * 3;
+                float term = 0.0f;
+                if (dp[2] > vis && tp[2] > vis) {
+                    const float scale_sq = pb_max((s.darea[d] + s.tarea[t]) * 0.5f, 1000.0f);
+                    const float t2 = 2.0f * scale_sq;
+                    const float dx = dp[0] - tp[0], dy = dp[1] - tp[1];
+                    const float d2 = dx * dx + dy * dy;
+                    const float sg = s.sig[k] * 2.0f;
+                    const float s2 = sg * sg;
+                    term = pb_expf(-d2 / (t2 * s2));
+                }
+                s.terms[idx] = term;
+            }
+            __syncthreads();
+            for (int e = c.tid; e < ncur; e += c.nthreads) {
+                const int key = s.cell_list[cb + e];
+                const int t = key >> 16, d = key & 0xffff;
+                const float* tp = c.pred + (size_t)t * POSE_F;
+                const float* dp = c.det + (size_t)d * POSE_F;
+                float sum = 0.0f;
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (dp[k * 3 + 2] > vis && tp[k * 3 + 2] > vis) { sum += s.terms[e * KP + k]; ++cnt; }
+                const float oks = (cnt >= 3) ? (sum / (float)cnt) : 0.0f;
+                c.cost[(size_t)t * D + d] = 1.0f - oks;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Torso-only OKS (kernelTorsoOKS :455-489): four exponentials per cell, one thread per cell.
+__device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
+    TkSmem& s = c.s;
+    const int D = c.D, Dw = c.Dw;
+    for (int i = c.tid; i < na * D; i += c.nthreads) {
+        const int ai = i / D, d = i - ai * D;
+        const int t = s.act_list[ai];
+        if ((gate[t * Dw + (d >> 5)] >> (d & 31)) & 1u)
+            c.cost[(size_t)t * D + d] = torso_cost(c.pred + (size_t)t * POSE_F, c.det + (size_t)d * POSE_F);
+    }
+    __syncthreads();
+}
+
+__device__ void backup_assign(Ctx& c) {      // no barrier: callers synchronise before the next solve
     TkSmem& s = c.s;
     for (int t = c.tid; t < c.T; t += c.nthreads) s.rowb[t] = s.row[t];
     for (int d = c.tid; d < c.D; d += c.nthreads) s.colb[d] = s.col[d];
-    __syncthreads();
 }
 __device__ void merge_assign(Ctx& c) {   // kernelMergeAssignments :575-588
     TkSmem& s = c.s;
@@ -278,7 +360,8 @@ __global__ void __launch_bounds__(NTHREADS)
 pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx c;
-    tk_carve(smem_raw, P.T, P.Dm, P.cost_in_smem, P.det_in_smem, P.pred_in_smem, &c.s);
+    tk_carve(smem_raw, P.T, P.Dm, P.cost_in_smem, P.det_in_smem, P.pred_in_smem, P.term_floats, &c.s);
+    c.term_floats = P.term_floats;
     TkSmem& s = c.s;
     const int b = blockIdx.x;
     const int T = P.T, Dm = P.Dm;
@@ -335,6 +418,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
     if (tid < 32) s.misc[tid] = 0;
     if (tid < 20) s.acc[tid] = 0ull;
+    if (tid < KP) s.sig[tid] = kSigmas[tid];
     __syncthreads();
     {   // active count + ordered active list (ascending t)
         for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
@@ -429,28 +513,29 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
 
     // ---------------- tier 1 (:1210-1274) ----------------
     if (assoc12) {
-        cost_pass<false>(c, s.gate, na);
+        cost_pass_oks(c, s.gate, na, 0.2f);
         stamp(12);
         auction_solve(c);
         stamp(13);
-        lock_pairs(c, s.gate);
+        lock_pairs(c, s.gate, na);
         stamp(14);
     }
     stamp(3);
     // ---------------- tier 2 (:1276-1335) ----------------
     if (assoc12) {
         backup_assign(c);
-        cost_pass<true>(c, s.gate, na);
+        cost_pass_torso(c, s.gate, na);
         auction_solve(c);
         merge_assign(c);
-        lock_pairs(c, s.gate);
+        lock_pairs(c, s.gate, na);
     }
     stamp(4);
     // ---------------- tier 3 (:1337-1436) ----------------
     if (D > 0) {
         backup_assign(c);
-        lock_pairs(c, s.lgate);
-        cost_pass<false>(c, s.lgate, na);
+        cost_inactive_rows(c);
+        lock_pairs(c, s.lgate, na);
+        cost_pass_oks(c, s.lgate, na, 0.2f);
         auction_solve(c);
         merge_assign(c);
     }
@@ -720,6 +805,7 @@ cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSourc
         configured[v] = plan.smem_bytes;
     }
     p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
+    p.term_floats = plan.term_floats;
     if (v == 0) pb_tracker_kernel<256><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
     else if (v == 1) pb_tracker_kernel<512><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
     else pb_tracker_kernel<1024><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
