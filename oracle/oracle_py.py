@@ -53,6 +53,9 @@ def lib() -> C.CDLL:
         L.orc_tracker_destroy.restype = None
         L.orc_tracker_update.argtypes = [vp, vp, vp, ip, ip]
         L.orc_tracker_get_tracks.argtypes = [vp, vp, ip]
+        L.orc_tracker_force_new.argtypes = [vp, vp, vp, ip]
+        L.orc_tracker_force_new.restype = None
+        L.orc_tracker_forced_errors.argtypes = [vp]
         L.orc_tracker_get_state.argtypes = [vp] * 16
         L.orc_tracker_get_state.restype = None
         L.orc_kf3_create.argtypes = [ip]
@@ -160,6 +163,14 @@ class Tracker:
     def update(self, det_poses, det_scores, frame_id: int) -> int:
         p = _f32(det_poses).reshape(-1, 51); s = _f32(det_scores)
         return lib().orc_tracker_update(self._t, p.ctypes.data, s.ctypes.data, len(s), frame_id)
+
+    def force_new(self, slots, ids):
+        """Replay mode: slot / id per detection index for the tracks the next update creates."""
+        s = np.ascontiguousarray(slots, np.int32); i = np.ascontiguousarray(ids, np.int32)
+        lib().orc_tracker_force_new(self._t, s.ctypes.data, i.ctypes.data, len(s))
+
+    def forced_errors(self) -> int:
+        return lib().orc_tracker_forced_errors(self._t)
 
     def get_tracks(self) -> np.ndarray:
         out = np.zeros(self.Dm, dtype=TRACK_OUTPUT)

@@ -582,12 +582,24 @@ struct Tracker {
 
     // A15 kernelAllocateNewTrackSlots :695-724 + kernelInitNewTracks :727-780
     // R3: detections take slots in ascending detection order; R4: ids in the same order.
+    // Replay mode (orc_tracker_force_new): the slot and id each new detection receives are
+    // GIVEN — the outcome the reference's atomics produced in a recorded run — so that the rest
+    // of the restatement can be compared with that run although the race fell differently.
+    std::vector<int> forced_slot, forced_id;
+    int forced_errors = 0;
     void new_tracks() {
+        const bool forced = !forced_slot.empty();
         for (int d = 0; d < D; ++d) slot_for_det[d] = -1;
         for (int d = 0; d < D; ++d) {
             if (col[d] >= 0) continue;
             if (det_scores[d] < cfg.new_track_thresh) continue;
             int start = (hint++) % T;
+            if (forced) {
+                int s = d < (int)forced_slot.size() ? forced_slot[d] : -1;
+                if (s >= 0 && s < T && active[s] == 0) { active[s] = 1; slot_for_det[d] = s; }
+                else ++forced_errors;
+                continue;
+            }
             for (int i = 0; i < T; ++i) {
                 int s = (start + i) % T;
                 if (active[s] == 0) { active[s] = 1; slot_for_det[d] = s; break; }
@@ -598,7 +610,8 @@ struct Tracker {
             if (det_scores[d] < cfg.new_track_thresh) continue;
             int s = slot_for_det[d];
             if (s < 0) continue;
-            ids[s] = next_id++;
+            ids[s] = forced ? forced_id[d] : next_id;
+            ++next_id;
             scores[s] = det_scores[d];
             hits[s] = 1; ages[s] = 0; states[s] = ST_TENTATIVE; last_frame[s] = frame;
             col[d] = s;
@@ -687,6 +700,7 @@ struct Tracker {
         if (D > 0) update_matched();                               // :1438-1472
         age_unmatched();                                           // :1474-1487
         if (D > 0) new_tracks();                                   // :1489-1526
+        forced_slot.clear(); forced_id.clear();
         dedup();                                                   // :1528-1557
         num_active = count_active();
         return num_active;
@@ -864,6 +878,12 @@ void orc_tracker_destroy(void* t) { delete static_cast<Tracker*>(t); }
 int orc_tracker_update(void* t, const float* dp, const float* ds, int n, int frame) {
     return static_cast<Tracker*>(t)->update(dp, ds, n, frame);
 }
+void orc_tracker_force_new(void* tp, const int* slots, const int* ids, int n) {
+    Tracker* t = static_cast<Tracker*>(tp);
+    t->forced_slot.assign(slots, slots + n);
+    t->forced_id.assign(ids, ids + n);
+}
+int orc_tracker_forced_errors(void* tp) { return static_cast<Tracker*>(tp)->forced_errors; }
 int orc_tracker_get_tracks(void* t, void* out, int cap) {
     return static_cast<Tracker*>(t)->get_tracks(static_cast<TrackOutput*>(out), cap);
 }

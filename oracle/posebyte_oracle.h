@@ -69,6 +69,13 @@ void* orc_tracker_create(const orc_tracker_config* cfg);
 void orc_tracker_destroy(void* t);
 int orc_tracker_update(void* t, const float* det_poses, const float* det_scores,
                        int num_dets, int frame_id);
+/* Replay mode for pinning against a recorded run of the reference: for the NEXT update only,
+ * new tracks take slots[d] / ids[d] (d = detection index, n entries, slot -1 = none) instead
+ * of rules R3/R4 — i.e. the outcome of the reference's atomics race is supplied, everything
+ * else is computed.  orc_tracker_forced_errors counts detections whose supplied slot was
+ * missing or occupied. */
+void orc_tracker_force_new(void* t, const int* slots, const int* ids, int n);
+int orc_tracker_forced_errors(void* t);
 int orc_tracker_get_tracks(void* t, void* track_outputs /*TrackOutput[cap]*/, int cap);
 /* Raw state readback; any pointer may be NULL.  Sizes: poses T*51, vel T*34, scores T,
  * states/ids/hits/ages/last_frame/active T, row_assign T, col_assign Dmax,
