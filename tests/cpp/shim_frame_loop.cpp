@@ -1,0 +1,104 @@
+// tests/cpp/shim_frame_loop.cpp — the reference's frame loop (reference src/main.cpp:132-140,
+// 207-224) written against include/cuda/*.h, i.e. against the B200 library through its C ABI.
+// Reads heads [F,56,N] fp32 from a file, prints one line per frame:
+//   frame f: kept K active A tracks M : id:score_bits:nose_x_bits ...
+// tests/test_cpp_shims.py compares those lines with the CPU checker.  Also exercises NMSCuda,
+// LinearAssignmentCUDA and KalmanFilterCUDA once and prints their results.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "cuda/gpu_postprocess.h"
+#include "cuda/gpu_tracker.h"
+#include "cuda/hungarian.h"
+#include "cuda/kalman_filter.h"
+#include "cuda/nms.h"
+
+using namespace posebyte;
+using namespace posebyte::cuda;
+
+static unsigned bits(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+
+int main(int argc, char** argv) {
+    if (argc < 6) { std::fprintf(stderr, "usage: %s heads.bin frames anchors conf max_age\n", argv[0]); return 2; }
+    const int F = std::atoi(argv[2]), N = std::atoi(argv[3]);
+    const float conf = (float)std::atof(argv[4]);
+    const int max_age = std::atoi(argv[5]);
+    const float nms = 0.65f;
+    std::vector<float> heads((size_t)F * 56 * N);
+    FILE* fp = std::fopen(argv[1], "rb");
+    if (!fp || std::fread(heads.data(), sizeof(float), heads.size(), fp) != heads.size()) { std::fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+    std::fclose(fp);
+    float* d_heads = nullptr;
+    cudaMalloc(&d_heads, heads.size() * sizeof(float));
+    cudaMemcpy(d_heads, heads.data(), heads.size() * sizeof(float), cudaMemcpyHostToDevice);
+
+    try {
+        // main.cpp:132-140
+        GPUTrackerConfig cfg;
+        cfg.max_tracks = 128; cfg.max_detections = 64; cfg.match_threshold = 0.5f;
+        cfg.high_thresh = conf; cfg.low_thresh = conf * 0.5f; cfg.new_track_thresh = conf;
+        cfg.min_hits = 3; cfg.max_age = max_age;
+        GPUTracker tracker(cfg);
+        GPUPostprocess post(1024, N);
+        cudaStream_t stream;
+        cudaStreamCreate(&stream);
+        for (int f = 0; f < F; ++f) {
+            // main.cpp:207-224
+            const int n = post.process(d_heads + (size_t)f * 56 * N, conf, nms, stream);
+            const int active = tracker.update(post.getDetectionPoses(), post.getDetectionScores(), n, f);
+            std::vector<TrackOutput> tracks = tracker.getActiveTracks();
+            std::printf("frame %d: kept %d active %d tracks %zu :", f, n, active, tracks.size());
+            for (const TrackOutput& t : tracks) std::printf(" %d:%08x:%08x", t.track_id, bits(t.score), bits(t.keypoints[0].x));
+            std::printf("\n");
+        }
+        std::vector<TrackOutput> raw = post.getRawDetections(post.getNumDetectionsHost());
+        std::printf("raw %zu first_score %08x\n", raw.size(), raw.empty() ? 0u : bits(raw[0].score));
+
+        // NMSCuda::apply on the last frame's kept detections duplicated with a shift
+        std::vector<PoseDetection> dets;
+        for (size_t i = 0; i < raw.size(); ++i)
+            for (int dup = 0; dup < 2; ++dup) {
+                PoseDetection d{};
+                for (int e = 0; e < 4; ++e) d.bbox[e] = raw[i].bbox[e] + 2.0f * dup;
+                d.score = raw[i].score - 0.01f * dup;
+                for (int k = 0; k < NUM_KEYPOINTS; ++k) { d.keypoints[k] = raw[i].keypoints[k]; d.keypoints[k].x += 2.0f * dup; }
+                dets.push_back(d);
+            }
+        NMSCuda nmsobj(1024);
+        std::vector<int> keep = nmsobj.apply(dets.data(), (int)dets.size(), 0.65f, 0.25f);
+        std::printf("nms_apply %zu of %zu :", keep.size(), dets.size());
+        for (int k : keep) std::printf(" %d", k);
+        std::printf("\n");
+
+        // LinearAssignmentCUDA on a 3x3 problem with an obvious optimum
+        const float cost[9] = {0.1f, 0.9f, 0.8f, 0.7f, 0.2f, 0.9f, 0.9f, 0.8f, 0.3f};
+        float* d_cost; int *d_row, *d_col;
+        cudaMalloc(&d_cost, sizeof(cost)); cudaMalloc(&d_row, 12); cudaMalloc(&d_col, 12);
+        cudaMemcpy(d_cost, cost, sizeof(cost), cudaMemcpyHostToDevice);
+        LinearAssignmentCUDA la(8);
+        la.solveDeviceAsync(d_cost, 3, 3, d_row, d_col, 0.5f, stream);
+        la.sync(stream);
+        int row[3];
+        cudaMemcpy(row, d_row, 12, cudaMemcpyDeviceToHost);
+        std::printf("auction %d %d %d\n", row[0], row[1], row[2]);
+
+        // KalmanFilterCUDA: initiate, predict, read back
+        KalmanFilterCUDA kf(4);
+        PoseDetection p{};
+        for (int k = 0; k < NUM_KEYPOINTS; ++k) p.keypoints[k] = Keypoint{100.0f + k, 200.0f + 2 * k, 0.9f};
+        kf.initiate(2, p);
+        kf.predict(4);
+        PoseDetection q{};
+        kf.getPredictedPose(2, q);
+        float mean[TOTAL_STATE_DIM];
+        std::vector<float> cov((size_t)TOTAL_STATE_DIM * TOTAL_STATE_DIM);
+        kf.getState(2, mean, cov.data());
+        std::printf("kf3 nose %.3f %.3f conf %.1f var_x %.3f offdiag %.3f\n", q.keypoints[0].x, q.keypoints[0].y, q.keypoints[0].confidence, cov[0], cov[1]);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
