@@ -53,6 +53,8 @@ typedef struct pb_config {
     int use_cuda_graph;      /* kept for API parity, unused upstream (gpu_tracker.cu:1660) */
     int gating_enabled;      /* extension: 0 replaces the spatial gate by all-ones (config 5) */
     int device;              /* CUDA device ordinal */
+    int pipeline_depth;      /* 1: pb_step runs entirely on the caller's stream.  2..8: pb_step
+                              * overlaps consecutive steps on internal streams (see pb_join) */
 } pb_config;
 
 /* TrackerTiming (gpu_tracker.h:29-41), filled from device timestamps. */
@@ -91,6 +93,11 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
  * call (main.cpp:207-224).  Asynchronous; results stay on the device. */
 int pb_step(pb_handle_t h, const float* d_heads, float conf_threshold, float nms_threshold,
             int frame_id, pb_stream_t stream);
+
+/* With pipeline_depth > 1 pb_step returns with NMS and tracker work still running on internal
+ * streams.  pb_join makes `stream` wait for all of it (asynchronous, no host blocking); every
+ * pb_get_* function and the stage-level entry points join implicitly. */
+int pb_join(pb_handle_t h, pb_stream_t stream);
 
 /* Same with HOST buffers: h_heads [B,56,N] (pinned or pageable) is staged to the device,
  * the step runs, and the TrackOutput records are returned in h_tracks

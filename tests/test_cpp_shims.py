@@ -54,11 +54,21 @@ def test_reference_frame_loop_through_shims_equals_checker(pb, orc, cuda, tmp_pa
     assert total > 100
     rest = {ln.split()[0]: ln for ln in lines[F:]}
     assert rest["raw"].startswith(f"raw {k['num_keep']} first_score {k['scores'][0].view(np.uint32):08x}")
-    # NMSCuda::apply on duplicated detections: every shifted copy is suppressed by its original
+    # NMSCuda::apply on the last frame's detections, each duplicated with a 2 px shift (built
+    # exactly as the C++ side builds them), against the checker's host-NMS restatement
     n = k["num_keep"]
-    assert rest["nms_apply"].startswith(f"nms_apply {n} of {2 * n} :")
-    kept = [int(x) for x in rest["nms_apply"].split(":")[1].split()]
-    assert all(i % 2 == 0 for i in kept)
+    dets = np.zeros(2 * n, orc.POSE_DETECTION)
+    for i in range(n):
+        for dup in range(2):
+            d = dets[2 * i + dup]
+            d["bbox"] = k["bboxes"][i] + np.float32(2.0 * dup)
+            d["score"] = k["scores"][i] - np.float32(0.01) * np.float32(dup)
+            kp = k["poses"][i].reshape(17, 3).copy()
+            kp[:, 0] += np.float32(2.0 * dup)
+            d["keypoints"] = kp
+    want_keep = orc.nms_legacy(dets, 0.65, 0.25)
+    assert rest["nms_apply"].strip() == (f"nms_apply {len(want_keep)} of {2 * n} :" + "".join(f" {i}" for i in want_keep)).strip()
+    assert all(i % 2 == 0 for i in want_keep) and len(want_keep) >= n - 2      # every shifted copy loses to its original
     assert rest["auction"] == "auction 0 1 2"
     # KF3: initiate at (100, 200), one predict with zero velocity keeps the position; confidence 1.0;
     # variance 10 (conf > 0) + process noise 1; off-diagonal 0

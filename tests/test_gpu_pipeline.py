@@ -79,3 +79,41 @@ def test_launch_counter_counts_real_kernels(pb, cuda):
         pipe.step(heads, f)
     torch.cuda.synchronize()
     assert pb.launch_count() - before == 15          # decode+gather, NMS and tracker: three launches per step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [2, 3])
+def test_pipelined_steps_equal_serial_steps(pb, orc, cuda, depth):
+    """pipeline_depth > 1 overlaps consecutive steps on internal streams; every result must be
+    the one the serial path (and hence the checker) produces."""
+    torch = cuda
+    B, F = 8, 40
+    scfg = pb.synth_config(canvas=640, persons=14, period=64, occlusion=1)
+    host = pb.synth_heads(scfg, 100, B, 0, F, frame_major=True)
+    heads = torch.from_numpy(host).cuda()
+    serial = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=5)
+    piped = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=5, pipeline_depth=depth)
+    for f in range(F):                       # no synchronisation between steps: real overlap
+        serial.step(heads[f], f)
+        piped.step(heads[f], f)
+    piped.join()
+    torch.cuda.synchronize()
+    o1, c1 = serial.get_tracks_all(); o2, c2 = piped.get_tracks_all()
+    assert np.array_equal(c1, c2) and c1.sum() > 0
+    for b in range(B):
+        assert o1[b, :c1[b]].tobytes() == o2[b, :c2[b]].tobytes()
+        s1, s2 = serial.get_state(b), piped.get_state(b)
+        for k in s1:
+            assert s1[k].tobytes() == s2[k].tobytes(), (b, k)
+        k1, k2 = serial.get_kept(b), piped.get_kept(b)
+        assert np.array_equal(k1["keep_anchors"], k2["keep_anchors"])
+    # and with a read-back after every step against the checker
+    piped.reset()
+    trk = [orc.Tracker(max_age=5) for _ in range(2)]
+    for f in range(12):
+        piped.step(heads[f], f)
+        for b in range(2):
+            ref = orc.postprocess(host[f, b])
+            trk[b].update(ref["poses"], ref["scores"], f)
+            assert np.array_equal(piped.get_kept(b)["keep_anchors"], ref["keep_anchors"])
+            assert piped.get_tracks(b).tobytes() == trk[b].get_tracks().tobytes()

@@ -27,6 +27,17 @@ print(f"step (device heads):      {timed(lambda i: pipe.step(d[i % F], i)):8.1f}
 print(f"postprocess only:         {timed(lambda i: pipe.postprocess(d[i % F])):8.1f} us")
 print(f"tracker only (own dets):  {timed(lambda i: pipe.tracker_update(i)):8.1f} us")
 print("  tracker stages:", pipe.tracker_stage_us())
+for depth in (2, 3, 4):
+    pp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=depth)
+    def run(n, f0):
+        for i in range(f0, f0 + n): pp.step(d[i % F], i)
+        pp.join()
+    run(20, 0); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(200, 20); e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 200 * 1e3
+    print(f"pipelined step depth {depth}:   {us:8.1f} us  -> {B / us * 1e6:.0f} stream-frames/s")
+    del pp
 t0 = time.perf_counter()
 us = timed(lambda i: pipe.step(pinned[i % F].data_ptr(), i), n=50, warm=5)
 print(f"step (zero-copy pinned host heads, same kernels): {us:8.1f} us  -> {B / us * 1e6:.0f} stream-frames/s")

@@ -43,7 +43,8 @@ class PbConfig(C.Structure):
                 ("max_keep", C.c_int), ("max_tracks", C.c_int), ("max_detections", C.c_int),
                 ("match_threshold", C.c_float), ("high_thresh", C.c_float), ("low_thresh", C.c_float),
                 ("new_track_thresh", C.c_float), ("max_age", C.c_int), ("min_hits", C.c_int),
-                ("use_cuda_graph", C.c_int), ("gating_enabled", C.c_int), ("device", C.c_int)]
+                ("use_cuda_graph", C.c_int), ("gating_enabled", C.c_int), ("device", C.c_int),
+                ("pipeline_depth", C.c_int)]
 
 
 class PbTiming(C.Structure):
@@ -68,7 +69,7 @@ class SynthConfig(C.Structure):
 # Every symbol include/posebyte_b200.h declares (tests check the library exports them all).
 ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
-    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_step_host", "pb_get_tracks",
+    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
     "pb_get_timing", "pb_launch_count", "pb_set_profiling", "pb_get_kernel_ms", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
@@ -98,6 +99,7 @@ def lib() -> C.CDLL:
         L.pb_tracker_update.argtypes = [vp, vp, vp, vp, ip, ip, vp]
         L.pb_step.argtypes = [vp, vp, fp, fp, ip, vp]
         L.pb_step_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
+        L.pb_join.argtypes = [vp, vp]
         L.pb_get_tracks.argtypes = [vp, ip, vp, ip, C.POINTER(ip)]
         L.pb_get_tracks_all.argtypes = [vp, vp, vp]
         L.pb_get_num_active.argtypes = [vp, vp]
@@ -186,6 +188,10 @@ class Pipeline:
 
     def step(self, heads, frame_id, conf=0.30, nms=0.65, stream=None):
         check(lib().pb_step(self._h, _ptr(heads), conf, nms, frame_id, _stream_ptr(stream)))
+
+    def join(self, stream=None):
+        """Make `stream` wait for work a pipelined step left on the internal streams."""
+        check(lib().pb_join(self._h, _stream_ptr(stream)))
 
     def step_host(self, heads_np: np.ndarray, frame_id, conf=0.30, nms=0.65):
         out = np.zeros((self.B, self.Dm), dtype=TRACK_OUTPUT)

@@ -30,10 +30,23 @@ void pb_set_error(const char* fmt, ...) {
 
 using namespace pb;
 
-struct pb_handle_st {
-    pb_config cfg;
+// One slot of the step pipeline: candidate scratch (decode+gather -> NMS) and kept detections
+// (NMS -> tracker) with the events that order their reuse.
+struct PipeSlot {
     PostBuffers post{};
     CandScratch cand{};
+    cudaEvent_t ev_gather = nullptr, ev_nms = nullptr, ev_trk = nullptr;
+    bool used = false;
+};
+
+struct pb_handle_st {
+    pb_config cfg;
+    PostBuffers post{};            // == ring[cur].post (the slot of the most recent step)
+    CandScratch cand{};            // == ring[cur].cand
+    std::vector<PipeSlot> ring;    // cfg.pipeline_depth slots
+    int cur = 0;
+    bool inflight = false;         // work of a pipelined pb_step may still run on the internal streams
+    cudaStream_t s_nms = nullptr, s_trk = nullptr;
     DecodePlan dplan{};
     TrackBuffers trk{};
     TrackerPlan plan{};
@@ -100,24 +113,38 @@ void pb_default_config(pb_config* c) {
     c->use_cuda_graph = 0;
     c->gating_enabled = 1;
     c->device = 0;
+    c->pipeline_depth = 1;
 }
 
 static int build_handle(pb_handle_st* h) {
     const pb_config& c = h->cfg;
     const size_t B = c.num_streams, T = c.max_tracks, Dm = c.max_detections, K = c.max_keep;
-    PB_TRY(dev_alloc(h, &h->post.det_poses, B * K * POSE_F));
-    PB_TRY(dev_alloc(h, &h->post.det_bboxes, B * K * 4));
-    PB_TRY(dev_alloc(h, &h->post.det_scores, B * K));
-    PB_TRY(dev_alloc(h, &h->post.keep_slots, B * K));
-    PB_TRY(dev_alloc(h, &h->post.keep_anchors, B * K));
-    PB_TRY(dev_alloc(h, &h->post.num_keep, B));
-    PB_TRY(dev_alloc(h, &h->post.num_cand, B));
-    PB_TRY(dev_alloc(h, &h->post.stage_ns, B * 16));
     h->dplan = decode_plan(c.num_streams, c.num_anchors, c.max_candidates);
     const size_t nsc = B * (size_t)h->dplan.nseg * (size_t)h->dplan.segcap;
-    PB_TRY(dev_alloc(h, &h->cand.records, nsc * HEAD_ROWS));
-    PB_TRY(dev_alloc(h, &h->cand.anchors, nsc));
-    PB_TRY(dev_alloc(h, &h->cand.counts, B * (size_t)h->dplan.nseg));
+    unsigned long long* post_ns = nullptr;
+    PB_TRY(dev_alloc(h, &post_ns, B * 16));
+    h->ring.resize((size_t)c.pipeline_depth);
+    for (PipeSlot& sl : h->ring) {
+        PB_TRY(dev_alloc(h, &sl.post.det_poses, B * K * POSE_F));
+        PB_TRY(dev_alloc(h, &sl.post.det_bboxes, B * K * 4));
+        PB_TRY(dev_alloc(h, &sl.post.det_scores, B * K));
+        PB_TRY(dev_alloc(h, &sl.post.keep_slots, B * K));
+        PB_TRY(dev_alloc(h, &sl.post.keep_anchors, B * K));
+        PB_TRY(dev_alloc(h, &sl.post.num_keep, B));
+        PB_TRY(dev_alloc(h, &sl.post.num_cand, B));
+        sl.post.stage_ns = post_ns;
+        PB_TRY(dev_alloc(h, &sl.cand.records, nsc * HEAD_ROWS));
+        PB_TRY(dev_alloc(h, &sl.cand.anchors, nsc));
+        PB_TRY(dev_alloc(h, &sl.cand.counts, B * (size_t)h->dplan.nseg));
+        PB_CUDA(cudaEventCreateWithFlags(&sl.ev_gather, cudaEventDisableTiming));
+        PB_CUDA(cudaEventCreateWithFlags(&sl.ev_nms, cudaEventDisableTiming));
+        PB_CUDA(cudaEventCreateWithFlags(&sl.ev_trk, cudaEventDisableTiming));
+    }
+    h->cur = 0; h->post = h->ring[0].post; h->cand = h->ring[0].cand;
+    if (c.pipeline_depth > 1) {
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_nms, cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk, cudaStreamNonBlocking));
+    }
     TrackBuffers& t = h->trk;
     PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
     PB_TRY(dev_alloc(h, &t.vel, B * T * 34));
@@ -159,6 +186,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     if (c.num_anchors > 65536) { pb_set_error("pb_create: num_anchors > 65536 unsupported"); return PB_ERR_UNSUPPORTED; }
     if (c.max_tracks >= 65536 || c.max_detections >= 65536) { pb_set_error("pb_create: max_tracks/max_detections too large"); return PB_ERR_UNSUPPORTED; }
     if (c.max_keep > c.max_candidates) { pb_set_error("pb_create: max_keep > max_candidates"); return PB_ERR_INVALID; }
+    if (c.pipeline_depth < 1 || c.pipeline_depth > 8) { pb_set_error("pb_create: pipeline_depth must be 1..8"); return PB_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c.device) {
         (void)cudaGetLastError();
@@ -194,21 +222,44 @@ int pb_destroy(pb_handle_t h) {
     if (h->h_out_pinned) cudaFreeHost(h->h_out_pinned);
     if (h->h_cnt_pinned) cudaFreeHost(h->h_cnt_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->s_nms) cudaStreamDestroy(h->s_nms);
+    if (h->s_trk) cudaStreamDestroy(h->s_trk);
+    for (PipeSlot& sl : h->ring) {
+        if (sl.ev_gather) cudaEventDestroy(sl.ev_gather);
+        if (sl.ev_nms) cudaEventDestroy(sl.ev_nms);
+        if (sl.ev_trk) cudaEventDestroy(sl.ev_trk);
+    }
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return PB_OK;
 }
 
+// Make `stream` wait for everything a pipelined pb_step left running on the internal streams.
+static int join_on(pb_handle_st* h, cudaStream_t stream) {
+    if (!h->inflight) return PB_OK;
+    for (PipeSlot& sl : h->ring)
+        if (sl.used) { PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0)); PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_trk, 0)); }
+    h->inflight = false;
+    return PB_OK;
+}
+
 int pb_reset(pb_handle_t h, pb_stream_t stream) {
     if (!h) { pb_set_error("pb_reset: null handle"); return PB_ERR_INVALID; }
+    PB_TRY(join_on(h, (cudaStream_t)stream));
     PB_CUDA(launch_tracker_reset(h->trk, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, (cudaStream_t)stream));
     h->frames = 0;
     return PB_OK;
 }
 
+int pb_join(pb_handle_t h, pb_stream_t stream) {
+    if (!h) { pb_set_error("pb_join: null handle"); return PB_ERR_INVALID; }
+    return join_on(h, (cudaStream_t)stream);
+}
+
 int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, pb_stream_t stream) {
     if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
     const pb_config& c = h->cfg;
+    PB_TRY(join_on(h, (cudaStream_t)stream));
     int e0 = -1, e1 = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->dplan, h->cand, (cudaStream_t)stream));
@@ -220,10 +271,19 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
     return PB_OK;
 }
 
+static TrackParams track_params(const pb_config& c, int frame_id) {
+    TrackParams p{};
+    p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
+    p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
+    p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
+    return p;
+}
+
 int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_det_scores,
                       const int* d_num_dets, int det_stride, int frame_id, pb_stream_t stream) {
     if (!h) { pb_set_error("pb_tracker_update: null handle"); return PB_ERR_INVALID; }
     const pb_config& c = h->cfg;
+    PB_TRY(join_on(h, (cudaStream_t)stream));
     DetSource src;
     if (d_det_poses == nullptr && d_det_scores == nullptr && d_num_dets == nullptr) {
         src = {h->post.det_poses, h->post.det_scores, h->post.num_keep, c.max_keep};
@@ -234,10 +294,7 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
         }
         src = {d_det_poses, d_det_scores, d_num_dets, det_stride};
     }
-    TrackParams p{};
-    p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
-    p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
-    p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
+    TrackParams p = track_params(c, frame_id);
     int e0 = -1, e1 = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_tracker(h->trk, p, src, h->plan, (cudaStream_t)stream));
@@ -249,7 +306,37 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
     return PB_OK;
 }
 
+// Pipelined step (pipeline_depth > 1): the three kernels of one step run on three streams —
+// decode+gather on the caller's (it is the only reader of the borrowed head tensor), NMS and
+// tracker on internal ones — chained by events, with `depth` slots of candidate scratch and
+// kept-detection buffers.  Step i+1's decode+gather and NMS overlap step i's tracker; tracker
+// launches stay in frame order on one stream (each stream's state depends on its previous
+// frame).  Results are complete for the caller after pb_join or any pb_get_* call.
+static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, float nms, int frame_id, cudaStream_t stream) {
+    const pb_config& c = h->cfg;
+    const int pos = h->inflight || h->ring[h->cur].used ? (h->cur + 1) % (int)h->ring.size() : h->cur;
+    PipeSlot& sl = h->ring[pos];
+    if (sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));          // scratch still being read
+    PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->dplan, sl.cand, stream));
+    PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
+    PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_gather, 0));
+    if (sl.used) PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_trk, 0));        // kept detections still being read
+    PB_CUDA(launch_nms(c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, h->s_nms));
+    PB_CUDA(cudaEventRecord(sl.ev_nms, h->s_nms));
+    PB_CUDA(cudaStreamWaitEvent(h->s_trk, sl.ev_nms, 0));
+    DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
+    PB_CUDA(launch_tracker(h->trk, track_params(c, frame_id), src, h->plan, h->s_trk));
+    PB_CUDA(cudaEventRecord(sl.ev_trk, h->s_trk));
+    sl.used = true;
+    h->cur = pos; h->post = sl.post; h->cand = sl.cand;
+    h->inflight = true;
+    h->frames++;
+    return PB_OK;
+}
+
 int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int frame_id, pb_stream_t stream) {
+    if (!h || !d_heads) { pb_set_error("pb_step: null argument"); return PB_ERR_INVALID; }
+    if (h->cfg.pipeline_depth > 1 && !h->profiling) return step_pipelined(h, d_heads, conf, nms, frame_id, (cudaStream_t)stream);
     PB_TRY(pb_postprocess(h, d_heads, conf, nms, stream));
     return pb_tracker_update(h, nullptr, nullptr, nullptr, 0, frame_id, stream);
 }
@@ -266,6 +353,7 @@ int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int
     cudaStream_t s = h->own_stream;
     PB_CUDA(cudaMemcpyAsync(h->d_stage, h_heads, head_bytes, cudaMemcpyHostToDevice, s));
     PB_TRY(pb_step(h, h->d_stage, conf, nms, frame_id, (pb_stream_t)s));
+    PB_TRY(join_on(h, s));
     PB_CUDA(cudaMemcpyAsync(h->h_cnt_pinned, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost, s));
     PB_CUDA(cudaMemcpyAsync(h->h_out_pinned, h->trk.outputs, B * Dm * 228, cudaMemcpyDeviceToHost, s));
     PB_CUDA(cudaStreamSynchronize(s));
