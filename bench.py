@@ -51,6 +51,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """dram__bytes_read+write per launch from the latest committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); {} if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return {k: int(v) for k, v in json.load(f)["bytes_per_launch"].items()}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason samples during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -62,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -82,7 +92,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in self.rows[1:]:                 # the first sample predates the load
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -176,11 +186,12 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-per-gpu", type=int, default=STREAMS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--pipeline-depth", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -209,7 +220,8 @@ def main():
     scfg = pb.synth_config(canvas=CANVAS, persons=PERSONS, period=PERIOD)
     host_heads = pb.synth_heads(scfg, shard.start, B, 0, PERIOD, frame_major=True)       # [F,B,56,N]
     d_heads = torch.from_numpy(host_heads).to(dev)
-    pipe = pb.Pipeline(num_streams=B, num_anchors=N_ANCHORS, max_tracks=T, max_detections=DM, max_age=MAX_AGE, device=local)
+    kw = dict(num_streams=B, num_anchors=N_ANCHORS, max_tracks=T, max_detections=DM, max_age=MAX_AGE, device=local)
+    pipe = pb.Pipeline(pipeline_depth=args.pipeline_depth, **kw)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -218,49 +230,86 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (`value`) ----------------
+    # K steps issued back to back through pb_step; with pipeline_depth > 1 the library overlaps the
+    # decode+gather / NMS / tracker kernels of consecutive steps on internal streams, pb_join makes
+    # the timing stream wait for all of it before the closing event.
     f = 0
-    for _ in range(args.warmup):
-        pipe.step(d_heads[f % PERIOD], f, CONF, NMS); f += 1
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    pipe.set_profiling(True)
+    t_load0 = time.perf_counter()
+    for _ in range(args.warmup):
+        pipe.step(d_heads[f % PERIOD], f, CONF, NMS); f += 1
+    pipe.join()
+    barrier()
     launches0 = pb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
         pipe.step(d_heads[f % PERIOD], f, CONF, NMS); f += 1
+    pipe.join()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = pb.launch_count() - launches0
-    kms = pipe.kernel_ms()
-    pipe.set_profiling(False)
+    # nvidia-smi samples every 50 ms; a short timed region is followed by a continuation of the
+    # same loop so that the clock record covers at least ~0.6 s of this load
+    while rank == 0 and time.perf_counter() - t_load0 < 0.6:
+        for _ in range(50):
+            pipe.step(d_heads[f % PERIOD], f, CONF, NMS); f += 1
+        pipe.join(); torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + continuation of the same step loop to >= 0.6 s"
     outs, counts = pipe.get_tracks_all()
     n_out_mean = float(counts.mean())
 
+    # ---------------- per-kernel device time (roofline) and single-step latency ----------------
+    # serial path (one stream), every launch bracketed by CUDA events on the launching stream
+    pipe.set_profiling(True)
+    nprof = min(args.steps, 100)
+    for _ in range(nprof):
+        pipe.step(d_heads[f % PERIOD], f, CONF, NMS); f += 1
+    kus = pipe.kernel_us()
+    pipe.set_profiling(False)
+    lat = []
+    for _ in range(30):
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        pipe.step(d_heads[f % PERIOD], f, CONF, NMS); f += 1
+        pipe.join()
+        b_.record(stream)
+        torch.cuda.synchronize()
+        lat.append(a.elapsed_time(b_) * 1e3)
+    latency_us = float(np.median(lat))
+
     # ---------------- end to end through the host-buffer entry point (`e2e`) ----------------
-    pinned = torch.from_numpy(host_heads[: min(PERIOD, 8)]).pin_memory()
+    # page-locked host heads in (read in place over PCIe), TrackOutput records out (page-locked)
+    nf = min(PERIOD, 8)
+    pinned = torch.from_numpy(host_heads[:nf]).pin_memory()
     pinned_np = pinned.numpy()
-    nf = pinned_np.shape[0]
+    out_p = torch.zeros(B * DM * 228, dtype=torch.uint8).pin_memory()
+    cnt_p = torch.zeros(B, dtype=torch.int32).pin_memory()
+    out_np = out_p.numpy().view(pb.TRACK_OUTPUT).reshape(B, DM)
+    cnt_np = cnt_p.numpy()
     for i in range(3):
-        pipe.step_host(pinned_np[i % nf], f, CONF, NMS); f += 1
+        pipe.step_host(pinned_np[i % nf], f, CONF, NMS, out=out_np, counts=cnt_np); f += 1
     barrier()
     t0 = time.perf_counter()
     e2e_tracks = 0
     for i in range(args.e2e_steps):
-        o, c = pipe.step_host(pinned_np[i % nf], f, CONF, NMS); f += 1
-        e2e_tracks += int(c.sum())
+        pipe.step_host(pinned_np[i % nf], f, CONF, NMS, out=out_np, counts=cnt_np); f += 1
+        e2e_tracks += int(cnt_np.sum())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    cand_mean = float(np.mean([pipe.get_kept(b)["num_cand"] for b in range(min(B, 8))]))
 
     # ---------------- max over ranks + final statistics gather (the only collective) ----------------
-    stats = torch.tensor([ms_total, e2e_s, float(launches), float(counts.sum()), kms["post_ms"], kms["track_ms"], float(e2e_tracks)],
-                         dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_total, e2e_s, float(launches), float(counts.sum()), kus["gather_us"], kus["nms_us"], kus["track_us"],
+                          float(e2e_tracks), latency_us], dtype=torch.float64, device=dev)
     if world > 1:
         gathered = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(gathered, stats)
@@ -275,37 +324,51 @@ def main():
     total_streams = B * world
     value = total_streams * args.steps / (ms_max / 1e3)
     e2e_value = total_streams * args.e2e_steps / e2e_max
-    post_ms = float(allstats[:, 4].max()) / max(kms["post_launches"], 1)
-    track_ms = float(allstats[:, 5].max()) / max(kms["track_launches"], 1)
+    gather_us, nms_us, track_us = (float(allstats[:, i].max()) for i in (4, 5, 6))
 
     peak, peak_src = measured_peak_gbs()
-    def roof(name, bytes_per_launch, ms, note):
-        ach = bytes_per_launch / (ms / 1e3) / 1e9 if ms > 0 else 0.0
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "avg_launch_us": ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "note": note}
-    r_post = roof("pb_decode_nms_kernel", B * BYTES_HEAD, post_ms,
-                  "dense-read model 224*N B per stream-frame; the kernel reads the confidence row and 32 B sectors at candidate anchors only "
-                  "(effective bandwidth; see profiles/ for dram__bytes)")
-    r_track = roof("pb_tracker_kernel", B * (BYTES_TRACK + BYTES_OUT), track_ms,
-                   "latency/issue-bound stage (auction iterations); HBM is not its limit")
-    dominant = r_post if post_ms >= track_ms else r_track
+    traffic = ncu_traffic()
+    def roof(name, bytes_per_launch, us, note):
+        ach = bytes_per_launch / (us / 1e6) / 1e9 if us > 0 else 0.0
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(name), "avg_launch_us": us, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "peak_source": peak_src, "note": note}
+    r_gather = roof("pb_decode_gather_kernel", B * BYTES_HEAD, gather_us,
+                    "dense-read model 224*N B per stream-frame (SURVEY.md 8d); the kernel reads the confidence row and 32 B sectors at "
+                    "candidate anchors only, so this is an EFFECTIVE bandwidth; `traffic` is ncu dram bytes per launch")
+    r_nms = roof("pb_nms_kernel", B * int(cand_mean) * 224, nms_us,
+                 "candidate records (224 B each) read once; latency/issue-bound, working set in shared memory")
+    r_track = roof("pb_tracker_kernel", B * (BYTES_TRACK + BYTES_OUT), track_us,
+                   "track state read+written once + TrackOutput records; latency-bound (up to 150 dependent auction iterations per "
+                   "stream-frame), HBM is not its limit")
+    kernels = [r_gather, r_nms, r_track]
+    dominant = max(kernels, key=lambda r: r["avg_launch_us"])
     step_ach = total_streams * BYTES_PER_STREAM_FRAME * args.steps / (ms_max / 1e3) / 1e9 / world
     line = {
         "metric": "tracked stream-frames/sec", "value": value, "unit": "stream-frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "us_per_batch": ms_max / args.steps * 1e3,
+        "us_per_batch_latency": float(allstats[:, 8].max()),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "total_streams": total_streams, "parallelism": f"stream-sharded x{world}, no data-path collective",
                    "l2": f"{PERIOD} distinct head batches rotate ({PERIOD * B * 56 * N_ANCHORS * 4 / 1e9:.2f} GB per GPU > 126 MB L2)",
-                   "conf": CONF, "nms": NMS, "max_tracks": T, "max_detections": DM, "max_age": MAX_AGE},
+                   "conf": CONF, "nms": NMS, "max_tracks": T, "max_detections": DM, "max_age": MAX_AGE,
+                   "pipeline_depth": args.pipeline_depth,
+                   "timing": "value: K pb_step calls back to back + pb_join between CUDA events (steps overlap on internal streams); "
+                             "us_per_batch_latency: median of single isolated steps; roofline: per-launch CUDA events on the serial path"},
         "roofline": dominant,
-        "roofline_kernels": [r_post, r_track],
+        "roofline_kernels": kernels,
         "roofline_step": {"bound": "hbm", "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
-                          "bytes_per_stream_frame": BYTES_PER_STREAM_FRAME, "note": "whole step per GPU, SURVEY.md 8(d) figure"},
-        "e2e": {"value": e2e_value, "unit": "stream-frames/s", "h2d_bytes_per_step": B * 56 * N_ANCHORS * 4,
-                "d2h_bytes_per_step": B * DM * 228 + B * 4, "steps": args.e2e_steps, "api": "pb_step_host (pinned host heads in, TrackOutput records out)"},
+                          "bytes_per_stream_frame": BYTES_PER_STREAM_FRAME, "note": "whole step per GPU, SURVEY.md 8(d) dense-read figure"},
+        "e2e": {"value": e2e_value, "unit": "stream-frames/s",
+                "h2d_bytes_per_step": int(B * (4 * N_ANCHORS + 55 * 32 * cand_mean)),
+                "host_input_bytes_per_step": B * 56 * N_ANCHORS * 4,
+                "d2h_bytes_per_step": B * DM * 228 + B * 4, "steps": args.e2e_steps,
+                "api": "pb_step_host: page-locked host heads [B,56,N] read in place by the decode kernel over PCIe (confidence rows + 32 B sectors at "
+                       "candidate anchors = h2d_bytes_per_step; the buffer itself is host_input_bytes_per_step), TrackOutput records copied back"},
         "gpu_launches": int(allstats[0, 2]),
         "clocks": clocks,
         "tracks_per_stream_frame": n_out_mean,
+        "candidates_per_stream_frame": cand_mean,
     }
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(pb)

@@ -99,9 +99,11 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf_threshold, float nms
  * pb_get_* function and the stage-level entry points join implicitly. */
 int pb_join(pb_handle_t h, pb_stream_t stream);
 
-/* Same with HOST buffers: h_heads [B,56,N] (pinned or pageable) is staged to the device,
- * the step runs, and the TrackOutput records are returned in h_tracks
- * [B, max_detections] (228-byte records) with h_counts [B].  Synchronous. */
+/* Same with HOST buffers: h_heads [B,56,N]; the TrackOutput records are returned in h_tracks
+ * [B, max_detections] (228-byte records) with h_counts [B].  Synchronous.  Page-locked input
+ * (cudaHostAlloc / cudaHostRegister) is read in place over PCIe by the decode kernel — only the
+ * confidence rows and the sectors at candidate anchors cross the bus; pageable input is staged
+ * with one full copy.  Page-locked output buffers receive the device-to-host copies directly. */
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf_threshold,
                  float nms_threshold, int frame_id, void* h_tracks, int* h_counts);
 
@@ -147,6 +149,10 @@ typedef struct pb_device_views {
 } pb_device_views;
 int pb_get_device_views(pb_handle_t h, pb_device_views* out);
 int pb_get_timing(pb_handle_t h, pb_timing* out);
+/* Raw per-stream accumulators behind pb_get_timing: out [B,20] nanosecond sums since creation:
+ * 0 prologue, 1 predict, 2 gate, 3 tier-1 rest, 4 tier 2, 5 tier 3, 6 update, 7 age, 8 new,
+ * 9 dedup, 10 total, 11 frame count, 12 tier-1 cost, 13 tier-1 auction, 14 tier-1 lock. */
+int pb_get_stream_stage_ns(pb_handle_t h, unsigned long long* out);
 /* Number of kernels this library has launched since process start (bench bookkeeping). */
 long long pb_launch_count(void);
 /* Per-kernel device timing for benchmarks: when enabled, every pb_postprocess /
@@ -159,6 +165,9 @@ int pb_set_profiling(pb_handle_t h, int enabled);
  * (in-kernel timestamps): scan+compaction, ranking, gather, suppression, output. */
 int pb_get_post_stage_us(pb_handle_t h, double* out5);
 int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_launches, double* track_ms, int* track_launches);
+/* Same record as mean microseconds per launch of each of the three kernels (decode+gather, NMS,
+ * tracker); clears the record. */
+int pb_get_kernel_us(pb_handle_t h, double* gather_us, double* nms_us, double* track_us, int* launches);
 
 /* ---- stage-level entry points ------------------------------------------------------ */
 

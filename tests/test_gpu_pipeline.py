@@ -68,6 +68,20 @@ def test_step_host_equals_device_path(pb, orc, cuda):
         for s in range(4):
             assert out_h[s, : cnt_h[s]].tobytes() == out_d[s, : cnt_d[s]].tobytes()
     assert cnt_h.sum() > 20
+    # page-locked buffers: the input is read in place over PCIe, the results land in `out`/`counts`
+    c = pb.Pipeline(num_streams=4)
+    pinned = torch.from_numpy(heads).pin_memory()
+    out_p = torch.zeros(4 * c.Dm * 228, dtype=torch.uint8).pin_memory()
+    cnt_p = torch.zeros(4, dtype=torch.int32).pin_memory()
+    out_np = out_p.numpy().view(pb.TRACK_OUTPUT).reshape(4, c.Dm)
+    d = pb.Pipeline(num_streams=4)
+    for f in range(10):
+        c.step_host(pinned[f].numpy(), f, out=out_np, counts=cnt_p.numpy())
+        d.step(torch.from_numpy(heads[f]).cuda(), f)
+        out_d, cnt_d = d.get_tracks_all()
+        assert np.array_equal(cnt_p.numpy(), cnt_d)
+        for s in range(4):
+            assert out_np[s, : cnt_d[s]].tobytes() == out_d[s, : cnt_d[s]].tobytes()
 
 
 def test_launch_counter_counts_real_kernels(pb, cuda):

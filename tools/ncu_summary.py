@@ -3,6 +3,7 @@
 usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [more.ncu-rep ...] > profiles/<name>.md
 Reads the report with `ncu -i … --page raw --csv` (works without a GPU)."""
 import csv
+import os
 import subprocess
 import sys
 
@@ -42,7 +43,31 @@ def load(rep):
     return hdr, units, data
 
 
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def traffic(reps, out_path):
+    """profiles/ncu_traffic.json: mean dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel."""
+    import collections
+    import json
+    acc = collections.defaultdict(list)
+    for rep in reps:
+        hdr, units, data = load(rep)
+        col = {h: i for i, h in enumerate(hdr)}
+        ir, iw = col["dram__bytes_read.sum"], col["dram__bytes_write.sum"]
+        for r in data:
+            name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+            acc[name].append(float(r[ir].replace(",", "")) * UNIT[units[ir]] + float(r[iw].replace(",", "")) * UNIT[units[iw]])
+    out = {"source": [os.path.basename(r) for r in reps], "what": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean per launch",
+           "bytes_per_launch": {k: int(sum(v) / len(v)) for k, v in acc.items()}, "launches": {k: len(v) for k, v in acc.items()}}
+    with open(out_path, "w") as f:
+        json.dump(out, f, indent=1)
+    print(out)
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[3:], sys.argv[2])
     for rep in sys.argv[1:]:
         hdr, units, data = load(rep)
         col = {h: i for i, h in enumerate(hdr)}

@@ -1,0 +1,30 @@
+"""Per-stream, per-frame tracker chain time: how heavy is the tail that sets the kernel time?"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import posebyte_b200 as pb
+B, F = 64, 16
+scfg = pb.synth_config(canvas=640, persons=20, period=32)
+d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()
+pipe = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+for f in range(32): pipe.step(d[f % F], f)
+prev = pipe.stream_stage_ns().astype(np.int64)
+rows = []
+for f in range(32, 96):
+    pipe.step(d[f % F], f)
+    cur = pipe.stream_stage_ns().astype(np.int64)
+    rows.append(cur - prev); prev = cur
+a = np.stack(rows) / 1e3            # [frames, B, 20] us
+names = {15: "iters", 16: "bidders", 17: "cyc_scan", 18: "cyc_resolve", 19: "cyc_update", 0: "prologue", 2: "gate", 12: "t1cost", 13: "t1auction", 4: "tier2", 5: "tier3", 9: "dedup", 10: "total"}
+for i, n in names.items():
+    x = a[:, :, i]
+    print(f"{n:10s} mean {x.mean():6.2f}  p50 {np.percentile(x, 50):6.2f}  p90 {np.percentile(x, 90):6.2f}  p99 {np.percentile(x, 99):6.2f}  max {x.max():6.2f} | mean over frames of max over streams {x.max(1).mean():6.2f}")
+tot = a[:, :, 10]
+worst = np.unravel_index(tot.argmax(), tot.shape)
+print("worst stream-frame:", worst, {n: round(float(a[worst[0], worst[1], i]), 2) for i, n in names.items()})
+na = pipe.get_num_active()
+it=a[:,:,15].sum()
+print(f"per iteration: bidders {a[:,:,16].sum()/it:.1f} scan cycles {a[:,:,17].sum()/it:.0f} resolve cycles {a[:,:,18].sum()/it:.0f}; update cycles {a[:,:,19].sum()/it:.0f}; iterations per frame {a[:,:,15].mean()*1e3:.1f}")
+w=worst; print(f"worst frame: iters {a[w[0],w[1],15]*1e3:.0f} bidders {a[w[0],w[1],16]*1e3:.0f} scan {a[w[0],w[1],17]*1e3:.0f} resolve {a[w[0],w[1],18]*1e3:.0f} build {a[w[0],w[1],19]*1e3:.0f} cycles")
+print("num_active per stream: min", na.min(), "max", na.max())

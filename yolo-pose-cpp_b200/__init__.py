@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
     "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
-    "pb_get_timing", "pb_launch_count", "pb_set_profiling", "pb_get_kernel_ms", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
+    "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
 ]
 
@@ -107,9 +107,11 @@ def lib() -> C.CDLL:
         L.pb_get_state.argtypes = [vp, ip] + [vp] * 15
         L.pb_get_device_views.argtypes = [vp, C.POINTER(PbDeviceViews)]
         L.pb_get_timing.argtypes = [vp, C.POINTER(PbTiming)]
+        L.pb_get_stream_stage_ns.argtypes = [vp, vp]
         L.pb_get_post_stage_us.argtypes = [vp, C.POINTER(C.c_double * 5)]
         L.pb_set_profiling.argtypes = [vp, ip]
         L.pb_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip), C.POINTER(C.c_double), C.POINTER(ip)]
+        L.pb_get_kernel_us.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ip)]
         L.launchPoseNMS.argtypes = [vp, vp, vp, vp, ip, ip, fp, fp, vp]
         L.pb_nms_legacy.argtypes = [vp, vp, ip, ip, fp, fp, vp, vp, vp]
         L.pb_auction_solve.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp]
@@ -193,9 +195,14 @@ class Pipeline:
         """Make `stream` wait for work a pipelined step left on the internal streams."""
         check(lib().pb_join(self._h, _stream_ptr(stream)))
 
-    def step_host(self, heads_np: np.ndarray, frame_id, conf=0.30, nms=0.65):
-        out = np.zeros((self.B, self.Dm), dtype=TRACK_OUTPUT)
-        counts = np.zeros(self.B, dtype=np.int32)
+    def step_host(self, heads_np: np.ndarray, frame_id, conf=0.30, nms=0.65, out=None, counts=None):
+        """Host buffers in, TrackOutput records out.  `heads_np` (and optionally `out` [B,Dm]
+        TRACK_OUTPUT / `counts` [B] int32) may be views of page-locked memory: the input is then
+        read in place by the GPU and the results are copied straight into `out` / `counts`."""
+        if out is None:
+            out = np.zeros((self.B, self.Dm), dtype=TRACK_OUTPUT)
+        if counts is None:
+            counts = np.zeros(self.B, dtype=np.int32)
         check(lib().pb_step_host(self._h, heads_np.ctypes.data, conf, nms, frame_id, out.ctypes.data, counts.ctypes.data))
         return out, counts
 
@@ -265,6 +272,18 @@ class Pipeline:
         pm, tm, pn, tn = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
         check(lib().pb_get_kernel_ms(self._h, C.byref(pm), C.byref(pn), C.byref(tm), C.byref(tn)))
         return dict(post_ms=pm.value, post_launches=pn.value, track_ms=tm.value, track_launches=tn.value)
+
+    def stream_stage_ns(self) -> np.ndarray:
+        """[B,20] per-stream nanosecond accumulators of the tracker stages (see the header)."""
+        out = np.zeros((self.B, 20), np.uint64)
+        check(lib().pb_get_stream_stage_ns(self._h, out.ctypes.data))
+        return out
+
+    def kernel_us(self) -> dict:
+        """Mean device microseconds per launch of the three kernels since the last call (needs set_profiling(True))."""
+        g, n, t, k = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+        check(lib().pb_get_kernel_us(self._h, C.byref(g), C.byref(n), C.byref(t), C.byref(k)))
+        return dict(gather_us=g.value, nms_us=n.value, track_us=t.value, launches=k.value)
 
     def timing(self) -> PbTiming:
         t = PbTiming()

@@ -188,110 +188,105 @@ __device__ __forceinline__ void auction_solve_warp(const float* cost, int R, int
 
 
 // ---------------------------------------------------------------------------------------
-// Register-resident single-warp variant: columns <= 32*CPL (CPL 1 or 2), rows <= 128.
-// Lane d owns column d (and d+32): its price, its owner and this iteration's best bid live in
-// registers; the set of unassigned active rows is four uniform 32-bit masks.  One bidder row
-// at a time: every lane loads its column's cost, the warp finds (best value, lowest column)
-// and the second value with three redux.sync operations on order-preserving integer keys, and
-// the owning lane records the bid.  No shared-memory atomics, no barriers inside the loop.
-// Same results as auction_solve_cta (explicit tie-breaks: lowest column among equal values,
-// lowest row among equal bids because rows are visited in ascending order with strict '>').
+// Row-parallel single-warp solve for the tracker's common case: at most 32 ACTIVE rows, cost
+// matrix in shared memory.  Same results as auction_solve_cta (tests compare them).
+//
+// Lane i owns the i-th active row (act_list, ascending slots) and one "unassigned" flag;
+// prices and owners live in shared memory.  All bidders of an iteration scan their rows in
+// parallel (SIMT over rows; a rolled, 4-way software-pipelined loop).  A single bidder applies
+// its bid directly; several bidders are grouped by column with match.any, the group's highest
+// bid found with one redux and the lowest row among equal bids with one ballot
+// (hungarian.cu:100) — no shared-memory atomics (a 64-bit shared atomicMax compiles to a CAS
+// spin loop on sm_100a and serialises when many rows want one column).
+// The cost of an iteration is ~constant instead of proportional to the number of bidders,
+// which bounds the slowest stream of a batch — the tail that sets the kernel time.  The loop
+// body is kept small on purpose: it runs up to 150 times per stream-frame and has to stay
+// inside the instruction cache (an unrolled multi-path version of this loop ran 3x slower).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned auc_ord(float v) {          // order-preserving float -> uint
-    unsigned u = __float_as_uint(v);
-    if (u == 0x80000000u) u = 0u;                               // -0 and +0 compare equal
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float auc_dec(unsigned k) {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
+struct AucScratch {          // shared memory
+    float* price;            // [C]
+    int* owner;              // [C] row INDEX (position in act_list), -1 = free
+};
 
-template <int CPL>
-__device__ __forceinline__ void auction_solve_regs(const float* cost, int R, int C, const int* active,
-                                                   int* row, int* col, int tid) {
+static __device__ __noinline__ void auction_solve_rows32(const float* cost_s, int R, int C, const int* act_list, int na,
+                                                  int* row, int* col, float* price, int* owner,
+                                                  unsigned* colbid, int* colrow) {
     const unsigned FULL = 0xffffffffu;
-    if (tid < 32 && R > 0 && C > 0) {
-        const int lane = tid;
-        const unsigned kFloor = auc_ord(-1e9f);
-        float price[CPL];
-        int owner[CPL];
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) { price[q] = 0.0f; owner[q] = -1; }
-        unsigned um[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int r = 32 * w + lane;
-            um[w] = __ballot_sync(FULL, r < R && (active == nullptr || active[r] != 0));
-        }
-        float eps = 1.0f / (float)(R + 1);
-        const int iters = (R * 3 < 50) ? R * 3 : 50;
-        for (int it = 0; it < iters; ++it) {
-            unsigned bidbits[CPL];
-            int bidrow[CPL];
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) { bidbits[q] = 0u; bidrow[q] = -1; }
-            bool any = false;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                unsigned bm = um[w];
-                while (bm) {
-                    const int rb = 32 * w + __ffs(bm) - 1;
-                    bm &= bm - 1;
-                    const float* cr = cost + (size_t)rb * C;
-                    unsigned kb = 0u, ks = 0u;
-                    int qb = 0;
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const int d = lane + 32 * q;
-                        const unsigned k = (d < C) ? auc_ord(-cr[d] - price[q]) : 0u;     // :61
-                        if (k > kb) { ks = kb; kb = k; qb = q; }
-                        else if (k > ks) { ks = k; }
-                    }
-                    const unsigned m1 = __reduce_max_sync(FULL, kb);
-                    if (m1 <= kFloor) continue;                  // no column with value > -1e9 (:55-63)
-                    const unsigned bc = __reduce_min_sync(FULL, (kb == m1) ? (unsigned)(lane + 32 * qb) : 0x7fffffffu);
-                    unsigned m2 = __reduce_max_sync(FULL, ((unsigned)(lane + 32 * qb) == bc) ? ks : kb);
-                    if (m2 < kFloor) m2 = kFloor;
-                    const float bid = auc_dec(m1) - auc_dec(m2) + eps;                     // :99
-                    if ((int)(bc & 31u) == lane) {
-#pragma unroll
-                        for (int q = 0; q < CPL; ++q)
-                            if ((int)(bc >> 5) == q && (bidrow[q] < 0 || bid > __uint_as_float(bidbits[q]))) {
-                                bidbits[q] = __float_as_uint(bid); bidrow[q] = rb;         // :100
-                            }
-                    }
-                    any = true;
-                }
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < R; t += 32) row[t] = -1;
+    for (int d = lane; d < C; d += 32) { col[d] = -1; price[d] = 0.0f; owner[d] = -1; colbid[d] = 0u; colrow[d] = 0x7fffffff; }
+    if (na <= 0 || C <= 0) return;
+    const bool mine = lane < na;
+    const float* cr = cost_s + (size_t)(mine ? act_list[lane] : 0) * C;
+    bool unas = mine;
+    __syncwarp();
+    float eps = 1.0f / (float)(R + 1);                                                     // :378
+    const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
+    const int C4 = C & ~3;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const unsigned ub = __ballot_sync(FULL, unas);
+        if (ub == 0u) break;                                                               // fixed point
+        int bc = -1;
+        unsigned bid = 0u;
+        if (unas) {
+            float bv = -1e9f, sv = -1e9f;
+#pragma unroll 1
+            for (int d = 0; d < C4; d += 4) {                                              // loads first, then the compare chain
+                const float v0 = -cr[d] - price[d], v1 = -cr[d + 1] - price[d + 1];        // :61
+                const float v2 = -cr[d + 2] - price[d + 2], v3 = -cr[d + 3] - price[d + 3];
+                if (v0 > bv) { sv = bv; bv = v0; bc = d; } else if (v0 > sv) sv = v0;      // ascending d: lowest column on ties (:63)
+                if (v1 > bv) { sv = bv; bv = v1; bc = d + 1; } else if (v1 > sv) sv = v1;
+                if (v2 > bv) { sv = bv; bv = v2; bc = d + 2; } else if (v2 > sv) sv = v2;
+                if (v3 > bv) { sv = bv; bv = v3; bc = d + 3; } else if (v3 > sv) sv = v3;
             }
-            if (!any) break;                                     // fixed point
-            unsigned clr[4] = {0u, 0u, 0u, 0u}, set[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                if (bidrow[q] >= 0) {                            // :107-121
-                    const int prev = owner[q];
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        if ((bidrow[q] >> 5) == w) clr[w] |= 1u << (bidrow[q] & 31);
-                        if (prev >= 0 && (prev >> 5) == w) set[w] |= 1u << (prev & 31);
-                    }
-                    owner[q] = bidrow[q];
-                    price[q] += __uint_as_float(bidbits[q]);
-                }
+#pragma unroll 1
+            for (int d = C4; d < C; ++d) {
+                const float v = -cr[d] - price[d];
+                if (v > bv) { sv = bv; bv = v; bc = d; } else if (v > sv) sv = v;
             }
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-                um[w] = (um[w] & ~__reduce_or_sync(FULL, clr[w])) | __reduce_or_sync(FULL, set[w]);
-            eps *= 0.9f;                                         // :402
+            if (bc >= 0) bid = __float_as_uint(bv - sv + eps);                             // :99 (positive: bits order like the floats)
         }
-        for (int t = lane; t < R; t += 32) row[t] = -1;
+        const unsigned pm = __ballot_sync(FULL, bc >= 0);
+        if (pm == 0u) break;                                                               // no bid: fixed point
+        bool win = bc >= 0;
+        const int nbid = __popc(pm);
+        if (nbid > 1 && nbid <= 8) {
+            // few bidders: every bidder compares itself with the others (highest bid, lowest row, :100)
+            unsigned rem = pm;
+            while (rem) {
+                const int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int obc = __shfl_sync(FULL, bc, j);
+                const unsigned obid = __shfl_sync(FULL, bid, j);
+                if (obc == bc && (obid > bid || (obid == bid && j < lane))) win = false;
+            }
+        } else if (nbid > 8) {
+            if (bc >= 0) atomicMax(&colbid[bc], bid);
+            __syncwarp();
+            if (bc >= 0 && colbid[bc] == bid) atomicMin(&colrow[bc], lane);
+            __syncwarp();
+            win = bc >= 0 && colbid[bc] == bid && colrow[bc] == lane;
+            __syncwarp();
+            if (win) { colbid[bc] = 0u; colrow[bc] = 0x7fffffff; }
+        }
+        int prev = -1;
+        if (win) {                                                                         // :107-121
+            prev = owner[bc];
+            owner[bc] = lane;
+            price[bc] += __uint_as_float(bid);
+            unas = false;
+        }
+        const unsigned em = __reduce_or_sync(FULL, prev >= 0 ? (1u << prev) : 0u);         // evicted owners bid again
+        if ((em >> lane) & 1u) unas = true;
         __syncwarp();
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-            const int d = lane + 32 * q;
-            if (d < C) { col[d] = owner[q]; if (owner[q] >= 0) row[owner[q]] = d; }
-        }
+        eps *= 0.9f;                                                                       // :402
     }
-    __syncthreads();
+    __syncwarp();
+    for (int d = lane; d < C; d += 32) {
+        const int o = owner[d];
+        if (o >= 0) { const int slot = act_list[o]; col[d] = slot; row[slot] = d; }
+    }
 }
 
 }  // namespace pb

@@ -60,7 +60,7 @@ struct pb_handle_st {
     // optional per-kernel event timing (pb_set_profiling)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
-    std::vector<std::pair<int, int>> ev_post, ev_track;   // indices into ev_pool (begin, end)
+    std::vector<std::pair<int, int>> ev_post, ev_track, ev_gather;   // indices into ev_pool (begin, end)
     size_t ev_used = 0;
 };
 
@@ -260,9 +260,13 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
     if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
     const pb_config& c = h->cfg;
     PB_TRY(join_on(h, (cudaStream_t)stream));
-    int e0 = -1, e1 = -1;
+    int e0 = -1, e1 = -1, em = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->dplan, h->cand, (cudaStream_t)stream));
+    if (h->profiling && e0 >= 0 && (em = prof_event(h)) >= 0) {
+        cudaEventRecord(h->ev_pool[em], (cudaStream_t)stream);
+        h->ev_gather.push_back({e0, em});
+    }
     PB_CUDA(launch_nms(c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
@@ -347,18 +351,42 @@ int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int
     const pb_config& c = h->cfg;
     const size_t B = c.num_streams, Dm = c.max_detections;
     const size_t head_bytes = B * HEAD_ROWS * (size_t)c.num_anchors * sizeof(float);
-    if (!h->d_stage) PB_CUDA(cudaMalloc(&h->d_stage, head_bytes));
-    if (!h->h_out_pinned) PB_CUDA(cudaMallocHost(&h->h_out_pinned, B * Dm * 228));
-    if (!h->h_cnt_pinned) PB_CUDA(cudaMallocHost(&h->h_cnt_pinned, B * sizeof(int)));
     cudaStream_t s = h->own_stream;
-    PB_CUDA(cudaMemcpyAsync(h->d_stage, h_heads, head_bytes, cudaMemcpyHostToDevice, s));
-    PB_TRY(pb_step(h, h->d_stage, conf, nms, frame_id, (pb_stream_t)s));
+    // Page-locked (cudaHostAlloc / cudaHostRegister) input is read IN PLACE by the decode kernel
+    // over PCIe: the confidence rows and the 32-byte sectors at the candidate anchors — about a
+    // seventh of the tensor at 130 candidates per stream — instead of staging all of it in HBM.
+    // Pageable input cannot be mapped and is staged with one copy.
+    const float* src = nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h_heads) == cudaSuccess && at.devicePointer != nullptr &&
+        (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+        src = static_cast<const float*>(at.devicePointer);
+    } else {
+        (void)cudaGetLastError();
+        if (!h->d_stage) PB_CUDA(cudaMalloc(&h->d_stage, head_bytes));
+        PB_CUDA(cudaMemcpyAsync(h->d_stage, h_heads, head_bytes, cudaMemcpyHostToDevice, s));
+        src = h->d_stage;
+    }
+    PB_TRY(pb_step(h, src, conf, nms, frame_id, (pb_stream_t)s));
     PB_TRY(join_on(h, s));
-    PB_CUDA(cudaMemcpyAsync(h->h_cnt_pinned, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaMemcpyAsync(h->h_out_pinned, h->trk.outputs, B * Dm * 228, cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaStreamSynchronize(s));
-    memcpy(h_counts, h->h_cnt_pinned, B * sizeof(int));
-    memcpy(h_tracks, h->h_out_pinned, B * Dm * 228);
+    // results: straight into the caller's buffers when they are page-locked, else via pinned staging
+    cudaPointerAttributes ot{}, oc{};
+    const bool direct = cudaPointerGetAttributes(&ot, h_tracks) == cudaSuccess && ot.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&oc, h_counts) == cudaSuccess && oc.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    if (direct) {
+        PB_CUDA(cudaMemcpyAsync(h_counts, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaMemcpyAsync(h_tracks, h->trk.outputs, B * Dm * 228, cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaStreamSynchronize(s));
+    } else {
+        if (!h->h_out_pinned) PB_CUDA(cudaMallocHost(&h->h_out_pinned, B * Dm * 228));
+        if (!h->h_cnt_pinned) PB_CUDA(cudaMallocHost(&h->h_cnt_pinned, B * sizeof(int)));
+        PB_CUDA(cudaMemcpyAsync(h->h_cnt_pinned, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaMemcpyAsync(h->h_out_pinned, h->trk.outputs, B * Dm * 228, cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaStreamSynchronize(s));
+        memcpy(h_counts, h->h_cnt_pinned, B * sizeof(int));
+        memcpy(h_tracks, h->h_out_pinned, B * Dm * 228);
+    }
     return PB_OK;
 }
 
@@ -486,7 +514,34 @@ int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_n, double* track_
     };
     sum(h->ev_post, post_ms, post_n);
     sum(h->ev_track, track_ms, track_n);
+    h->ev_gather.clear();
     h->ev_used = 0;
+    return PB_OK;
+}
+
+int pb_get_kernel_us(pb_handle_t h, double* gather_us, double* nms_us, double* track_us, int* launches) {
+    if (!h) { pb_set_error("pb_get_kernel_us: null handle"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    auto total = [&](std::vector<std::pair<int, int>>& v) {
+        double acc = 0;
+        for (auto& pr : v) { float t = 0; if (cudaEventElapsedTime(&t, h->ev_pool[pr.first], h->ev_pool[pr.second]) == cudaSuccess) acc += t; }
+        return acc * 1e3;
+    };
+    const double g = total(h->ev_gather), p = total(h->ev_post), t = total(h->ev_track);
+    const int n = (int)h->ev_post.size(), nt = (int)h->ev_track.size();
+    if (gather_us) *gather_us = n ? g / n : 0.0;
+    if (nms_us) *nms_us = n ? (p - g) / n : 0.0;
+    if (track_us) *track_us = nt ? t / nt : 0.0;
+    if (launches) *launches = n;
+    h->ev_gather.clear(); h->ev_post.clear(); h->ev_track.clear();
+    h->ev_used = 0;
+    return PB_OK;
+}
+
+int pb_get_stream_stage_ns(pb_handle_t h, unsigned long long* out) {
+    if (!h || !out) { pb_set_error("pb_get_stream_stage_ns: bad argument"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    PB_CUDA(cudaMemcpy(out, h->trk.stage_ns, (size_t)h->cfg.num_streams * 20 * 8, cudaMemcpyDeviceToHost));
     return PB_OK;
 }
 

@@ -41,6 +41,7 @@ struct TkSmem {
     float* terms;                                                                     // [term_floats]
     float* sig;                                                                       // [17]
     int* cell_list;                                                                   // [CELL_LIST_CAP]
+    int* aowner;                                                                      // [Dm] auction scratch
     float *cost, *det, *pred;                                                         // optional
 };
 
@@ -60,6 +61,7 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
     size_t o_gate = take((size_t)T * Dw * 4), o_lgate = take((size_t)T * Dw * 4), o_colmask = take((size_t)Dw * 4);
     size_t o_dup = take(DUP_CAP * 4), o_misc = take(32 * 4);
     size_t o_terms = take((size_t)term_floats * 4), o_sig = take(KP * 4), o_cl = take(CELL_LIST_CAP * 4);
+    size_t o_aown = take((size_t)Dm * 4);
     size_t o_cost = cost_s ? take((size_t)T * Dm * 4) : 0;
     size_t o_det = det_s ? take((size_t)Dm * POSE_F * 4) : 0;
     size_t o_pred = pred_s ? take((size_t)T * POSE_F * 4) : 0;
@@ -79,6 +81,7 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
         s->colmask = (unsigned*)(base + o_colmask);
         s->dup = (int*)(base + o_dup); s->misc = (int*)(base + o_misc);
         s->terms = (float*)(base + o_terms); s->sig = (float*)(base + o_sig); s->cell_list = (int*)(base + o_cl);
+        s->aowner = (int*)(base + o_aown);
         s->cost = cost_s ? (float*)(base + o_cost) : nullptr;
         s->det = det_s ? (float*)(base + o_det) : nullptr;
         s->pred = pred_s ? (float*)(base + o_pred) : nullptr;
@@ -197,12 +200,12 @@ struct Ctx {
 };
 
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
-__device__ __forceinline__ void auction_solve(Ctx& c) {
+__device__ __forceinline__ void auction_solve(Ctx& c, int na) {
     TkSmem& s = c.s;
-    if (c.warp_auction && c.T <= 128 && c.D <= 32) {
-        auction_solve_regs<1>(c.cost, c.T, c.D, s.active, s.row, s.col, c.tid);
-    } else if (c.warp_auction && c.T <= 128 && c.D <= 64) {
-        auction_solve_regs<2>(c.cost, c.T, c.D, s.active, s.row, s.col, c.tid);
+    if (c.warp_auction && na <= 32) {
+        if (c.tid < 32) auction_solve_rows32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
+                                              reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D);
+        __syncthreads();
     } else if (c.warp_auction) {
         // colbid (8 B per column) doubles as the 32-bit bid array + the lowest-row array
         unsigned* colbid32 = reinterpret_cast<unsigned*>(s.colbid);
@@ -515,7 +518,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     if (assoc12) {
         cost_pass_oks(c, s.gate, na, 0.2f);
         stamp(12);
-        auction_solve(c);
+        auction_solve(c, na);
         stamp(13);
         lock_pairs(c, s.gate, na);
         stamp(14);
@@ -525,7 +528,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     if (assoc12) {
         backup_assign(c);
         cost_pass_torso(c, s.gate, na);
-        auction_solve(c);
+        auction_solve(c, na);
         merge_assign(c);
         lock_pairs(c, s.gate, na);
     }
@@ -536,7 +539,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         cost_inactive_rows(c);
         lock_pairs(c, s.lgate, na);
         cost_pass_oks(c, s.lgate, na, 0.2f);
-        auction_solve(c);
+        auction_solve(c, na);
         merge_assign(c);
     }
     stamp(5);
