@@ -151,7 +151,7 @@ def reference_gpu_b1(pb, torch, frames=200):
         return {"error": str(e)}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -180,10 +180,25 @@ def run_reference_arm(args):
                              "sample": f"{cores} streams x {sample_frames} frames per step; scalar C++ transcription of the reference kernels "
                                        "(the reference has no host implementation of the tracker)"},
             "e2e": {"value": value, "unit": "stream-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
+
+
+class OnlyJsonOnStdout:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the one
+    JSON line is written to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
 
 
 def main():
+    out = OnlyJsonOnStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -198,7 +213,7 @@ def main():
         args.warmup = 3
 
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     import torch
@@ -376,7 +391,7 @@ def main():
         if ref_gpu:
             cb["reference_gpu_b1"] = ref_gpu
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
