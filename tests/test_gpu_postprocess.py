@@ -28,9 +28,10 @@ def test_postprocess_matches_checker(pb, orc, cuda, canvas, persons, clumps, B, 
     cfg = pb.synth_config(canvas=canvas, persons=persons, period=16, clumps=clumps, kp_drop_prob=0.15 if clumps else 0.05)
     heads = pb.synth_heads(cfg, 0, B, 0, frames, frame_major=True)
     for f in range(frames):
-        _, got = run_post(pb, cuda, heads[f])
-        for b in range(B):
-            assert_same(got[b], orc.postprocess(heads[f, b]), f"f{f} b{b}")
+        for mode in (0, 1):                  # default (complete records from the decode kernel) and lazy keypoints
+            _, got = run_post(pb, cuda, heads[f], keypoint_fetch=mode)
+            for b in range(B):
+                assert_same(got[b], orc.postprocess(heads[f, b]), f"f{f} b{b} mode{mode}")
 
 
 def test_empty_and_single(pb, orc, cuda):
@@ -85,3 +86,38 @@ def test_unaligned_anchor_count(pb, orc, cuda):
     _, got = run_post(pb, cuda, heads)
     for b in range(2):
         assert_same(got[b], orc.postprocess(heads[b]), f"b{b}")
+
+
+def test_fast_path_and_complete_path_both_match_checker(pb, orc, cuda):
+    """The NMS kernel first sweeps by IoU alone and fetches keypoints only for the survivors; if one
+    of them would fall to an OKS rule it reruns with all keypoints.  Stream 0: ordinary duplicates
+    (IoU decides: fast path).  Stream 1: two anchors with the same skeleton but boxes that overlap
+    too little for the IoU rule — only the OKS rule removes the weaker one (complete path).
+    Stream 2: same skeletons, IoU in (0.2, thr] and OKS in (0.4, thr]: the combined rule fires."""
+    cfg = pb.synth_config(canvas=640, persons=6, period=16)
+    base = pb.synth_heads(cfg, 9, 1, 0, 1, frame_major=True)[0, 0]
+    heads = np.stack([base, base.copy(), base.copy()])
+    tmpl = np.array([[0.0, -1.5], [-0.1, -1.6], [0.1, -1.6], [-0.2, -1.5], [0.2, -1.5], [-0.5, -1.0], [0.5, -1.0], [-0.8, -0.3],
+                     [0.8, -0.3], [-1.0, 0.3], [1.0, 0.3], [-0.3, 0.0], [0.3, 0.0], [-0.3, 0.8], [0.3, 0.8], [-0.3, 1.5], [0.3, 1.5]], np.float32)
+
+    def put(h, anchor, score, cx, cy, w, hh, kps, kshift=0.0):
+        h[:4, anchor] = [cx, cy, w, hh]; h[4, anchor] = score
+        for k in range(17):
+            h[5 + 3 * k, anchor] = kps[k, 0] + kshift; h[6 + 3 * k, anchor] = kps[k, 1]; h[7 + 3 * k, anchor] = 0.9
+    kps = np.array([320.0, 520.0], np.float32) + tmpl * 40.0
+    # stream 1: identical skeletons, boxes 120x200 shifted by 70 px -> IoU = 50*200/(2*24000-10000) = 0.26 < 0.65, OKS = 1
+    put(heads[1], 7000, 0.93, 320, 520, 120, 200, kps)
+    put(heads[1], 7003, 0.91, 390, 520, 120, 200, kps)
+    # stream 2: skeleton shifted by 14 px (OKS between 0.4 and 0.65 at this scale), boxes shifted 40 px (IoU = 0.5)
+    put(heads[2], 7000, 0.93, 320, 520, 120, 200, kps)
+    put(heads[2], 7003, 0.91, 360, 520, 120, 200, kps, kshift=14.0)
+    refs = [orc.postprocess(heads[b]) for b in range(3)]
+    for mode in (2, 1):                      # never lazy / always lazy: same results
+        pipe, got = run_post(pb, cuda, heads, keypoint_fetch=mode)
+        for b in range(3):
+            assert_same(got[b], refs[b], f"mode {mode} stream {b}")
+    assert 7000 in got[1]["keep_anchors"] and 7003 not in got[1]["keep_anchors"]      # removed by the OKS rule alone
+    counts = pipe.nms_path_counts()
+    assert counts["fast"] >= 1 and counts["complete"] >= 1, counts
+    if 7003 not in refs[2]["keep_anchors"]:
+        assert counts["complete"] >= 2, counts

@@ -44,7 +44,7 @@ class PbConfig(C.Structure):
                 ("match_threshold", C.c_float), ("high_thresh", C.c_float), ("low_thresh", C.c_float),
                 ("new_track_thresh", C.c_float), ("max_age", C.c_int), ("min_hits", C.c_int),
                 ("use_cuda_graph", C.c_int), ("gating_enabled", C.c_int), ("device", C.c_int),
-                ("pipeline_depth", C.c_int)]
+                ("pipeline_depth", C.c_int), ("keypoint_fetch", C.c_int)]
 
 
 class PbTiming(C.Structure):
@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
     "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
-    "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
+    "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
 ]
 
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         L.pb_get_post_stage_us.argtypes = [vp, C.POINTER(C.c_double * 5)]
         L.pb_set_profiling.argtypes = [vp, ip]
         L.pb_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip), C.POINTER(C.c_double), C.POINTER(ip)]
+        L.pb_get_nms_path_counts.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.pb_get_kernel_us.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ip)]
         L.launchPoseNMS.argtypes = [vp, vp, vp, vp, ip, ip, fp, fp, vp]
         L.pb_nms_legacy.argtypes = [vp, vp, ip, ip, fp, fp, vp, vp, vp]
@@ -278,6 +279,12 @@ class Pipeline:
         out = np.zeros((self.B, 20), np.uint64)
         check(lib().pb_get_stream_stage_ns(self._h, out.ctypes.data))
         return out
+
+    def nms_path_counts(self) -> dict:
+        """Stream-frames finished on the NMS fast path / total that needed the complete path."""
+        f, c = C.c_longlong(0), C.c_longlong(0)
+        check(lib().pb_get_nms_path_counts(self._h, C.byref(f), C.byref(c)))
+        return dict(fast=f.value - c.value, complete=c.value)
 
     def kernel_us(self) -> dict:
         """Mean device microseconds per launch of the three kernels since the last call (needs set_profiling(True))."""

@@ -37,10 +37,11 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int DG_THREADS = 256;
 constexpr int DG_WARPS = DG_THREADS / 32;
 constexpr int DG_MAX_CHUNKS = 16;            // float4 groups per segment <= 16 * 256
+constexpr int BOX_ROWS = 5;                  // cx, cy, w, h, confidence
 
 __global__ void __launch_bounds__(DG_THREADS)
 pb_decode_gather_kernel(const float* __restrict__ heads, int N, int nseg, int groups_per_seg, int segcap,
-                        float conf_thr, CandScratch cs) {
+                        float conf_thr, int rows, CandScratch cs) {
     __shared__ int s_cnt[DG_MAX_CHUNKS * DG_WARPS];
     __shared__ int s_total;
     extern __shared__ int s_anchor[];            // [segcap]
@@ -129,24 +130,27 @@ pb_decode_gather_kernel(const float* __restrict__ heads, int N, int nseg, int gr
     const int total = s_total;
     const int n_s = total < segcap ? total : segcap;   // only the first Ccap overall can matter (R1)
 
-    // ---- gather all 56 rows at the hit anchors; one contiguous record per candidate ----
+    // ---- gather head rows [0, rows) at the hit anchors into one record per candidate.  rows = 56: the
+    // complete column (head in HBM: sector reads are cheap, NMS then never touches the head again);
+    // rows = 5: box + confidence only (head in page-locked host memory: the 51 keypoint rows are
+    // fetched later, by the NMS kernel, only for the candidates that can survive) ----
     float* rec = cs.records + ((size_t)(b * nseg + seg) * segcap) * HEAD_ROWS;
     int* anc = cs.anchors + (size_t)(b * nseg + seg) * segcap;
-    const int items = n_s * HEAD_ROWS;
+    const int items = n_s * rows;
     for (int it0 = tid; it0 < items; it0 += DG_THREADS * 8) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int it = it0 + u * DG_THREADS;
             if (it < items) {
-                const int h = it / HEAD_ROWS, row = it - h * HEAD_ROWS;
+                const int h = it / rows, row = it - h * rows;
                 v[u] = ldg_stream_f(head + (size_t)row * N + s_anchor[h]);
             }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int it = it0 + u * DG_THREADS;
-            if (it < items) rec[it] = v[u];
+            if (it < items) { const int h = it / rows, row = it - h * rows; rec[h * HEAD_ROWS + row] = v[u]; }
         }
     }
     for (int h = tid; h < n_s; h += DG_THREADS) anc[h] = s_anchor[h];
@@ -293,7 +297,8 @@ __device__ __forceinline__ bool nms_stage_b(const NmSmem& s, int CS, int i, int 
 }
 
 // Stages B and C over the pairs queued in list 1.  MODE 0: pairs inside the tile -> tile mask;
-// MODE 1: survivor x later rank -> suppressed bitmap.  All threads of the CTA call this.
+// MODE 1: survivor x later rank -> suppressed bitmap; MODE 2: verification of the fast path
+// (any overlapping pair raises misc[5]).  All threads of the CTA call this.
 template <int MODE>
 __device__ __forceinline__ void resolve_lists(const NmSmem& s, int CS, int t0, float thr, int tid) {
     const int n1 = s.misc[3];
@@ -344,7 +349,8 @@ __device__ __forceinline__ void resolve_lists(const NmSmem& s, int CS, int t0, f
             const float iou = pair_iou(s, CS, i, j);
             if ((oks > thr) || (oks > 0.4f && iou > 0.2f)) {
                 if (MODE == 0) atomicOr(&s.tmask[i - t0], 1ull << (j - t0));
-                else atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+                else if (MODE == 1) atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+                else s.misc[5] = 1;
             }
         }
         __syncthreads();
@@ -352,15 +358,22 @@ __device__ __forceinline__ void resolve_lists(const NmSmem& s, int CS, int t0, f
 }
 
 __global__ void __launch_bounds__(NM_THREADS, 1)
-pb_nms_kernel(CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr, PostBuffers out) {
+pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr,
+              PostBuffers out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmSmem s;
     nm_carve(smem_raw, Ccap, Kcap, &s);
     const int CS = Ccap + 1;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* recs = cs.records + (size_t)b * nseg * segcap * HEAD_ROWS;
+    float* recs = cs.records + (size_t)b * nseg * segcap * HEAD_ROWS;
     const int* ancs = cs.anchors + (size_t)b * nseg * segcap;
+    const float* head = heads + (size_t)b * HEAD_ROWS * N;
+    float* o_pose = out.det_poses + (size_t)b * Kcap * POSE_F;
+    float* o_box = out.det_bboxes + (size_t)b * Kcap * 4;
+    float* o_score = out.det_scores + (size_t)b * Kcap;
+    int* o_slot = out.keep_slots + (size_t)b * Kcap;
+    int* o_anchor = out.keep_anchors + (size_t)b * Kcap;
 
     unsigned long long t_stamp = 0;
     if (tid == 0) t_stamp = globaltimer_ns();
@@ -411,6 +424,142 @@ pb_nms_kernel(CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nm
     }
     __syncthreads();
     stamp(1);
+
+    // ---------------- F. fast path: box-only sweep, keypoints for its survivors only ----------------
+    // Greedy suppression by the IoU rule alone (:113-137) over all candidates gives a set S0.  Only S0's
+    // keypoints are then fetched from the head tensor (51 sectors each) and every pair inside S0 is put
+    // through the complete test (:88-172).  If no pair overlaps, S0 IS the reference's result: by
+    // induction in rank order the kept set so far equals S0 so far — a candidate outside S0 has an
+    // earlier member of S0 with IoU > thr and is suppressed by it, a member of S0 overlaps no earlier
+    // member and is kept.  Otherwise (an S0 member would fall to an OKS rule) the kernel fetches the
+    // keypoints of all candidates and runs the complete sweep below.  With 5-9 near-duplicate anchors
+    // per person this skips ~85 % of the keypoint sectors.  Used when the head lives in page-locked host
+    // memory (lazy != 0), where every sector is a PCIe read; with the head in HBM the decode kernel has
+    // already gathered complete records and the complete sweep runs directly.
+    if (lazy) {
+    for (int it = tid; it < C * 4; it += NM_THREADS) {
+        const int r = it >> 2, e = it & 3;
+        s.box[e * CS + r] = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + e];
+    }
+    __syncthreads();
+    for (int r = tid; r < C; r += NM_THREADS) {   // cx,cy,w,h -> corners (:66-69), area (:128)
+        const float cx = s.box[0 * CS + r], cy = s.box[1 * CS + r], w = s.box[2 * CS + r], h = s.box[3 * CS + r];
+        const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f, x2 = cx + w * 0.5f, y2 = cy + h * 0.5f;
+        s.box[0 * CS + r] = x1; s.box[1 * CS + r] = y1; s.box[2 * CS + r] = x2; s.box[3 * CS + r] = y2;
+        s.area[r] = (x2 - x1) * (y2 - y1);
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < C; t0 += 64) {
+        const int tl = (C - t0) < 64 ? (C - t0) : 64;
+        if (tid < 64) s.tmask[tid] = 0ull;
+        __syncthreads();
+        for (int p = tid; p < 2016; p += NM_THREADS) {
+            const unsigned short ab = s.tri[p];
+            const int a = ab >> 8, bb = ab & 0xff;
+            if (bb < tl && !is_sup(s.sup, t0 + a) && !is_sup(s.sup, t0 + bb) && pair_iou(s, CS, t0 + a, t0 + bb) > nms_thr)
+                atomicOr(&s.tmask[a], 1ull << bb);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long supt = (unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32);
+            const unsigned long long valid = (tl == 64) ? ~0ull : ((1ull << tl) - 1ull);
+            unsigned long long rem = valid & ~supt;
+            int nk = s.misc[1], ntk = 0;
+            while (rem != 0ull && nk < Kcap) {
+                const int a = __ffsll((long long)rem) - 1;
+                s.keep[nk++] = t0 + a;
+                s.tk[ntk++] = t0 + a;
+                supt |= s.tmask[a];
+                rem &= ~supt;
+                rem &= ~(1ull << a);
+            }
+            s.sup[t0 >> 5] = (unsigned)supt;
+            s.sup[(t0 >> 5) + 1] = (unsigned)(supt >> 32);
+            s.misc[1] = nk; s.misc[2] = ntk;
+        }
+        __syncthreads();
+        const int ntk = s.misc[2];
+        if (s.misc[1] >= Kcap) break;
+        const int j0 = t0 + 64, rem_n = C - j0;
+        if (rem_n > 0 && ntk > 0) {
+            for (int p = tid; p < ntk * rem_n; p += NM_THREADS) {
+                const int ai = p / rem_n, j = j0 + (p - ai * rem_n);
+                if (!is_sup(s.sup, j) && pair_iou(s, CS, s.tk[ai], j) > nms_thr) atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+            }
+        }
+        __syncthreads();
+    }
+    const int n0 = s.misc[1];
+    stamp(3);
+    for (int it = tid; it < n0 * POSE_F; it += NM_THREADS) {          // keypoints of S0: head -> final place + shared memory
+        const int p = it / POSE_F, e = it - p * POSE_F;
+        const int r = s.keep[p];
+        const float v = ldg_stream_f(head + (size_t)(5 + e) * N + ancs[s.recidx[s.order[r]]]);
+        o_pose[it] = v;                                               // verbatim (:75-80)
+        const int k = e / 3, comp = e - 3 * k;
+        if (comp == 0) s.kx[k * CS + r] = v;
+        else if (comp == 1) s.ky[k * CS + r] = v;
+        else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
+    }
+    __syncthreads();
+    for (int p = tid; p < n0; p += NM_THREADS) {
+        const int r = s.keep[p];
+        float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
+#pragma unroll
+        for (int k = 1; k < KP; ++k) {
+            const float x = s.kx[k * CS + r], y = s.ky[k * CS + r];
+            lx = fminf(lx, x); hx = fmaxf(hx, x); ly = fminf(ly, y); hy = fmaxf(hy, y);
+        }
+        s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
+    }
+    if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; }
+    __syncthreads();
+    stamp(2);
+    for (int pbase = 0; pbase < n0 * n0; pbase += NM_LIST) {          // every pair inside S0 through the complete test
+        for (int p0 = 0; p0 < NM_LIST; p0 += NM_THREADS) {
+            const int idx = pbase + p0 + tid;
+            int q = 0, i = 0, j = 0;
+            if (idx < n0 * n0) {
+                const int pa = idx / n0, pq = idx - pa * n0;
+                if (pa < pq) { i = s.keep[pa]; j = s.keep[pq]; q = nms_stage_a(s, CS, i, j, nms_thr); }
+            }
+            if (q == 1) s.misc[5] = 1;
+            list_push(&s.misc[3], s.l1_key, q == 2, ((unsigned)i << 16) | (unsigned)j);
+        }
+        __syncthreads();
+        resolve_lists<2>(s, CS, 0, nms_thr, tid);
+        if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; }
+        __syncthreads();
+        if (s.misc[5]) break;
+    }
+    stamp(3);
+    if (s.misc[5] == 0) {
+        for (int it = tid; it < n0 * 4; it += NM_THREADS) o_box[it] = s.box[(it & 3) * CS + s.keep[it >> 2]];
+        for (int p = tid; p < n0; p += NM_THREADS) {
+            const int slot = s.order[s.keep[p]];
+            o_score[p] = s.score[slot];
+            o_slot[p] = slot;
+            o_anchor[p] = ancs[s.recidx[slot]];
+        }
+        stamp(4);
+        if (tid == 0) { out.num_keep[b] = n0; out.num_cand[b] = C; s.acc[7] = 1ull; }
+        __syncthreads();
+        if (tid < 16 && s.acc[tid] != 0ull) out.stage_ns[(size_t)b * 16 + tid] += s.acc[tid];
+        return;
+    }
+
+    // ---------------- G. complete path: keypoints of ALL candidates, then the complete sweep ----------------
+    __syncthreads();
+    for (int it = tid; it < C * POSE_F; it += NM_THREADS) {
+        const int c = it / POSE_F, e = it - c * POSE_F;
+        const int ri = s.recidx[c];
+        recs[(size_t)ri * HEAD_ROWS + 5 + e] = ldg_stream_f(head + (size_t)(5 + e) * N + ancs[ri]);
+    }
+    for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.sup[i] = 0u;
+    for (int i = tid; i < Ccap; i += NM_THREADS) s.vis[i] = 0u;
+    if (tid == 0) { s.misc[1] = 0; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.acc[8] += 1ull; }
+    __syncthreads();
+    }   // lazy
 
     // ---------------- 2. records -> shared memory SoA in rank order ----------------
     for (int it = tid; it < C * HEAD_ROWS; it += NM_THREADS) {
@@ -515,11 +664,6 @@ pb_nms_kernel(CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nm
     stamp(3);
 
     // ---------------- 4. kept detections in score order ----------------
-    float* o_pose = out.det_poses + (size_t)b * Kcap * POSE_F;
-    float* o_box = out.det_bboxes + (size_t)b * Kcap * 4;
-    float* o_score = out.det_scores + (size_t)b * Kcap;
-    int* o_slot = out.keep_slots + (size_t)b * Kcap;
-    int* o_anchor = out.keep_anchors + (size_t)b * Kcap;
     for (int it = tid; it < nkeep * POSE_F; it += NM_THREADS) {
         const int k = it / POSE_F, e = it - k * POSE_F;
         o_pose[it] = recs[(size_t)s.recidx[s.order[s.keep[k]]] * HEAD_ROWS + 5 + e];   // verbatim (:75-80)
@@ -557,17 +701,17 @@ DecodePlan decode_plan(int B, int N, int max_cand) {
     return p;
 }
 
-cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, const DecodePlan& plan,
+cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, bool lazy_keypoints, const DecodePlan& plan,
                                  const CandScratch& cs, cudaStream_t stream) {
     const size_t smem1 = (size_t)plan.segcap * sizeof(int);
     pb_decode_gather_kernel<<<dim3(plan.nseg, B), DG_THREADS, smem1, stream>>>(d_heads, N, plan.nseg, plan.groups_per_seg,
-                                                                              plan.segcap, conf_thr, cs);
+                                                                              plan.segcap, conf_thr, lazy_keypoints ? BOX_ROWS : HEAD_ROWS, cs);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_nms(int B, int max_cand, int max_keep, float nms_thr, const DecodePlan& plan, const CandScratch& cs,
-                       const PostBuffers& out, cudaStream_t stream) {
+cudaError_t launch_nms(const float* d_heads, int N, bool lazy_keypoints, int B, int max_cand, int max_keep, float nms_thr,
+                       const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream) {
     const size_t smem2 = decode_nms_smem_bytes(max_cand, max_keep);
     static size_t configured = 0;
     if (smem2 > configured) {
@@ -575,7 +719,7 @@ cudaError_t launch_nms(int B, int max_cand, int max_keep, float nms_thr, const D
         if (e != cudaSuccess) return e;
         configured = smem2;
     }
-    pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out);
+    pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, lazy_keypoints ? 1 : 0, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out);
     count_launch();
     return cudaGetLastError();
 }

@@ -57,6 +57,7 @@ struct pb_handle_st {
     int* h_cnt_pinned = nullptr;   // [B]
     cudaStream_t own_stream = nullptr;
     int frames = 0;
+    bool lazy_keypoints = false;   // set by pb_step_host while the head is read in place from host memory
     // optional per-kernel event timing (pb_set_profiling)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -114,6 +115,7 @@ void pb_default_config(pb_config* c) {
     c->gating_enabled = 1;
     c->device = 0;
     c->pipeline_depth = 1;
+    c->keypoint_fetch = 0;
 }
 
 static int build_handle(pb_handle_st* h) {
@@ -186,6 +188,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     if (c.num_anchors > 65536) { pb_set_error("pb_create: num_anchors > 65536 unsupported"); return PB_ERR_UNSUPPORTED; }
     if (c.max_tracks >= 65536 || c.max_detections >= 65536) { pb_set_error("pb_create: max_tracks/max_detections too large"); return PB_ERR_UNSUPPORTED; }
     if (c.max_keep > c.max_candidates) { pb_set_error("pb_create: max_keep > max_candidates"); return PB_ERR_INVALID; }
+    if (c.keypoint_fetch < 0 || c.keypoint_fetch > 2) { pb_set_error("pb_create: keypoint_fetch must be 0, 1 or 2"); return PB_ERR_INVALID; }
     if (c.pipeline_depth < 1 || c.pipeline_depth > 8) { pb_set_error("pb_create: pipeline_depth must be 1..8"); return PB_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c.device) {
@@ -208,6 +211,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     pb_handle_st* h = new (std::nothrow) pb_handle_st();
     if (!h) { pb_set_error("pb_create: out of host memory"); return PB_ERR_INVALID; }
     h->cfg = c;
+    h->lazy_keypoints = (c.keypoint_fetch == 1);
     int r = build_handle(h);
     if (r != PB_OK) { pb_destroy(h); return r; }
     *out = h;
@@ -262,12 +266,12 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
     PB_TRY(join_on(h, (cudaStream_t)stream));
     int e0 = -1, e1 = -1, em = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
-    PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->dplan, h->cand, (cudaStream_t)stream));
+    PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, h->cand, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (em = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[em], (cudaStream_t)stream);
         h->ev_gather.push_back({e0, em});
     }
-    PB_CUDA(launch_nms(c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
         h->ev_post.push_back({e0, e1});
@@ -321,12 +325,15 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     const int pos = h->inflight || h->ring[h->cur].used ? (h->cur + 1) % (int)h->ring.size() : h->cur;
     PipeSlot& sl = h->ring[pos];
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));          // scratch still being read
-    PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->dplan, sl.cand, stream));
+    PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, sl.cand, stream));
     PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
     PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_trk, 0));        // kept detections still being read
-    PB_CUDA(launch_nms(c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, h->s_nms));
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, h->s_nms));
     PB_CUDA(cudaEventRecord(sl.ev_nms, h->s_nms));
+    // the NMS kernel fetches keypoints from the borrowed head tensor: later work on the caller's
+    // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it
+    PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));
     PB_CUDA(cudaStreamWaitEvent(h->s_trk, sl.ev_nms, 0));
     DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
     PB_CUDA(launch_tracker(h->trk, track_params(c, frame_id), src, h->plan, h->s_trk));
@@ -367,7 +374,11 @@ int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int
         PB_CUDA(cudaMemcpyAsync(h->d_stage, h_heads, head_bytes, cudaMemcpyHostToDevice, s));
         src = h->d_stage;
     }
-    PB_TRY(pb_step(h, src, conf, nms, frame_id, (pb_stream_t)s));
+    const bool lazy_before = h->lazy_keypoints;
+    if (c.keypoint_fetch == 0) h->lazy_keypoints = (src != h->d_stage) && at.type == cudaMemoryTypeHost;
+    const int step_rc = pb_step(h, src, conf, nms, frame_id, (pb_stream_t)s);
+    h->lazy_keypoints = lazy_before;
+    PB_TRY(step_rc);
     PB_TRY(join_on(h, s));
     // results: straight into the caller's buffers when they are page-locked, else via pinned staging
     cudaPointerAttributes ot{}, oc{};
@@ -493,6 +504,19 @@ int pb_get_post_stage_us(pb_handle_t h, double* out5) {
         fprintf(stderr, "[pb] nms us/launch: (unused) %.2f %.2f %.2f %.2f\n",
                 acc[8] / acc[7] / 1e3, acc[9] / acc[7] / 1e3, acc[10] / acc[7] / 1e3, acc[11] / acc[7] / 1e3);
     for (int i = 0; i < 5; ++i) out5[i] = acc[7] > 0 ? acc[i] / acc[7] / 1e3 : 0.0;
+    return PB_OK;
+}
+
+int pb_get_nms_path_counts(pb_handle_t h, long long* fast_path, long long* complete_path) {
+    if (!h) { pb_set_error("pb_get_nms_path_counts: null handle"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    const int B = h->cfg.num_streams;
+    std::vector<unsigned long long> ns((size_t)B * 16);
+    PB_CUDA(cudaMemcpy(ns.data(), h->post.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long fast = 0, full = 0;
+    for (int b = 0; b < B; ++b) { fast += ns[(size_t)b * 16 + 7]; full += ns[(size_t)b * 16 + 8]; }
+    if (fast_path) *fast_path = (long long)fast;
+    if (complete_path) *complete_path = (long long)full;
     return PB_OK;
 }
 

@@ -104,10 +104,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // host-side launchers (defined in the .cu files, called from pb_api.cu)
 size_t decode_nms_smem_bytes(int max_cand, int max_keep);
 DecodePlan decode_plan(int B, int N, int max_cand);
-cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, const DecodePlan& plan,
+cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, bool lazy_keypoints, const DecodePlan& plan,
                                  const CandScratch& cs, cudaStream_t stream);
-cudaError_t launch_nms(int B, int max_cand, int max_keep, float nms_thr, const DecodePlan& plan, const CandScratch& cs,
-                       const PostBuffers& out, cudaStream_t stream);
+cudaError_t launch_nms(const float* d_heads, int N, bool lazy_keypoints, int B, int max_cand, int max_keep, float nms_thr,
+                       const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
 struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats; };
 TrackerPlan tracker_plan(int T, int Dm);
