@@ -514,35 +514,32 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     __syncthreads();
     stamp(2);
 
-    // ---------------- tier 1 (:1210-1274) ----------------
-    if (assoc12) {
-        cost_pass_oks(c, s.gate, na, 0.2f);
-        stamp(12);
-        auction_solve(c, na);
-        stamp(13);
-        lock_pairs(c, s.gate, na);
-        stamp(14);
+    // ---------------- tiers 1-3 (:1210-1274, :1276-1335, :1337-1436) ----------------
+    // One rolled loop: a single copy of the cost passes, the auction and the lock in the instruction
+    // stream (the kernel runs each of them once or a few times per launch, from a cold instruction cache).
+#pragma unroll 1
+    for (int tier = 0; tier < 3; ++tier) {
+        const bool run = (tier < 2) ? assoc12 : (D > 0);
+        if (run) {
+            if (tier > 0) backup_assign(c);
+            if (tier == 0) {
+                cost_pass_oks(c, s.gate, na, 0.2f);
+                stamp(12);
+            } else if (tier == 1) {
+                cost_pass_torso(c, s.gate, na);
+            } else {
+                cost_inactive_rows(c);
+                lock_pairs(c, s.lgate, na);
+                cost_pass_oks(c, s.lgate, na, 0.2f);
+            }
+            auction_solve(c, na);
+            if (tier == 0) stamp(13);
+            if (tier > 0) merge_assign(c);
+            if (tier < 2) lock_pairs(c, s.gate, na);
+            if (tier == 0) stamp(14);
+        }
+        stamp(3 + tier);
     }
-    stamp(3);
-    // ---------------- tier 2 (:1276-1335) ----------------
-    if (assoc12) {
-        backup_assign(c);
-        cost_pass_torso(c, s.gate, na);
-        auction_solve(c, na);
-        merge_assign(c);
-        lock_pairs(c, s.gate, na);
-    }
-    stamp(4);
-    // ---------------- tier 3 (:1337-1436) ----------------
-    if (D > 0) {
-        backup_assign(c);
-        cost_inactive_rows(c);
-        lock_pairs(c, s.lgate, na);
-        cost_pass_oks(c, s.lgate, na, 0.2f);
-        auction_solve(c, na);
-        merge_assign(c);
-    }
-    stamp(5);
 
     // ---------------- update matched (:1438-1472, kernels :141-189, :612-648) -------------
     if (D > 0) {
