@@ -55,9 +55,9 @@ typedef struct pb_config {
     int device;              /* CUDA device ordinal */
     int pipeline_depth;      /* 1: pb_step runs entirely on the caller's stream.  2..8: pb_step
                               * overlaps consecutive steps on internal streams (see pb_join) */
-    int keypoint_fetch;      /* 0 (default): the NMS kernel fetches keypoints lazily (box-only sweep first,
-                              * keypoints for its survivors only) iff the head is read in place from host
-                              * memory (pb_step_host); 1: always lazy; 2: never */
+    int keypoint_fetch;      /* 0 (default): the NMS kernel fetches keypoints lazily (IoU rule first, keypoints
+                              * only for the ranks whose OKS tests are unavoidable) iff the head is read in
+                              * place from host memory (pb_step_host); 1: always lazy; 2: never */
 } pb_config;
 
 /* TrackerTiming (gpu_tracker.h:29-41), filled from device timestamps. */
@@ -169,9 +169,10 @@ int pb_set_profiling(pb_handle_t h, int enabled);
 /* Mean microseconds per launch and stream of the decode+NMS kernel's stages since creation
  * (in-kernel timestamps): scan+compaction, ranking, gather, suppression, output. */
 int pb_get_post_stage_us(pb_handle_t h, double* out5);
-/* How many stream-frames the NMS kernel finished on its fast path (keypoints fetched only for the
- * survivors of the box-only sweep) and how many needed the complete path, since creation. */
-int pb_get_nms_path_counts(pb_handle_t h, long long* fast_path, long long* complete_path);
+/* Lazy-sweep telemetry since creation: stream-frames processed by the NMS kernel, and how many
+ * 64-rank tiles needed their second round (keypoints fetched for every live rank of the tile
+ * because a speculative survivor fell to an OKS rule). */
+int pb_get_nms_path_counts(pb_handle_t h, long long* stream_frames, long long* second_rounds);
 int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_launches, double* track_ms, int* track_launches);
 /* Same record as mean microseconds per launch of each of the three kernels (decode+gather, NMS,
  * tracker); clears the record. */

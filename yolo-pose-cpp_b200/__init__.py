@@ -281,10 +281,11 @@ class Pipeline:
         return out
 
     def nms_path_counts(self) -> dict:
-        """Stream-frames finished on the NMS fast path / total that needed the complete path."""
+        """Stream-frames the NMS kernel processed, and how many 64-rank tiles of the lazy sweep
+        needed their second round (keypoints for every live rank)."""
         f, c = C.c_longlong(0), C.c_longlong(0)
         check(lib().pb_get_nms_path_counts(self._h, C.byref(f), C.byref(c)))
-        return dict(fast=f.value - c.value, complete=c.value)
+        return dict(stream_frames=f.value, second_rounds=c.value)
 
     def kernel_us(self) -> dict:
         """Mean device microseconds per launch of the three kernels since the last call (needs set_profiling(True))."""

@@ -185,6 +185,9 @@ struct NmSmem {
     float* terms;      // [NM_TERM_PAIRS * 17]
     float* sig;        // [17]
     unsigned short* tri;  // [2016] (a << 8 | b) for a < b < 64
+    unsigned* have;    // [Ccap/32 + 2] lazy sweep: keypoints of this rank are in shared memory
+    int* fl;           // [64] lazy sweep: ranks to fetch / to test
+    unsigned long long* spec;   // [2] lazy sweep: ranks of the current tile with keypoints fetched / added in this attempt
 };
 
 __host__ __device__ inline size_t nm_align(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -200,6 +203,7 @@ __host__ __device__ inline size_t nm_carve(unsigned char* base, int Ccap, int Kc
     const size_t o_sup = take((size_t)((Ccap + 31) / 32) * 4 + 8), o_keep = take((size_t)Kcap * 4), o_tk = take(64 * 4), o_misc = take(16 * 4);
     const size_t o_l1k = take(NM_LIST * 4), o_l2k = take(NM_LIST * 4);
     const size_t o_terms = take((size_t)NM_TERM_PAIRS * KP * 4), o_sig = take(KP * 4), o_tri = take(2016 * 2);
+    const size_t o_have = take((size_t)((Ccap + 31) / 32) * 4 + 8), o_fl = take(64 * 4), o_spec = take(16);
     if (s) {
         s->tmask = (unsigned long long*)(base + o_tmask); s->acc = (unsigned long long*)(base + o_acc);
         s->score = (float*)(base + o_score); s->recidx = (int*)(base + o_rec); s->order = (int*)(base + o_order);
@@ -211,6 +215,7 @@ __host__ __device__ inline size_t nm_carve(unsigned char* base, int Ccap, int Kc
         s->l1_key = (unsigned*)(base + o_l1k); s->l2_key = (unsigned*)(base + o_l2k);
         s->terms = (float*)(base + o_terms); s->sig = (float*)(base + o_sig);
         s->tri = (unsigned short*)(base + o_tri);
+        s->have = (unsigned*)(base + o_have); s->fl = (int*)(base + o_fl); s->spec = (unsigned long long*)(base + o_spec);
     }
     return off;
 }
@@ -425,22 +430,29 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     __syncthreads();
     stamp(1);
 
-    // ---------------- F. fast path: box-only sweep, keypoints for its survivors only ----------------
-    // Greedy suppression by the IoU rule alone (:113-137) over all candidates gives a set S0.  Only S0's
-    // keypoints are then fetched from the head tensor (51 sectors each) and every pair inside S0 is put
-    // through the complete test (:88-172).  If no pair overlaps, S0 IS the reference's result: by
-    // induction in rank order the kept set so far equals S0 so far — a candidate outside S0 has an
-    // earlier member of S0 with IoU > thr and is suppressed by it, a member of S0 overlaps no earlier
-    // member and is kept.  Otherwise (an S0 member would fall to an OKS rule) the kernel fetches the
-    // keypoints of all candidates and runs the complete sweep below.  With 5-9 near-duplicate anchors
-    // per person this skips ~85 % of the keypoint sectors.  Used when the head lives in page-locked host
-    // memory (lazy != 0), where every sector is a PCIe read; with the head in HBM the decode kernel has
-    // already gathered complete records and the complete sweep runs directly.
+    // ---------------- L. lazy sweep: IoU first, keypoints only where an OKS test is unavoidable ----------------
+    // Same result as the complete sweep below (sections 2-3), different evaluation order.  A candidate
+    // needs its keypoints only if no kept candidate removes it by the IoU rule (:113-137) — with 5-9
+    // near-duplicate anchors per person that is ~15 % of the candidates — so the decode kernel has
+    // gathered box rows only and keypoints are fetched from the head tensor here, on demand.  Used when
+    // the head lives in page-locked host memory (every sector is a PCIe read).  Per tile of 64 ranks:
+    //   live   = tile ranks no kept candidate of an earlier tile removes by IoU (struck eagerly, step 5);
+    //   round 1: S = survivors of a box-only greedy pass over live; fetch S's keypoints; complete tests of
+    //            S against every earlier kept candidate and inside S; walk the tile in rank order: a
+    //            member of S is kept unless struck; a live rank outside S must be struck by a kept rank
+    //            of this tile — if one is not (the rank that shadowed it fell to an OKS rule), round 1 is
+    //            abandoned;
+    //   round 2: fetch the keypoints of all live ranks and decide the tile with every pair tested, exactly
+    //            as the complete sweep does.
+    // Every decision is the one the reference's sweep takes (:209-242): a rank is dropped only when a
+    // kept earlier rank overlaps it by the complete rule, kept only when all kept earlier ranks were
+    // tested against it.
     if (lazy) {
     for (int it = tid; it < C * 4; it += NM_THREADS) {
         const int r = it >> 2, e = it & 3;
         s.box[e * CS + r] = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + e];
     }
+    for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.have[i] = 0u;
     __syncthreads();
     for (int r = tid; r < C; r += NM_THREADS) {   // cx,cy,w,h -> corners (:66-69), area (:128)
         const float cx = s.box[0 * CS + r], cy = s.box[1 * CS + r], w = s.box[2 * CS + r], h = s.box[3 * CS + r];
@@ -449,37 +461,201 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         s.area[r] = (x2 - x1) * (y2 - y1);
     }
     __syncthreads();
+    stamp(2);
+    // fetch the keypoints of the ranks listed in s.fl[0..nf): head -> candidate record (for the output
+    // stage) + shared memory (rank-indexed), then their keypoint extents
+    auto fetch_list = [&](int nf) {
+        for (int it = tid; it < nf * POSE_F; it += NM_THREADS) {
+            const int p = it / POSE_F, e = it - p * POSE_F;
+            const int r = s.fl[p];
+            const int ri = s.recidx[s.order[r]];
+            const float v = ldg_stream_f(head + (size_t)(5 + e) * N + ancs[ri]);
+            recs[(size_t)ri * HEAD_ROWS + 5 + e] = v;                 // verbatim (:75-80)
+            const int k = e / 3, comp = e - 3 * k;
+            if (comp == 0) s.kx[k * CS + r] = v;
+            else if (comp == 1) s.ky[k * CS + r] = v;
+            else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
+        }
+        __syncthreads();
+        for (int p = tid; p < nf; p += NM_THREADS) {
+            const int r = s.fl[p];
+            float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
+#pragma unroll
+            for (int k = 1; k < KP; ++k) {
+                const float x = s.kx[k * CS + r], y = s.ky[k * CS + r];
+                lx = fminf(lx, x); hx = fmaxf(hx, x); ly = fminf(ly, y); hy = fmaxf(hy, y);
+            }
+            s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
+            atomicOr(&s.have[r >> 5], 1u << (r & 31));
+        }
+        __syncthreads();
+    };
+    // complete tests of the ranks in s.fl[0..nf) against the kept candidates keep[0..nk): IoU is known to
+    // be <= thr for these pairs (the eager IoU strikes), the OKS rules may still remove the later rank
+    auto cross_tests = [&](int nf, int nk) {
+        const int pairs = nf * nk;
+        for (int pbase = 0; pbase < pairs; pbase += NM_LIST) {
+            const int pend = (pairs - pbase) < NM_LIST ? (pairs - pbase) : NM_LIST;
+            for (int p0 = 0; p0 < pend; p0 += NM_THREADS) {
+                int q = 0, i = 0, j = 0;
+                if (p0 + tid < pend) {
+                    const int p = pbase + p0 + tid;
+                    const int a = p / nf;
+                    i = s.keep[a]; j = s.fl[p - a * nf];
+                    if (!is_sup(s.sup, j)) q = nms_stage_a(s, CS, i, j, nms_thr);
+                }
+                if (q == 1) atomicOr(&s.sup[j >> 5], 1u << (j & 31));
+                list_push(&s.misc[3], s.l1_key, q == 2, ((unsigned)i << 16) | (unsigned)j);
+            }
+            __syncthreads();
+            resolve_lists<1>(s, CS, 0, nms_thr, tid);
+            if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; }
+            __syncthreads();
+        }
+    };
     for (int t0 = 0; t0 < C; t0 += 64) {
         const int tl = (C - t0) < 64 ? (C - t0) : 64;
+        const int nk0 = s.misc[1];                                    // kept before this tile
         if (tid < 64) s.tmask[tid] = 0ull;
+        if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; }
         __syncthreads();
+        const unsigned long long valid = (tl == 64) ? ~0ull : ((1ull << tl) - 1ull);
+        const unsigned long long live = valid & ~((unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32));
+        // (1) IoU mask among the live ranks of the tile
         for (int p = tid; p < 2016; p += NM_THREADS) {
             const unsigned short ab = s.tri[p];
             const int a = ab >> 8, bb = ab & 0xff;
-            if (bb < tl && !is_sup(s.sup, t0 + a) && !is_sup(s.sup, t0 + bb) && pair_iou(s, CS, t0 + a, t0 + bb) > nms_thr)
+            if (((live >> a) & 1ull) && ((live >> bb) & 1ull) && pair_iou(s, CS, t0 + a, t0 + bb) > nms_thr)
                 atomicOr(&s.tmask[a], 1ull << bb);
         }
         __syncthreads();
+        // (2) round 1: speculative box-only greedy pass -> S
         if (tid == 0) {
-            unsigned long long supt = (unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32);
-            const unsigned long long valid = (tl == 64) ? ~0ull : ((1ull << tl) - 1ull);
-            unsigned long long rem = valid & ~supt;
-            int nk = s.misc[1], ntk = 0;
-            while (rem != 0ull && nk < Kcap) {
+            unsigned long long rem = live, spec = 0ull;
+            int room = Kcap - nk0;
+            while (rem != 0ull && room > 0) {
                 const int a = __ffsll((long long)rem) - 1;
-                s.keep[nk++] = t0 + a;
-                s.tk[ntk++] = t0 + a;
-                supt |= s.tmask[a];
-                rem &= ~supt;
+                spec |= 1ull << a;
+                --room;
+                rem &= ~s.tmask[a];
                 rem &= ~(1ull << a);
             }
-            s.sup[t0 >> 5] = (unsigned)supt;
-            s.sup[(t0 >> 5) + 1] = (unsigned)(supt >> 32);
-            s.misc[1] = nk; s.misc[2] = ntk;
+            s.spec[0] = spec;          // ranks whose keypoints are (being) fetched
+            s.spec[1] = spec;          // the ones added in this attempt
         }
         __syncthreads();
+        // Two attempts: S, then S plus every rank the walk found unshadowed together with the ranks it
+        // shadows itself (its own near-duplicates, which are needed as soon as it falls too).
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const unsigned long long spec = s.spec[0], added = s.spec[1];
+            if (tid == 0) {
+                int n = 0;
+                for (unsigned long long m = added; m; m &= m - 1ull) s.fl[n++] = t0 + __ffsll((long long)m) - 1;
+                s.misc[6] = n;
+            }
+            __syncthreads();
+            const int na_ = s.misc[6];
+            fetch_list(na_);
+            cross_tests(na_, nk0);                                    // (3) the added ranks against every earlier kept candidate
+            // (4) pairs inside the fetched set that involve an added rank: IoU is in the mask already, the OKS rules may fire
+            for (int p0 = 0; p0 < 2016; p0 += NM_THREADS) {
+                const int p = p0 + tid;
+                int q = 0, a = 0, bb = 0;
+                if (p < 2016) {
+                    const unsigned short ab = s.tri[p];
+                    a = ab >> 8; bb = ab & 0xff;
+                    if (((spec >> a) & 1ull) && ((spec >> bb) & 1ull) && (((added >> a) | (added >> bb)) & 1ull) &&
+                        !((s.tmask[a] >> bb) & 1ull) && !is_sup(s.sup, t0 + a) && !is_sup(s.sup, t0 + bb))
+                        q = nms_stage_a(s, CS, t0 + a, t0 + bb, nms_thr);
+                }
+                list_push(&s.misc[3], s.l1_key, q == 2, ((unsigned)(t0 + a) << 16) | (unsigned)(t0 + bb));
+            }
+            __syncthreads();
+            resolve_lists<0>(s, CS, t0, nms_thr, tid);
+            // (5) walk the tile in rank order
+            if (tid == 0) {
+                unsigned long long supt = (unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32);
+                unsigned long long extra = 0ull;
+                int nk = nk0, ntk = 0;
+                for (unsigned long long m = live; m && nk < Kcap; m &= m - 1ull) {
+                    const int a = __ffsll((long long)m) - 1;
+                    if ((supt >> a) & 1ull) continue;                // struck: by an earlier tile (OKS) or by a kept rank of this tile
+                    if (!((spec >> a) & 1ull)) {                     // shadowed only by a rank that fell: needs its own tests,
+                        extra |= (1ull << a) | (s.tmask[a] & live);  // and so may the ranks it shadows itself
+                        supt |= s.tmask[a];
+                        continue;
+                    }
+                    s.keep[nk++] = t0 + a;
+                    s.tk[ntk++] = t0 + a;
+                    supt |= s.tmask[a];
+                }
+                extra &= ~spec;
+                s.misc[7] = (extra != 0ull) ? 1 : 0;
+                if (extra == 0ull) {
+                    s.sup[t0 >> 5] = (unsigned)(supt | ~live);
+                    s.sup[(t0 >> 5) + 1] = (unsigned)((supt | ~live) >> 32);
+                    s.misc[1] = nk; s.misc[2] = ntk;
+                } else {
+                    s.spec[0] = spec | extra;
+                    s.spec[1] = extra;
+                }
+                s.misc[3] = 0; s.misc[4] = 0;
+            }
+            __syncthreads();
+            if (!s.misc[7]) break;
+        }
+        if (s.misc[7]) {
+            // round 2: keypoints for every live rank, every pair tested (the complete sweep's tile step)
+            if (tid == 0) {
+                int nf = 0;
+                for (unsigned long long m = live; m; m &= m - 1ull) {
+                    const int a = __ffsll((long long)m) - 1;
+                    if (!is_sup(s.have, t0 + a)) s.fl[nf++] = t0 + a;
+                }
+                s.misc[6] = nf;
+                s.acc[8] += 1ull;
+            }
+            __syncthreads();
+            const int nf2 = s.misc[6];
+            fetch_list(nf2);
+            cross_tests(nf2, nk0);                                    // the newly fetched ranks against the earlier kept
+            if (tid < 64) s.tmask[tid] = 0ull;
+            __syncthreads();
+            for (int p0 = 0; p0 < 2016; p0 += NM_THREADS) {
+                const int p = p0 + tid;
+                int q = 0, a = 0, bb = 0;
+                if (p < 2016) {
+                    const unsigned short ab = s.tri[p];
+                    a = ab >> 8; bb = ab & 0xff;
+                    if (bb < tl && !is_sup(s.sup, t0 + a) && !is_sup(s.sup, t0 + bb))
+                        q = nms_stage_a(s, CS, t0 + a, t0 + bb, nms_thr);
+                }
+                if (q == 1) atomicOr(&s.tmask[a], 1ull << bb);
+                list_push(&s.misc[3], s.l1_key, q == 2, ((unsigned)(t0 + a) << 16) | (unsigned)(t0 + bb));
+            }
+            __syncthreads();
+            resolve_lists<0>(s, CS, t0, nms_thr, tid);
+            if (tid == 0) {
+                unsigned long long supt = (unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32);
+                unsigned long long rem = valid & ~supt;
+                int nk = nk0, ntk = 0;
+                while (rem != 0ull && nk < Kcap) {                   // :224 "num_keep < 256"
+                    const int a = __ffsll((long long)rem) - 1;
+                    s.keep[nk++] = t0 + a;
+                    s.tk[ntk++] = t0 + a;
+                    supt |= s.tmask[a];
+                    rem &= ~supt;
+                    rem &= ~(1ull << a);
+                }
+                s.sup[t0 >> 5] = (unsigned)supt;
+                s.sup[(t0 >> 5) + 1] = (unsigned)(supt >> 32);
+                s.misc[1] = nk; s.misc[2] = ntk; s.misc[3] = 0; s.misc[4] = 0;
+            }
+            __syncthreads();
+        }
         const int ntk = s.misc[2];
         if (s.misc[1] >= Kcap) break;
+        // (6) the tile's kept ranks strike the later ranks by the IoU rule (their OKS tests wait for the keypoints)
         const int j0 = t0 + 64, rem_n = C - j0;
         if (rem_n > 0 && ntk > 0) {
             for (int p = tid; p < ntk * rem_n; p += NM_THREADS) {
@@ -489,77 +665,9 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         }
         __syncthreads();
     }
-    const int n0 = s.misc[1];
+    __syncthreads();
     stamp(3);
-    for (int it = tid; it < n0 * POSE_F; it += NM_THREADS) {          // keypoints of S0: head -> final place + shared memory
-        const int p = it / POSE_F, e = it - p * POSE_F;
-        const int r = s.keep[p];
-        const float v = ldg_stream_f(head + (size_t)(5 + e) * N + ancs[s.recidx[s.order[r]]]);
-        o_pose[it] = v;                                               // verbatim (:75-80)
-        const int k = e / 3, comp = e - 3 * k;
-        if (comp == 0) s.kx[k * CS + r] = v;
-        else if (comp == 1) s.ky[k * CS + r] = v;
-        else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
-    }
-    __syncthreads();
-    for (int p = tid; p < n0; p += NM_THREADS) {
-        const int r = s.keep[p];
-        float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
-#pragma unroll
-        for (int k = 1; k < KP; ++k) {
-            const float x = s.kx[k * CS + r], y = s.ky[k * CS + r];
-            lx = fminf(lx, x); hx = fmaxf(hx, x); ly = fminf(ly, y); hy = fmaxf(hy, y);
-        }
-        s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
-    }
-    if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; }
-    __syncthreads();
-    stamp(2);
-    for (int pbase = 0; pbase < n0 * n0; pbase += NM_LIST) {          // every pair inside S0 through the complete test
-        for (int p0 = 0; p0 < NM_LIST; p0 += NM_THREADS) {
-            const int idx = pbase + p0 + tid;
-            int q = 0, i = 0, j = 0;
-            if (idx < n0 * n0) {
-                const int pa = idx / n0, pq = idx - pa * n0;
-                if (pa < pq) { i = s.keep[pa]; j = s.keep[pq]; q = nms_stage_a(s, CS, i, j, nms_thr); }
-            }
-            if (q == 1) s.misc[5] = 1;
-            list_push(&s.misc[3], s.l1_key, q == 2, ((unsigned)i << 16) | (unsigned)j);
-        }
-        __syncthreads();
-        resolve_lists<2>(s, CS, 0, nms_thr, tid);
-        if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; }
-        __syncthreads();
-        if (s.misc[5]) break;
-    }
-    stamp(3);
-    if (s.misc[5] == 0) {
-        for (int it = tid; it < n0 * 4; it += NM_THREADS) o_box[it] = s.box[(it & 3) * CS + s.keep[it >> 2]];
-        for (int p = tid; p < n0; p += NM_THREADS) {
-            const int slot = s.order[s.keep[p]];
-            o_score[p] = s.score[slot];
-            o_slot[p] = slot;
-            o_anchor[p] = ancs[s.recidx[slot]];
-        }
-        stamp(4);
-        if (tid == 0) { out.num_keep[b] = n0; out.num_cand[b] = C; s.acc[7] = 1ull; }
-        __syncthreads();
-        if (tid < 16 && s.acc[tid] != 0ull) out.stage_ns[(size_t)b * 16 + tid] += s.acc[tid];
-        return;
-    }
-
-    // ---------------- G. complete path: keypoints of ALL candidates, then the complete sweep ----------------
-    __syncthreads();
-    for (int it = tid; it < C * POSE_F; it += NM_THREADS) {
-        const int c = it / POSE_F, e = it - c * POSE_F;
-        const int ri = s.recidx[c];
-        recs[(size_t)ri * HEAD_ROWS + 5 + e] = ldg_stream_f(head + (size_t)(5 + e) * N + ancs[ri]);
-    }
-    for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.sup[i] = 0u;
-    for (int i = tid; i < Ccap; i += NM_THREADS) s.vis[i] = 0u;
-    if (tid == 0) { s.misc[1] = 0; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.acc[8] += 1ull; }
-    __syncthreads();
-    }   // lazy
+    } else {
 
     // ---------------- 2. records -> shared memory SoA in rank order ----------------
     for (int it = tid; it < C * HEAD_ROWS; it += NM_THREADS) {
@@ -591,7 +699,6 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     stamp(2);
 
     // ---------------- 3. greedy suppression in rank order (:88-172 + :209-242) ----------------
-    int nkeep = 0;
     for (int t0 = 0; t0 < C; t0 += 64) {
         const int tl = (C - t0) < 64 ? (C - t0) : 64;
         if (tid < 64) s.tmask[tid] = 0ull;
@@ -631,9 +738,8 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             s.misc[1] = nk; s.misc[2] = ntk; s.misc[3] = 0; s.misc[4] = 0;
         }
         __syncthreads();
-        nkeep = s.misc[1];
         const int ntk = s.misc[2];
-        if (nkeep >= Kcap) break;
+        if (s.misc[1] >= Kcap) break;
         // (c) the tile's survivors strike the remaining ranks, NM_LIST candidate pairs per round
         const int j0 = t0 + 64, rem_n = C - j0;
         if (rem_n > 0 && ntk > 0) {
@@ -660,8 +766,9 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         }
     }
     __syncthreads();
-    nkeep = s.misc[1];
     stamp(3);
+    }   // complete sweep
+    const int nkeep = s.misc[1];
 
     // ---------------- 4. kept detections in score order ----------------
     for (int it = tid; it < nkeep * POSE_F; it += NM_THREADS) {
