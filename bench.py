@@ -312,6 +312,7 @@ def main():
     for i in range(3):
         pipe.step_host(pinned_np[i % nf], f, CONF, NMS, out=out_np, counts=cnt_np); f += 1
     barrier()
+    paths0 = pipe.nms_path_counts()
     t0 = time.perf_counter()
     e2e_tracks = 0
     for i in range(args.e2e_steps):
@@ -320,6 +321,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    paths1 = pipe.nms_path_counts()
+    kp_fetch_mean = (paths1["keypoint_fetches"] - paths0["keypoint_fetches"]) / max(B * args.e2e_steps, 1)
     cand_mean = float(np.mean([pipe.get_kept(b)["num_cand"] for b in range(min(B, 8))]))
 
     # ---------------- max over ranks + final statistics gather (the only collective) ----------------
@@ -375,11 +378,13 @@ def main():
         "roofline_step": {"bound": "hbm", "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
                           "bytes_per_stream_frame": BYTES_PER_STREAM_FRAME, "note": "whole step per GPU, SURVEY.md 8(d) dense-read figure"},
         "e2e": {"value": e2e_value, "unit": "stream-frames/s",
-                "h2d_bytes_per_step": int(B * (4 * N_ANCHORS + 55 * 32 * cand_mean)),
+                "h2d_bytes_per_step": int(B * (4 * N_ANCHORS + 4 * 32 * cand_mean + 51 * 32 * kp_fetch_mean)),
+                "keypoint_fetches_per_stream_frame": kp_fetch_mean,
                 "host_input_bytes_per_step": B * 56 * N_ANCHORS * 4,
                 "d2h_bytes_per_step": B * DM * 228 + B * 4, "steps": args.e2e_steps,
-                "api": "pb_step_host: page-locked host heads [B,56,N] read in place by the decode kernel over PCIe (confidence rows + 32 B sectors at "
-                       "candidate anchors = h2d_bytes_per_step; the buffer itself is host_input_bytes_per_step), TrackOutput records copied back"},
+                "api": "pb_step_host: page-locked host heads [B,56,N] read in place over PCIe — confidence rows, 32 B sectors of the 4 box rows at every "
+                       "candidate anchor and of the 51 keypoint rows at the candidates the lazy NMS sweep has to test (= h2d_bytes_per_step; the buffer "
+                       "itself is host_input_bytes_per_step); TrackOutput records copied back into page-locked memory"},
         "gpu_launches": int(allstats[0, 2]),
         "clocks": clocks,
         "tracks_per_stream_frame": n_out_mean,

@@ -172,7 +172,8 @@ int pb_get_post_stage_us(pb_handle_t h, double* out5);
 /* Lazy-sweep telemetry since creation: stream-frames processed by the NMS kernel, and how many
  * 64-rank tiles needed their second round (keypoints fetched for every live rank of the tile
  * because a speculative survivor fell to an OKS rule). */
-int pb_get_nms_path_counts(pb_handle_t h, long long* stream_frames, long long* second_rounds);
+int pb_get_nms_path_counts(pb_handle_t h, long long* stream_frames, long long* second_rounds,
+                           long long* keypoint_fetches /* candidates whose 51 keypoint values were fetched */);
 int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_launches, double* track_ms, int* track_launches);
 /* Same record as mean microseconds per launch of each of the three kernels (decode+gather, NMS,
  * tracker); clears the record. */

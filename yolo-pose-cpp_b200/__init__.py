@@ -111,7 +111,7 @@ def lib() -> C.CDLL:
         L.pb_get_post_stage_us.argtypes = [vp, C.POINTER(C.c_double * 5)]
         L.pb_set_profiling.argtypes = [vp, ip]
         L.pb_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip), C.POINTER(C.c_double), C.POINTER(ip)]
-        L.pb_get_nms_path_counts.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.pb_get_nms_path_counts.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.pb_get_kernel_us.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ip)]
         L.launchPoseNMS.argtypes = [vp, vp, vp, vp, ip, ip, fp, fp, vp]
         L.pb_nms_legacy.argtypes = [vp, vp, ip, ip, fp, fp, vp, vp, vp]
@@ -283,9 +283,9 @@ class Pipeline:
     def nms_path_counts(self) -> dict:
         """Stream-frames the NMS kernel processed, and how many 64-rank tiles of the lazy sweep
         needed their second round (keypoints for every live rank)."""
-        f, c = C.c_longlong(0), C.c_longlong(0)
-        check(lib().pb_get_nms_path_counts(self._h, C.byref(f), C.byref(c)))
-        return dict(stream_frames=f.value, second_rounds=c.value)
+        f, c, k = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        check(lib().pb_get_nms_path_counts(self._h, C.byref(f), C.byref(c), C.byref(k)))
+        return dict(stream_frames=f.value, second_rounds=c.value, keypoint_fetches=k.value)
 
     def kernel_us(self) -> dict:
         """Mean device microseconds per launch of the three kernels since the last call (needs set_profiling(True))."""

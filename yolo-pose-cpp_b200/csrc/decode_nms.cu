@@ -39,9 +39,11 @@ constexpr int DG_WARPS = DG_THREADS / 32;
 constexpr int DG_MAX_CHUNKS = 16;            // float4 groups per segment <= 16 * 256
 constexpr int BOX_ROWS = 5;                  // cx, cy, w, h, confidence
 
+template <int ROWS>
 __global__ void __launch_bounds__(DG_THREADS)
 pb_decode_gather_kernel(const float* __restrict__ heads, int N, int nseg, int groups_per_seg, int segcap,
-                        float conf_thr, int rows, CandScratch cs) {
+                        float conf_thr, CandScratch cs) {
+    constexpr int rows = ROWS;
     __shared__ int s_cnt[DG_MAX_CHUNKS * DG_WARPS];
     __shared__ int s_total;
     extern __shared__ int s_anchor[];            // [segcap]
@@ -488,6 +490,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
             atomicOr(&s.have[r >> 5], 1u << (r & 31));
         }
+        if (tid == 0) s.acc[9] += (unsigned long long)nf;
         __syncthreads();
     };
     // complete tests of the ranks in s.fl[0..nf) against the kept candidates keep[0..nk): IoU is known to
@@ -811,8 +814,12 @@ DecodePlan decode_plan(int B, int N, int max_cand) {
 cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, bool lazy_keypoints, const DecodePlan& plan,
                                  const CandScratch& cs, cudaStream_t stream) {
     const size_t smem1 = (size_t)plan.segcap * sizeof(int);
-    pb_decode_gather_kernel<<<dim3(plan.nseg, B), DG_THREADS, smem1, stream>>>(d_heads, N, plan.nseg, plan.groups_per_seg,
-                                                                              plan.segcap, conf_thr, lazy_keypoints ? BOX_ROWS : HEAD_ROWS, cs);
+    if (lazy_keypoints)
+        pb_decode_gather_kernel<BOX_ROWS><<<dim3(plan.nseg, B), DG_THREADS, smem1, stream>>>(d_heads, N, plan.nseg, plan.groups_per_seg,
+                                                                                            plan.segcap, conf_thr, cs);
+    else
+        pb_decode_gather_kernel<HEAD_ROWS><<<dim3(plan.nseg, B), DG_THREADS, smem1, stream>>>(d_heads, N, plan.nseg, plan.groups_per_seg,
+                                                                                             plan.segcap, conf_thr, cs);
     count_launch();
     return cudaGetLastError();
 }

@@ -507,16 +507,17 @@ int pb_get_post_stage_us(pb_handle_t h, double* out5) {
     return PB_OK;
 }
 
-int pb_get_nms_path_counts(pb_handle_t h, long long* fast_path, long long* complete_path) {
+int pb_get_nms_path_counts(pb_handle_t h, long long* fast_path, long long* complete_path, long long* keypoint_fetches) {
     if (!h) { pb_set_error("pb_get_nms_path_counts: null handle"); return PB_ERR_INVALID; }
     PB_CUDA(cudaDeviceSynchronize());
     const int B = h->cfg.num_streams;
     std::vector<unsigned long long> ns((size_t)B * 16);
     PB_CUDA(cudaMemcpy(ns.data(), h->post.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
-    unsigned long long fast = 0, full = 0;
-    for (int b = 0; b < B; ++b) { fast += ns[(size_t)b * 16 + 7]; full += ns[(size_t)b * 16 + 8]; }
+    unsigned long long fast = 0, full = 0, fetched = 0;
+    for (int b = 0; b < B; ++b) { fast += ns[(size_t)b * 16 + 7]; full += ns[(size_t)b * 16 + 8]; fetched += ns[(size_t)b * 16 + 9]; }
     if (fast_path) *fast_path = (long long)fast;
     if (complete_path) *complete_path = (long long)full;
+    if (keypoint_fetches) *keypoint_fetches = (long long)fetched;
     return PB_OK;
 }
 
