@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-per-gpu", type=int, default=STREAMS_PER_GPU)
-    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--pipeline-depth", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -305,19 +305,28 @@ def main():
     nf = min(PERIOD, 8)
     pinned = torch.from_numpy(host_heads[:nf]).pin_memory()
     pinned_np = pinned.numpy()
-    out_p = torch.zeros(B * DM * 228, dtype=torch.uint8).pin_memory()
-    cnt_p = torch.zeros(B, dtype=torch.int32).pin_memory()
-    out_np = out_p.numpy().view(pb.TRACK_OUTPUT).reshape(B, DM)
-    cnt_np = cnt_p.numpy()
-    for i in range(3):
-        pipe.step_host(pinned_np[i % nf], f, CONF, NMS, out=out_np, counts=cnt_np); f += 1
+    R = 4                                         # ring of page-locked result buffers, results consumed every R steps
+    out_p = torch.zeros(R, B * DM * 228, dtype=torch.uint8).pin_memory()
+    cnt_p = torch.zeros(R, B, dtype=torch.int32).pin_memory()
+    out_np = [out_p[i].numpy().view(pb.TRACK_OUTPUT).reshape(B, DM) for i in range(R)]
+    cnt_np = [cnt_p[i].numpy() for i in range(R)]
+
+    def e2e_run(nsteps, f0):
+        """pb_submit_host per step (in-place PCIe read of the heads, records copied back), pb_wait and a
+        host-side read of every step's counts every R steps."""
+        tracks = 0
+        for i in range(nsteps):
+            pipe.submit_host(pinned_np[i % nf], f0 + i, out_np[i % R], cnt_np[i % R], CONF, NMS)
+            if (i + 1) % R == 0 or i == nsteps - 1:
+                pipe.wait()
+                tracks += int(sum(int(c.sum()) for c in cnt_np[: (i % R) + 1]))
+        return tracks
+
+    e2e_run(4, f); f += 4
     barrier()
     paths0 = pipe.nms_path_counts()
     t0 = time.perf_counter()
-    e2e_tracks = 0
-    for i in range(args.e2e_steps):
-        pipe.step_host(pinned_np[i % nf], f, CONF, NMS, out=out_np, counts=cnt_np); f += 1
-        e2e_tracks += int(cnt_np.sum())
+    e2e_tracks = e2e_run(args.e2e_steps, f); f += args.e2e_steps
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -382,7 +391,7 @@ def main():
                 "keypoint_fetches_per_stream_frame": kp_fetch_mean,
                 "host_input_bytes_per_step": B * 56 * N_ANCHORS * 4,
                 "d2h_bytes_per_step": B * DM * 228 + B * 4, "steps": args.e2e_steps,
-                "api": "pb_step_host: page-locked host heads [B,56,N] read in place over PCIe — confidence rows, 32 B sectors of the 4 box rows at every "
+                "api": "pb_submit_host / pb_wait (results read on the host every 4 steps): page-locked host heads [B,56,N] read in place over PCIe — confidence rows, 32 B sectors of the 4 box rows at every "
                        "candidate anchor and of the 51 keypoint rows at the candidates the lazy NMS sweep has to test (= h2d_bytes_per_step; the buffer "
                        "itself is host_input_bytes_per_step); TrackOutput records copied back into page-locked memory"},
         "gpu_launches": int(allstats[0, 2]),

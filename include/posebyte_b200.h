@@ -112,6 +112,15 @@ int pb_join(pb_handle_t h, pb_stream_t stream);
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf_threshold,
                  float nms_threshold, int frame_id, void* h_tracks, int* h_counts);
 
+/* Asynchronous form of pb_step_host for throughput: all three buffers must be page-locked.  The
+ * step (in-place read of h_heads over PCIe, kernels, copies of the records into h_tracks /
+ * h_counts) is enqueued on the handle's own streams and overlaps earlier submissions when
+ * pipeline_depth > 1.  The buffers of a submission belong to the library until pb_wait returns.
+ * pb_wait blocks until every submitted step has completed and its results are in place. */
+int pb_submit_host(pb_handle_t h, const float* h_heads, float conf_threshold, float nms_threshold,
+                   int frame_id, void* h_tracks, int* h_counts);
+int pb_wait(pb_handle_t h);
+
 /* ---- results --------------------------------------------------------------------- */
 
 /* GPUTracker::getActiveTracks (gpu_tracker.cu:1559-1639) for one stream; synchronises.

@@ -131,3 +131,34 @@ def test_pipelined_steps_equal_serial_steps(pb, orc, cuda, depth):
             trk[b].update(ref["poses"], ref["scores"], f)
             assert np.array_equal(piped.get_kept(b)["keep_anchors"], ref["keep_anchors"])
             assert piped.get_tracks(b).tobytes() == trk[b].get_tracks().tobytes()
+
+
+@pytest.mark.gpu
+def test_submit_host_pipelined_equals_serial_device_path(pb, cuda):
+    """pb_submit_host / pb_wait: page-locked heads read in place, lazy NMS sweep, records copied into
+    per-step page-locked buffers, consecutive steps overlapping; results = the plain device path."""
+    torch = cuda
+    B, F = 6, 24
+    scfg = pb.synth_config(canvas=640, persons=12, period=64)
+    host = pb.synth_heads(scfg, 40, B, 0, F, frame_major=True)
+    pinned = torch.from_numpy(host).pin_memory()
+    ref = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+    piped = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=3)
+    outs = torch.zeros(F, B * piped.Dm * 228, dtype=torch.uint8).pin_memory()
+    cnts = torch.zeros(F, B, dtype=torch.int32).pin_memory()
+    for f in range(F):
+        piped.submit_host(pinned[f].numpy(), f, outs[f].numpy(), cnts[f].numpy())
+    piped.wait()
+    d = torch.from_numpy(host).cuda()
+    total = 0
+    for f in range(F):
+        ref.step(d[f], f)
+        o, c = ref.get_tracks_all()
+        assert np.array_equal(c, cnts[f].numpy()), f
+        got = outs[f].numpy().view(pb.TRACK_OUTPUT).reshape(B, piped.Dm)
+        for b in range(B):
+            assert got[b, : c[b]].tobytes() == o[b, : c[b]].tobytes(), (f, b)
+        total += int(c.sum())
+    assert total > 500
+    with pytest.raises(pb.PbError):                       # pageable buffers are refused
+        piped.submit_host(host[0], 0, outs[0].numpy(), cnts[0].numpy())

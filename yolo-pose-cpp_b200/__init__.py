@@ -69,7 +69,7 @@ class SynthConfig(C.Structure):
 # Every symbol include/posebyte_b200.h declares (tests check the library exports them all).
 ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
-    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_get_tracks",
+    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
     "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
@@ -100,6 +100,8 @@ def lib() -> C.CDLL:
         L.pb_step.argtypes = [vp, vp, fp, fp, ip, vp]
         L.pb_step_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
         L.pb_join.argtypes = [vp, vp]
+        L.pb_submit_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
+        L.pb_wait.argtypes = [vp]
         L.pb_get_tracks.argtypes = [vp, ip, vp, ip, C.POINTER(ip)]
         L.pb_get_tracks_all.argtypes = [vp, vp, vp]
         L.pb_get_num_active.argtypes = [vp, vp]
@@ -206,6 +208,14 @@ class Pipeline:
             counts = np.zeros(self.B, dtype=np.int32)
         check(lib().pb_step_host(self._h, heads_np.ctypes.data, conf, nms, frame_id, out.ctypes.data, counts.ctypes.data))
         return out, counts
+
+    def submit_host(self, heads_np: np.ndarray, frame_id, out: np.ndarray, counts: np.ndarray, conf=0.30, nms=0.65):
+        """Asynchronous step_host: all three arrays must be views of page-locked memory and stay
+        untouched until wait() returns."""
+        check(lib().pb_submit_host(self._h, heads_np.ctypes.data, conf, nms, frame_id, out.ctypes.data, counts.ctypes.data))
+
+    def wait(self):
+        check(lib().pb_wait(self._h))
 
     # -- results ----------------------------------------------------------------------
     def get_tracks(self, b: int) -> np.ndarray:

@@ -58,6 +58,8 @@ struct pb_handle_st {
     cudaStream_t own_stream = nullptr;
     int frames = 0;
     bool lazy_keypoints = false;   // set by pb_step_host while the head is read in place from host memory
+    void* rb_tracks = nullptr;     // page-locked read-back targets of the step being enqueued (pb_submit_host)
+    int* rb_counts = nullptr;
     // optional per-kernel event timing (pb_set_profiling)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -314,6 +316,15 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
     return PB_OK;
 }
 
+// Device-to-host copies of a step's TrackOutput records, enqueued right behind its tracker launch.
+static int enqueue_readback(pb_handle_st* h, cudaStream_t stream) {
+    if (!h->rb_tracks) return PB_OK;
+    const size_t B = h->cfg.num_streams, Dm = h->cfg.max_detections;
+    PB_CUDA(cudaMemcpyAsync(h->rb_counts, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaMemcpyAsync(h->rb_tracks, h->trk.outputs, B * Dm * 228, cudaMemcpyDeviceToHost, stream));
+    return PB_OK;
+}
+
 // Pipelined step (pipeline_depth > 1): the three kernels of one step run on three streams —
 // decode+gather on the caller's (it is the only reader of the borrowed head tensor), NMS and
 // tracker on internal ones — chained by events, with `depth` slots of candidate scratch and
@@ -337,6 +348,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     PB_CUDA(cudaStreamWaitEvent(h->s_trk, sl.ev_nms, 0));
     DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
     PB_CUDA(launch_tracker(h->trk, track_params(c, frame_id), src, h->plan, h->s_trk));
+    PB_TRY(enqueue_readback(h, h->s_trk));
     PB_CUDA(cudaEventRecord(sl.ev_trk, h->s_trk));
     sl.used = true;
     h->cur = pos; h->post = sl.post; h->cand = sl.cand;
@@ -349,7 +361,8 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int fram
     if (!h || !d_heads) { pb_set_error("pb_step: null argument"); return PB_ERR_INVALID; }
     if (h->cfg.pipeline_depth > 1 && !h->profiling) return step_pipelined(h, d_heads, conf, nms, frame_id, (cudaStream_t)stream);
     PB_TRY(pb_postprocess(h, d_heads, conf, nms, stream));
-    return pb_tracker_update(h, nullptr, nullptr, nullptr, 0, frame_id, stream);
+    PB_TRY(pb_tracker_update(h, nullptr, nullptr, nullptr, 0, frame_id, stream));
+    return enqueue_readback(h, (cudaStream_t)stream);
 }
 
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
@@ -398,6 +411,32 @@ int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int
         memcpy(h_counts, h->h_cnt_pinned, B * sizeof(int));
         memcpy(h_tracks, h->h_out_pinned, B * Dm * 228);
     }
+    return PB_OK;
+}
+
+int pb_submit_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
+                   void* h_tracks, int* h_counts) {
+    if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_submit_host: null argument"); return PB_ERR_INVALID; }
+    const pb_config& c = h->cfg;
+    cudaPointerAttributes at{}, ot{}, oc{};
+    const bool ok = cudaPointerGetAttributes(&at, h_heads) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+                    cudaPointerGetAttributes(&ot, h_tracks) == cudaSuccess && ot.type == cudaMemoryTypeHost &&
+                    cudaPointerGetAttributes(&oc, h_counts) == cudaSuccess && oc.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    if (!ok) { pb_set_error("pb_submit_host: heads, tracks and counts must be page-locked host memory (cudaHostAlloc / cudaHostRegister)"); return PB_ERR_INVALID; }
+    const bool lazy_before = h->lazy_keypoints;
+    if (c.keypoint_fetch == 0) h->lazy_keypoints = true;
+    h->rb_tracks = h_tracks; h->rb_counts = h_counts;
+    const int rc = pb_step(h, static_cast<const float*>(at.devicePointer), conf, nms, frame_id, (pb_stream_t)h->own_stream);
+    h->rb_tracks = nullptr; h->rb_counts = nullptr;
+    h->lazy_keypoints = lazy_before;
+    return rc;
+}
+
+int pb_wait(pb_handle_t h) {
+    if (!h) { pb_set_error("pb_wait: null handle"); return PB_ERR_INVALID; }
+    PB_TRY(join_on(h, h->own_stream));
+    PB_CUDA(cudaStreamSynchronize(h->own_stream));
     return PB_OK;
 }
 
