@@ -4,9 +4,13 @@
 // src/cuda/hungarian.cu:341-405): forward auction with eps0 = 1/(rows+1), min(3*rows, 50)
 // iterations, eps *= 0.9, lowest column on equal value and lowest row on equal bid.  `threshold`
 // is accepted and ignored, as upstream.  One launch per solve instead of 100 kernels + 53
-// memsets.  The host-side legacy solve() (hungarian.cu:235-339) and GreedyMatcherCUDA are not
-// part of the hot path and are not provided.
+// memsets.  GreedyMatcherCUDA (hungarian.cu:407-543) is provided with the deterministic rule of
+// its own host path.  The host-side legacy LinearAssignmentCUDA::solve() (hungarian.cu:235-339) is
+// not part of the hot path and is not provided.
 #pragma once
+
+#include <utility>
+#include <vector>
 
 #include "pb_shim_common.h"
 
@@ -40,6 +44,51 @@ public:
 
 private:
     int max_size_;
+};
+
+// GreedyMatcherCUDA: cells below the threshold in ascending (cost, row, col) order, each taken when
+// its row and column are still free — the rule of the reference's own host path (hungarian.cu:441-467).
+// The reference's device kernel (:126-157) races on the columns; here host and device entry points
+// give the same, deterministic answer.
+class GreedyMatcherCUDA {
+public:
+    explicit GreedyMatcherCUDA(int max_size = 256) : max_size_(max_size) {
+        detail::cu_check(cudaStreamCreate(&stream_), "cudaStreamCreate");
+        detail::cu_check(cudaMalloc(&d_costs_, (size_t)max_size * max_size * sizeof(float)), "cudaMalloc");
+        detail::cu_check(cudaMalloc(&d_row_, (size_t)max_size * sizeof(int)), "cudaMalloc");
+    }
+    ~GreedyMatcherCUDA() {
+        cudaFree(d_costs_); cudaFree(d_row_);
+        cudaStreamDestroy(stream_);
+    }
+    GreedyMatcherCUDA(const GreedyMatcherCUDA&) = delete;
+    GreedyMatcherCUDA& operator=(const GreedyMatcherCUDA&) = delete;
+
+    // host cost matrix [num_rows, num_cols] -> (row, col) pairs in ascending row order
+    std::vector<std::pair<int, int>> match(const float* cost_matrix, int num_rows, int num_cols, float threshold) {
+        std::vector<std::pair<int, int>> out;
+        if (num_rows == 0 || num_cols == 0) return out;
+        if (num_rows > max_size_ || num_cols > max_size_) throw std::runtime_error("GreedyMatcherCUDA: matrix larger than max_size");
+        detail::cu_check(cudaMemcpyAsync(d_costs_, cost_matrix, (size_t)num_rows * num_cols * sizeof(float), cudaMemcpyHostToDevice, stream_), "upload");
+        matchDeviceAsync(d_costs_, num_rows, num_cols, d_row_, threshold, stream_);
+        std::vector<int> rows((size_t)num_rows);
+        detail::cu_check(cudaMemcpyAsync(rows.data(), d_row_, rows.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "download");
+        detail::cu_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+        for (int r = 0; r < num_rows; ++r) if (rows[r] >= 0) out.push_back({r, rows[r]});
+        return out;
+    }
+    // d_row_matched [num_rows] = matched column or -1; asynchronous
+    void matchDeviceAsync(const float* d_cost_matrix, int num_rows, int num_cols, int* d_row_matched, float threshold, cudaStream_t stream = 0) {
+        if (num_rows == 0 || num_cols == 0) return;
+        detail::pb_check(pb_greedy_match(d_cost_matrix, 1, num_rows, num_cols, threshold, d_row_matched, detail::as_pb(stream ? stream : stream_)), "pb_greedy_match");
+    }
+    void sync(cudaStream_t stream = 0) { detail::cu_check(cudaStreamSynchronize(stream ? stream : stream_), "cudaStreamSynchronize"); }
+
+private:
+    int max_size_;
+    float* d_costs_ = nullptr;
+    int* d_row_ = nullptr;
+    cudaStream_t stream_ = nullptr;
 };
 
 }  // namespace cuda

@@ -188,6 +188,34 @@ int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_launches, double*
  * tracker); clears the record. */
 int pb_get_kernel_us(pb_handle_t h, double* gather_us, double* nms_us, double* track_us, int* launches);
 
+/* ---- rows next to the path ------------------------------------------------- */
+
+/* scaleTrackOutputs (src/main.cpp:48-68) fused into the output stage: every TrackOutput of stream b
+ * leaves as (value - pad) * scale for the box and the keypoints.  h_xform = [B,4] host floats
+ * (scale_x, scale_y, pad_x, pad_y) or NULL to switch it off (default).  Synchronises. */
+int pb_set_output_transform(pb_handle_t h, const float* h_xform);
+
+/* Tracker state snapshot / restore (all streams): a flat host blob of pb_state_size bytes.
+ * A handle restored from a snapshot continues exactly as the saved one would have. */
+int pb_state_size(pb_handle_t h, size_t* bytes);
+int pb_state_save(pb_handle_t h, void* h_blob, size_t capacity);
+int pb_state_load(pb_handle_t h, const void* h_blob, size_t bytes);
+
+/* OKSDistanceCUDA device entry points (oks_distance.cu:26-261, 479-537) for `batch` independent
+ * problems in one launch: d_tracks [batch, num_tracks, 17*3], d_dets [batch, num_dets, 17*3],
+ * d_out_costs [batch, num_tracks, num_dets].  mode 0: computeOKSDistanceDeviceAsync (1 - OKS,
+ * ungated, with the 0.05-confidence fallback); 1: computeIoUDistanceDeviceAsync (keypoint boxes
+ * with a 10 px margin); 2: computeCombinedDistance (alpha * OKS cost + (1 - alpha) * IoU cost). */
+int pb_pose_distance(const float* d_tracks, const float* d_dets, int batch, int num_tracks, int num_dets,
+                     int mode, float alpha, float* d_out_costs, pb_stream_t stream);
+
+/* GreedyMatcherCUDA (hungarian.cu:407-543) for `batch` problems: d_row_matched [batch, num_rows]
+ * = matched column or -1.  Deterministic rule = the class's own host path (:441-467): cells below
+ * the threshold in ascending (cost, row, col) order, taken when row and column are free.  (The
+ * reference's device kernel, :126-157, races on the columns.) */
+int pb_greedy_match(const float* d_cost, int batch, int num_rows, int num_cols, float threshold,
+                    int* d_row_matched, pb_stream_t stream);
+
 /* ---- stage-level entry points ------------------------------------------------------ */
 
 /* nms.h:48-60 declares this symbol and never defines it.  Device pointers; keep[i] in

@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         L.orc_pose_nms.restype = None
         L.orc_auction.argtypes = [vp, ip, ip, vp, vp, vp]
         L.orc_auction.restype = None
+        L.orc_pose_distance.argtypes = [vp, vp, ip, ip, ip, fp, vp]
+        L.orc_pose_distance.restype = None
+        L.orc_greedy_match.argtypes = [vp, ip, ip, fp, vp]
+        L.orc_greedy_match.restype = None
         L.orc_tracker_create.argtypes = [C.POINTER(TrackerConfig)]
         L.orc_tracker_create.restype = vp
         L.orc_tracker_destroy.argtypes = [vp]
@@ -147,6 +151,21 @@ def auction(cost: np.ndarray, row_active=None):
     ra = None if row_active is None else np.ascontiguousarray(row_active, dtype=np.int32)
     lib().orc_auction(cost.ctypes.data, R, Cc, row.ctypes.data, col.ctypes.data, None if ra is None else ra.ctypes.data)
     return row, col
+
+
+def pose_distance(tracks, dets, mode=0, alpha=0.7) -> np.ndarray:
+    t = _f32(tracks).reshape(-1, 51); d = _f32(dets).reshape(-1, 51)
+    out = np.zeros((len(t), len(d)), np.float32)
+    lib().orc_pose_distance(t.ctypes.data, d.ctypes.data, len(t), len(d), mode, alpha, out.ctypes.data)
+    return out
+
+
+def greedy_match(cost, threshold) -> np.ndarray:
+    c = _f32(cost)
+    R, Cc = c.shape
+    out = np.full(R, -1, np.int32)
+    lib().orc_greedy_match(c.ctypes.data, R, Cc, threshold, out.ctypes.data)
+    return out
 
 
 class Tracker:

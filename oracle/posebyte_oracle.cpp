@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 namespace {
@@ -865,6 +866,96 @@ int orc_nms_legacy(const void* dets, int n, float oks_thr, float score_thr, int*
 void orc_pose_nms(const float* poses, const float* scores, const float* sigmas, int* keep, int n,
                   int nk, float oks_thr, float score_thr) {
     pose_nms(poses, scores, sigmas, keep, n, nk, oks_thr, score_thr);
+}
+
+// ---- OKSDistanceCUDA (oks_distance.cu) and GreedyMatcherCUDA (hungarian.cu) ----
+
+// kernelOKSDistance :26-164 for one (track, detection) pair.
+static float pose_oks_cost(const float* tp, const float* dp) {
+    float dlx = 1e9f, dly = 1e9f, dhx = -1e9f, dhy = -1e9f;
+    int dvalid = 0;
+    for (int k = 0; k < KP; ++k)
+        if (dp[k * 3 + 2] > 0.1f) {
+            dlx = pb_min(dlx, dp[k * 3]); dly = pb_min(dly, dp[k * 3 + 1]);
+            dhx = pb_max(dhx, dp[k * 3]); dhy = pb_max(dhy, dp[k * 3 + 1]); ++dvalid;
+        }
+    float tlx = 1e9f, tly = 1e9f, thx = -1e9f, thy = -1e9f;
+    for (int k = 0; k < KP; ++k)
+        if (tp[k * 3 + 2] > 0.1f) {
+            tlx = pb_min(tlx, tp[k * 3]); tly = pb_min(tly, tp[k * 3 + 1]);
+            thx = pb_max(thx, tp[k * 3]); thy = pb_max(thy, tp[k * 3 + 1]);
+        }
+    float det_scale = (dhx - dlx) * (dhy - dly), trk_scale = (thx - tlx) * (thy - tly);
+    float scale_sq = (det_scale + trk_scale) * 0.5f;                     // :78-86
+    if (scale_sq < 1000.0f) scale_sq = 1000.0f;
+    if (dvalid < 2) return 1.0f;                                         // :89-92
+    auto pass = [&](float thr, float& sum, int& cnt) {
+        sum = 0.0f; cnt = 0;
+        for (int k = 0; k < KP; ++k)
+            if (dp[k * 3 + 2] > thr && tp[k * 3 + 2] > thr) {
+                float dx = dp[k * 3] - tp[k * 3], dy = dp[k * 3 + 1] - tp[k * 3 + 1];
+                float d2 = dx * dx + dy * dy;
+                float sg = COCO_SIGMAS[k] * 2.0f;
+                sum += pb_expf(-d2 / (2.0f * scale_sq * (sg * sg)));
+                ++cnt;
+            }
+    };
+    float sum; int cnt;
+    pass(0.2f, sum, cnt);                                                // :101-127
+    float oks;
+    if (cnt >= 3) oks = sum / (float)cnt;
+    else { pass(0.05f, sum, cnt); oks = cnt > 0 ? sum / (float)cnt : 0.0f; }   // :134-160
+    return 1.0f - oks;
+}
+
+// kernelExtractBboxes :213-245 + kernelIoUDistance :167-210.
+static float pose_iou_cost(const float* tp, const float* dp) {
+    auto box = [](const float* p, float* b) {
+        float lx = 1e9f, ly = 1e9f, hx = -1e9f, hy = -1e9f;
+        for (int k = 0; k < KP; ++k)
+            if (p[k * 3 + 2] > 0.0f) {
+                lx = pb_min(lx, p[k * 3]); ly = pb_min(ly, p[k * 3 + 1]);
+                hx = pb_max(hx, p[k * 3]); hy = pb_max(hy, p[k * 3 + 1]);
+            }
+        b[0] = lx - 10.0f; b[1] = ly - 10.0f; b[2] = hx + 10.0f; b[3] = hy + 10.0f;
+    };
+    float t[4], d[4];
+    box(tp, t); box(dp, d);
+    float ix1 = pb_max(t[0], d[0]), iy1 = pb_max(t[1], d[1]), ix2 = pb_min(t[2], d[2]), iy2 = pb_min(t[3], d[3]);
+    float iw = pb_max(0.0f, ix2 - ix1), ih = pb_max(0.0f, iy2 - iy1);
+    float inter = iw * ih;
+    float ta = (t[2] - t[0]) * (t[3] - t[1]), da = (d[2] - d[0]) * (d[3] - d[1]);
+    float uni = ta + da - inter;
+    float iou = (uni > 0.0f) ? (inter / uni) : 0.0f;
+    return 1.0f - iou;
+}
+
+// mode 0: OKS cost, 1: IoU cost, 2: alpha * OKS + (1 - alpha) * IoU (kernelCombineCosts :248-261).
+void orc_pose_distance(const float* tracks, const float* dets, int nt, int nd, int mode, float alpha, float* out) {
+    for (int t = 0; t < nt; ++t)
+        for (int d = 0; d < nd; ++d) {
+            const float* tp = tracks + (size_t)t * 51;
+            const float* dp = dets + (size_t)d * 51;
+            float c;
+            if (mode == 0) c = pose_oks_cost(tp, dp);
+            else if (mode == 1) c = pose_iou_cost(tp, dp);
+            else { float o = pose_oks_cost(tp, dp), u = pose_iou_cost(tp, dp); c = alpha * o + (1.0f - alpha) * u; }
+            out[(size_t)t * nd + d] = c;
+        }
+}
+
+// GreedyMatcherCUDA::match host path, hungarian.cu:441-467: cells below the threshold sorted by
+// (cost, row, col), taken greedily.  (The device kernel :126-157 races; this is the stated rule.)
+void orc_greedy_match(const float* cost, int R, int C, float threshold, int* row_matched) {
+    std::vector<std::tuple<float, int, int>> cells;
+    for (int r = 0; r < R; ++r)
+        for (int c = 0; c < C; ++c)
+            if (cost[(size_t)r * C + c] < threshold) cells.push_back({cost[(size_t)r * C + c], r, c});
+    std::sort(cells.begin(), cells.end());
+    std::vector<char> ru(R, 0), cu(C, 0);
+    for (int r = 0; r < R; ++r) row_matched[r] = -1;
+    for (auto& [v, r, c] : cells)
+        if (!ru[r] && !cu[c]) { ru[r] = 1; cu[c] = 1; row_matched[r] = c; }
 }
 
 void orc_auction(const float* cost, int R, int C, int* row, int* col, const int* row_active) {

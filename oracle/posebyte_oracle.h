@@ -64,6 +64,12 @@ void orc_pose_nms(const float* poses, const float* scores, const float* sigmas, 
 void orc_auction(const float* cost, int num_rows, int num_cols,
                  int* row_assign, int* col_assign, const int* row_active);
 
+/* SURVEY.md 8f row f1.  OKSDistanceCUDA: oks_distance.cu:26-261 (mode 0 OKS cost, 1 keypoint-box IoU
+ * cost, 2 alpha-combined); tracks [nt,51], dets [nd,51], out [nt,nd]. */
+void orc_pose_distance(const float* tracks, const float* dets, int nt, int nd, int mode, float alpha, float* out);
+/* GreedyMatcherCUDA::match host rule, hungarian.cu:441-467; row_matched [R] = column or -1. */
+void orc_greedy_match(const float* cost, int R, int C, float threshold, int* row_matched);
+
 /* A5-A16  gpu_tracker.cu:102-919,1057-1639. */
 void* orc_tracker_create(const orc_tracker_config* cfg);
 void orc_tracker_destroy(void* t);

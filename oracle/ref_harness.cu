@@ -128,6 +128,25 @@ void ref_auction(const float* h_cost, int R, int C, int* h_row, int* h_col, cons
     cudaFree(d_cost); cudaFree(d_row); cudaFree(d_col); if (d_act) cudaFree(d_act);
 }
 
+// ---- OKSDistanceCUDA / GreedyMatcherCUDA -------------------------------------------------------
+// tracks / dets: PoseDetection arrays (224 B); mode 0 OKS, 1 IoU, 2 combined.
+void ref_pose_distance(const void* tracks, const void* dets, int nt, int nd, int mode, float alpha, float* out) {
+    OKSDistanceCUDA od(std::max(nt, 1), std::max(nd, 1));
+    const PoseDetection* t = static_cast<const PoseDetection*>(tracks);
+    const PoseDetection* d = static_cast<const PoseDetection*>(dets);
+    if (mode == 0) od.computeOKSDistance(t, d, out, nt, nd);
+    else if (mode == 1) od.computeIoUDistance(t, d, out, nt, nd);
+    else od.computeCombinedDistance(t, d, out, nt, nd, alpha);
+}
+// GreedyMatcherCUDA::match: deterministic host path below 200 cells, racy device kernel above.
+int ref_greedy_match(const float* cost, int R, int C, float threshold, int* row_matched) {
+    GreedyMatcherCUDA gm(std::max(std::max(R, C), 1));
+    std::vector<std::pair<int, int>> m = gm.match(cost, R, C, threshold);
+    for (int r = 0; r < R; ++r) row_matched[r] = -1;
+    for (auto& pr : m) row_matched[pr.first] = pr.second;
+    return (int)m.size();
+}
+
 // ---- KalmanFilterCUDA -----------------------------------------------------------------
 void* ref_kf3_create(int max_tracks) { return new KalmanFilterCUDA(max_tracks); }
 void ref_kf3_destroy(void* k) { delete static_cast<KalmanFilterCUDA*>(k); }

@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         L.ref_tracker_get_state.argtypes = [vp] * 16; L.ref_tracker_get_state.restype = None
         L.ref_nms_apply.argtypes = [vp, ip, fp, fp, vp]
         L.ref_auction.argtypes = [vp, ip, ip, vp, vp, vp]; L.ref_auction.restype = None
+        L.ref_pose_distance.argtypes = [vp, vp, ip, ip, ip, fp, vp]; L.ref_pose_distance.restype = None
+        L.ref_greedy_match.argtypes = [vp, ip, ip, fp, vp]
         L.ref_kf3_create.argtypes = [ip]; L.ref_kf3_create.restype = vp
         L.ref_kf3_destroy.argtypes = [vp]; L.ref_kf3_destroy.restype = None
         L.ref_kf3_initiate.argtypes = [vp, vp, vp, ip]; L.ref_kf3_initiate.restype = None
@@ -93,6 +95,32 @@ def auction(cost: np.ndarray, row_active=None):
     with quiet():
         lib().ref_auction(cost.ctypes.data, R, Cc, row.ctypes.data, col.ctypes.data, None if ra is None else ra.ctypes.data)
     return row, col
+
+
+def _as_dets(poses) -> np.ndarray:
+    p = _f32(poses).reshape(-1, 17, 3)
+    d = np.zeros(len(p), POSE_DETECTION)
+    d["keypoints"] = p
+    return d
+
+
+def pose_distance(tracks, dets, mode=0, alpha=0.7) -> np.ndarray:
+    """OKSDistanceCUDA::computeOKSDistance / computeIoUDistance / computeCombinedDistance (GPU)."""
+    t, d = _as_dets(tracks), _as_dets(dets)
+    out = np.zeros((len(t), len(d)), np.float32)
+    with quiet():
+        lib().ref_pose_distance(t.ctypes.data, d.ctypes.data, len(t), len(d), mode, alpha, out.ctypes.data)
+    return out
+
+
+def greedy_match(cost, threshold) -> np.ndarray:
+    """GreedyMatcherCUDA::match (deterministic host path below 200 cells)."""
+    c = _f32(cost)
+    R, Cc = c.shape
+    out = np.full(R, -1, np.int32)
+    with quiet():
+        lib().ref_greedy_match(c.ctypes.data, R, Cc, threshold, out.ctypes.data)
+    return out
 
 
 class Postprocess:

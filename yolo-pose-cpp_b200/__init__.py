@@ -72,6 +72,7 @@ ABI_SYMBOLS = [
     "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
     "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
+    "pb_set_output_transform", "pb_state_size", "pb_state_save", "pb_state_load", "pb_pose_distance", "pb_greedy_match",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
 ]
 
@@ -118,6 +119,12 @@ def lib() -> C.CDLL:
         L.launchPoseNMS.argtypes = [vp, vp, vp, vp, ip, ip, fp, fp, vp]
         L.pb_nms_legacy.argtypes = [vp, vp, ip, ip, fp, fp, vp, vp, vp]
         L.pb_auction_solve.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp]
+        L.pb_set_output_transform.argtypes = [vp, vp]
+        L.pb_state_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+        L.pb_state_save.argtypes = [vp, vp, C.c_size_t]
+        L.pb_state_load.argtypes = [vp, vp, C.c_size_t]
+        L.pb_pose_distance.argtypes = [vp, vp, ip, ip, ip, ip, fp, vp, vp]
+        L.pb_greedy_match.argtypes = [vp, ip, ip, ip, fp, vp, vp]
         L.pb_kf3_initiate.argtypes = [vp, vp, vp, vp, ip, vp]
         L.pb_kf3_predict.argtypes = [vp, vp, ip, fp, fp, vp]
         L.pb_kf3_update.argtypes = [vp, vp, vp, vp, ip, vp]
@@ -217,6 +224,26 @@ class Pipeline:
     def wait(self):
         check(lib().pb_wait(self._h))
 
+    # -- rows next to the path ---------------------------------------------------------
+    def set_output_transform(self, xform):
+        """xform [B,4] = scale_x, scale_y, pad_x, pad_y per stream (scaleTrackOutputs), or None."""
+        if xform is None:
+            check(lib().pb_set_output_transform(self._h, None))
+        else:
+            x = np.ascontiguousarray(xform, np.float32).reshape(self.B, 4)
+            check(lib().pb_set_output_transform(self._h, x.ctypes.data))
+
+    def state_save(self) -> bytes:
+        n = C.c_size_t(0)
+        check(lib().pb_state_size(self._h, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        check(lib().pb_state_save(self._h, buf.ctypes.data, n.value))
+        return buf.tobytes()
+
+    def state_load(self, blob: bytes):
+        buf = np.frombuffer(blob, np.uint8)
+        check(lib().pb_state_load(self._h, buf.ctypes.data, buf.size))
+
     # -- results ----------------------------------------------------------------------
     def get_tracks(self, b: int) -> np.ndarray:
         out = np.zeros(self.Dm, dtype=TRACK_OUTPUT)
@@ -307,6 +334,25 @@ class Pipeline:
         t = PbTiming()
         check(lib().pb_get_timing(self._h, C.byref(t)))
         return t
+
+
+def pose_distance(tracks, dets, mode=0, alpha=0.7, stream=None):
+    """tracks [batch, nt, 51], dets [batch, nd, 51] CUDA tensors -> costs [batch, nt, nd]."""
+    import torch
+    batch, nt, _ = tracks.shape
+    nd = dets.shape[1]
+    out = torch.empty(batch, nt, nd, device=tracks.device, dtype=torch.float32)
+    check(lib().pb_pose_distance(tracks.data_ptr(), dets.data_ptr(), batch, nt, nd, mode, alpha, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def greedy_match(cost, threshold, stream=None):
+    """cost [batch, R, C] CUDA tensor -> row_matched [batch, R] int32."""
+    import torch
+    batch, R, Cc = cost.shape
+    out = torch.empty(batch, R, device=cost.device, dtype=torch.int32)
+    check(lib().pb_greedy_match(cost.data_ptr(), batch, R, Cc, threshold, out.data_ptr(), _stream_ptr(stream)))
+    return out
 
 
 def launch_count() -> int:

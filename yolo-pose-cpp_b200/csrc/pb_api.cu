@@ -58,6 +58,7 @@ struct pb_handle_st {
     cudaStream_t own_stream = nullptr;
     int frames = 0;
     bool lazy_keypoints = false;   // set by pb_step_host while the head is read in place from host memory
+    float* d_xform = nullptr;      // [B,4] output transform (pb_set_output_transform)
     void* rb_tracks = nullptr;     // page-locked read-back targets of the step being enqueued (pb_submit_host)
     int* rb_counts = nullptr;
     // optional per-kernel event timing (pb_set_profiling)
@@ -92,6 +93,23 @@ static int dev_alloc(pb_handle_st* h, T** p, size_t count) {
     return PB_OK;
 }
 #define PB_TRY(x) do { int r_ = (x); if (r_ != PB_OK) return r_; } while (0)
+
+// Tracker state snapshot: header + every persistent slab, in one host blob.
+struct SnapHeader { unsigned magic, version; int B, T, Dm, frames; };
+static const unsigned kSnapMagic = 0x50425354u;   // "PBST"
+
+template <typename F>
+static int for_each_state_slab(pb_handle_st* h, F&& f) {
+    const size_t B = h->cfg.num_streams, T = h->cfg.max_tracks, Dm = h->cfg.max_detections;
+    TrackBuffers& t = h->trk;
+    PB_TRY(f(t.poses, B * T * POSE_F * 4)); PB_TRY(f(t.vel, B * T * 34 * 4)); PB_TRY(f(t.scores, B * T * 4));
+    PB_TRY(f(t.predicted, B * T * POSE_F * 4)); PB_TRY(f(t.tcent, B * T * 16)); PB_TRY(f(t.dcent, B * Dm * 16));
+    PB_TRY(f(t.cost, B * T * Dm * 4)); PB_TRY(f(t.det_scores, B * Dm * 4));
+    PB_TRY(f(t.states, B * T * 4)); PB_TRY(f(t.ids, B * T * 4)); PB_TRY(f(t.hits, B * T * 4)); PB_TRY(f(t.ages, B * T * 4));
+    PB_TRY(f(t.last_frame, B * T * 4)); PB_TRY(f(t.active, B * T * 4)); PB_TRY(f(t.pred_dirty, B * T * 4));
+    PB_TRY(f(t.row_assign, B * T * 4)); PB_TRY(f(t.col_assign, B * Dm * 4)); PB_TRY(f(t.scalars, B * 4 * 4));
+    return PB_OK;
+}
 
 extern "C" {
 
@@ -412,6 +430,63 @@ int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int
         memcpy(h_tracks, h->h_out_pinned, B * Dm * 228);
     }
     return PB_OK;
+}
+
+// ---- SURVEY.md §8f rows f2 / f4 ---------------------------------------------------------------
+
+int pb_set_output_transform(pb_handle_t h, const float* h_xform) {
+    if (!h) { pb_set_error("pb_set_output_transform: null handle"); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    if (!h_xform) { h->trk.out_xform = nullptr; return PB_OK; }
+    const size_t n = (size_t)h->cfg.num_streams * 4;
+    if (!h->d_xform) PB_TRY(dev_alloc(h, &h->d_xform, n));
+    PB_CUDA(cudaMemcpy(h->d_xform, h_xform, n * sizeof(float), cudaMemcpyHostToDevice));
+    h->trk.out_xform = h->d_xform;
+    return PB_OK;
+}
+
+int pb_state_size(pb_handle_t h, size_t* bytes) {
+    if (!h || !bytes) { pb_set_error("pb_state_size: bad argument"); return PB_ERR_INVALID; }
+    size_t total = sizeof(SnapHeader);
+    PB_TRY(for_each_state_slab(h, [&](void*, size_t n) -> int { total += n; return PB_OK; }));
+    *bytes = total;
+    return PB_OK;
+}
+
+int pb_state_save(pb_handle_t h, void* h_blob, size_t capacity) {
+    size_t need = 0;
+    PB_TRY(pb_state_size(h, &need));
+    if (!h_blob || capacity < need) { pb_set_error("pb_state_save: blob too small (%zu < %zu)", capacity, need); return PB_ERR_INVALID; }
+    PB_CUDA(cudaDeviceSynchronize());
+    SnapHeader hd{kSnapMagic, 1u, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, h->frames};
+    unsigned char* p = static_cast<unsigned char*>(h_blob);
+    memcpy(p, &hd, sizeof(hd)); p += sizeof(hd);
+    return for_each_state_slab(h, [&](void* d, size_t n) -> int {
+        PB_CUDA(cudaMemcpy(p, d, n, cudaMemcpyDeviceToHost));
+        p += n;
+        return PB_OK;
+    });
+}
+
+int pb_state_load(pb_handle_t h, const void* h_blob, size_t bytes) {
+    size_t need = 0;
+    PB_TRY(pb_state_size(h, &need));
+    if (!h_blob || bytes < need) { pb_set_error("pb_state_load: blob too small"); return PB_ERR_INVALID; }
+    SnapHeader hd{};
+    memcpy(&hd, h_blob, sizeof(hd));
+    if (hd.magic != kSnapMagic || hd.version != 1u || hd.B != h->cfg.num_streams || hd.T != h->cfg.max_tracks || hd.Dm != h->cfg.max_detections) {
+        pb_set_error("pb_state_load: snapshot is for %d streams x %d tracks x %d detections, handle has %d x %d x %d", hd.B, hd.T, hd.Dm,
+                     h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections);
+        return PB_ERR_INVALID;
+    }
+    PB_CUDA(cudaDeviceSynchronize());
+    const unsigned char* p = static_cast<const unsigned char*>(h_blob) + sizeof(hd);
+    h->frames = hd.frames;
+    return for_each_state_slab(h, [&](void* d, size_t n) -> int {
+        PB_CUDA(cudaMemcpy(d, p, n, cudaMemcpyHostToDevice));
+        p += n;
+        return PB_OK;
+    });
 }
 
 int pb_submit_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,

@@ -58,6 +58,7 @@ struct TrackBuffers {
     int* row_assign;     // [B, T]
     int* col_assign;     // [B, Dm]
     int* scalars;        // [B, 4]  next_id, slot_hint, D, num_active
+    const float* out_xform;  // [B, 4] scale_x, scale_y, pad_x, pad_y applied to the output records, or nullptr
     void* outputs;       // [B, Dm] TrackOutput (228 B)
     int* num_outputs;    // [B]
     float* det_poses_scratch;  // [B, Dm, 51]  used when the detections do not fit in shared memory

@@ -708,6 +708,11 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     __syncthreads();
     const int n_out = s.misc[3];
     {
+        // optional un-letterboxing of the records, scaleTrackOutputs (reference src/main.cpp:48-68):
+        // value = (value - pad) * scale, applied to the box and the keypoints after the box was built
+        const bool xf = tb.out_xform != nullptr;
+        const float sx = xf ? tb.out_xform[b * 4 + 0] : 1.0f, sy = xf ? tb.out_xform[b * 4 + 1] : 1.0f;
+        const float px_ = xf ? tb.out_xform[b * 4 + 2] : 0.0f, py_ = xf ? tb.out_xform[b * 4 + 3] : 0.0f;
         float* outw = reinterpret_cast<float*>(tb.outputs) + (size_t)b * Dm * 57;
         for (int o = c.warp; o < n_out; o += c.nwarps) {
             const int d = s.out_list[o];
@@ -717,7 +722,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
             float lx = 1e9f, ly = 1e9f, hx = -1e9f, hy = -1e9f;
             if (c.lane < KP) {
                 x = g_poses[sl * POSE_F + c.lane * 3]; y = g_poses[sl * POSE_F + c.lane * 3 + 1]; cf = g_poses[sl * POSE_F + c.lane * 3 + 2];
-                rec[6 + c.lane * 3] = x; rec[7 + c.lane * 3] = y; rec[8 + c.lane * 3] = cf;
+                rec[6 + c.lane * 3] = xf ? (x - px_) * sx : x; rec[7 + c.lane * 3] = xf ? (y - py_) * sy : y; rec[8 + c.lane * 3] = cf;
                 if (cf > 0.2f) { lx = x; ly = y; hx = x; hy = y; }
             }
 #pragma unroll
@@ -729,7 +734,9 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
                 const float px = (hx - lx) * 0.1f, py = (hy - ly) * 0.1f;
                 reinterpret_cast<int*>(rec)[0] = s.ids[sl];
                 rec[1] = s.dscore[d];
-                rec[2] = lx - px; rec[3] = ly - py; rec[4] = hx + px; rec[5] = hy + py;
+                const float b0 = lx - px, b1 = ly - py, b2 = hx + px, b3 = hy + py;
+                rec[2] = xf ? (b0 - px_) * sx : b0; rec[3] = xf ? (b1 - py_) * sy : b1;
+                rec[4] = xf ? (b2 - px_) * sx : b2; rec[5] = xf ? (b3 - py_) * sy : b3;
             }
         }
     }
