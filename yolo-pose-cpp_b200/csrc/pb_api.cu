@@ -241,6 +241,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
 int pb_destroy(pb_handle_t h) {
     if (!h) return PB_OK;
     cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();          // pipelined steps may still be running on the internal streams
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_out_pinned) cudaFreeHost(h->h_out_pinned);
