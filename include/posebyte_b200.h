@@ -57,7 +57,9 @@ typedef struct pb_config {
                               * overlaps consecutive steps on internal streams (see pb_join) */
     int keypoint_fetch;      /* 0 (default): the NMS kernel fetches keypoints lazily (IoU rule first, keypoints
                               * only for the ranks whose OKS tests are unavoidable) iff the head is read in
-                              * place from host memory (pb_step_host); 1: always lazy; 2: never */
+                              * place from host memory (pb_step_host); 1: always lazy; 2: never (complete
+                              * sweep); 3: complete records, but the lazy sweep's evaluation order (OKS tests
+                              * deferred until a rank's own tile; ~12 % faster on dense 1280x1280 crowds) */
 } pb_config;
 
 /* TrackerTiming (gpu_tracker.h:29-41), filled from device timestamps. */

@@ -28,7 +28,7 @@ def test_postprocess_matches_checker(pb, orc, cuda, canvas, persons, clumps, B, 
     cfg = pb.synth_config(canvas=canvas, persons=persons, period=16, clumps=clumps, kp_drop_prob=0.15 if clumps else 0.05)
     heads = pb.synth_heads(cfg, 0, B, 0, frames, frame_major=True)
     for f in range(frames):
-        for mode in (0, 1):                  # default (complete records from the decode kernel) and lazy keypoints
+        for mode in (0, 1, 3):               # complete sweep, lazy keypoints, deferred OKS tests on complete records
             _, got = run_post(pb, cuda, heads[f], keypoint_fetch=mode)
             for b in range(B):
                 assert_same(got[b], orc.postprocess(heads[f, b]), f"f{f} b{b} mode{mode}")
@@ -118,7 +118,7 @@ def test_lazy_sweep_rounds_match_checker(pb, orc, cuda):
     put(heads[0], 7003, 0.91, 390, 520, 120, 200, kps)
     put(heads[0], 7010, 0.89, 400, 520, 120, 200, kps, kshift=200.0)
     refs = [orc.postprocess(heads[b]) for b in range(3)]
-    for mode in (2, 1):                      # never lazy / always lazy: same results
+    for mode in (2, 3, 1):                   # complete sweep / deferred OKS tests / lazy keypoints: same results
         pipe, got = run_post(pb, cuda, heads, keypoint_fetch=mode)
         for b in range(3):
             assert_same(got[b], refs[b], f"mode {mode} stream {b}")

@@ -463,6 +463,31 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         s.area[r] = (x2 - x1) * (y2 - y1);
     }
     __syncthreads();
+    if (lazy == 2) {
+        // "deferred" flavour: the decode kernel gathered complete records (head in HBM), so all keypoints
+        // go to shared memory now and nothing is fetched later; what remains of the lazy sweep is its
+        // evaluation ORDER — IoU strikes first, OKS tests only for the ranks still alive at their own tile.
+        for (int it = tid; it < C * POSE_F; it += NM_THREADS) {
+            const int r = it / POSE_F, e = it - r * POSE_F;
+            const float v = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + 5 + e];
+            const int k = e / 3, comp = e - 3 * k;
+            if (comp == 0) s.kx[k * CS + r] = v;
+            else if (comp == 1) s.ky[k * CS + r] = v;
+            else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
+        }
+        __syncthreads();
+        for (int r = tid; r < C; r += NM_THREADS) {
+            float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
+#pragma unroll
+            for (int k = 1; k < KP; ++k) {
+                const float x = s.kx[k * CS + r], y = s.ky[k * CS + r];
+                lx = fminf(lx, x); hx = fmaxf(hx, x); ly = fminf(ly, y); hy = fmaxf(hy, y);
+            }
+            s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
+        }
+        for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.have[i] = 0xffffffffu;
+        __syncthreads();
+    }
     stamp(2);
     // fetch the keypoints of the ranks listed in s.fl[0..nf): head -> candidate record (for the output
     // stage) + shared memory (rank-indexed), then their keypoint extents
@@ -532,6 +557,10 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
                 atomicOr(&s.tmask[a], 1ull << bb);
         }
         __syncthreads();
+        if (lazy == 2) {
+            if (tid == 0) s.misc[7] = 1;                              // straight to the full tile step
+            __syncthreads();
+        } else {
         // (2) round 1: speculative box-only greedy pass -> S
         if (tid == 0) {
             unsigned long long rem = live, spec = 0ull;
@@ -607,20 +636,21 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             __syncthreads();
             if (!s.misc[7]) break;
         }
+        }   // speculative attempts
         if (s.misc[7]) {
             // round 2: keypoints for every live rank, every pair tested (the complete sweep's tile step)
             if (tid == 0) {
                 int nf = 0;
                 for (unsigned long long m = live; m; m &= m - 1ull) {
                     const int a = __ffsll((long long)m) - 1;
-                    if (!is_sup(s.have, t0 + a)) s.fl[nf++] = t0 + a;
+                    if (lazy == 2 || !is_sup(s.have, t0 + a)) s.fl[nf++] = t0 + a;
                 }
                 s.misc[6] = nf;
                 s.acc[8] += 1ull;
             }
             __syncthreads();
             const int nf2 = s.misc[6];
-            fetch_list(nf2);
+            if (lazy != 2) fetch_list(nf2);
             cross_tests(nf2, nk0);                                    // the newly fetched ranks against the earlier kept
             if (tid < 64) s.tmask[tid] = 0ull;
             __syncthreads();
@@ -824,7 +854,7 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
     return cudaGetLastError();
 }
 
-cudaError_t launch_nms(const float* d_heads, int N, bool lazy_keypoints, int B, int max_cand, int max_keep, float nms_thr,
+cudaError_t launch_nms(const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream) {
     const size_t smem2 = decode_nms_smem_bytes(max_cand, max_keep);
     static size_t configured = 0;
@@ -833,7 +863,7 @@ cudaError_t launch_nms(const float* d_heads, int N, bool lazy_keypoints, int B, 
         if (e != cudaSuccess) return e;
         configured = smem2;
     }
-    pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, lazy_keypoints ? 1 : 0, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out);
+    pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, sweep, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out);
     count_launch();
     return cudaGetLastError();
 }

@@ -208,7 +208,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     if (c.num_anchors > 65536) { pb_set_error("pb_create: num_anchors > 65536 unsupported"); return PB_ERR_UNSUPPORTED; }
     if (c.max_tracks >= 65536 || c.max_detections >= 65536) { pb_set_error("pb_create: max_tracks/max_detections too large"); return PB_ERR_UNSUPPORTED; }
     if (c.max_keep > c.max_candidates) { pb_set_error("pb_create: max_keep > max_candidates"); return PB_ERR_INVALID; }
-    if (c.keypoint_fetch < 0 || c.keypoint_fetch > 2) { pb_set_error("pb_create: keypoint_fetch must be 0, 1 or 2"); return PB_ERR_INVALID; }
+    if (c.keypoint_fetch < 0 || c.keypoint_fetch > 3) { pb_set_error("pb_create: keypoint_fetch must be 0..3"); return PB_ERR_INVALID; }
     if (c.pipeline_depth < 1 || c.pipeline_depth > 8) { pb_set_error("pb_create: pipeline_depth must be 1..8"); return PB_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c.device) {
@@ -292,7 +292,7 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
         cudaEventRecord(h->ev_pool[em], (cudaStream_t)stream);
         h->ev_gather.push_back({e0, em});
     }
-    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
         h->ev_post.push_back({e0, e1});
@@ -359,7 +359,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
     PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_trk, 0));        // kept detections still being read
-    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, h->s_nms));
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, h->s_nms));
     PB_CUDA(cudaEventRecord(sl.ev_nms, h->s_nms));
     // the NMS kernel fetches keypoints from the borrowed head tensor: later work on the caller's
     // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it

@@ -107,7 +107,7 @@ size_t decode_nms_smem_bytes(int max_cand, int max_keep);
 DecodePlan decode_plan(int B, int N, int max_cand);
 cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, bool lazy_keypoints, const DecodePlan& plan,
                                  const CandScratch& cs, cudaStream_t stream);
-cudaError_t launch_nms(const float* d_heads, int N, bool lazy_keypoints, int B, int max_cand, int max_keep, float nms_thr,
+cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 lazy, 2 deferred*/, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
 struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats; };
