@@ -1,4 +1,6 @@
-"""A/B timing of tracker variants inside one process group: pipelined step time + tier-1 auction tail."""
+"""A/B timing of tracker build variants inside one gpurun call (run it once per variant, selected by an
+environment variable the build under test reads): pipelined step time + tier-1 auction tail.  Single runs on
+different boxes differ by more than the effects being measured; runs inside one call repeat to 0.2 %."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -23,4 +25,4 @@ prev = pipe.stream_stage_ns().astype(np.int64); rows = []
 for f in range(32, 96):
     pipe.step(d[f % F], f); cur = pipe.stream_stage_ns().astype(np.int64); rows.append(cur - prev); prev = cur
 a = np.stack(rows) / 1e3
-print(f"variant {os.environ.get('PB_AUCTION_VARIANT', '0')}: pipelined us/step {[round(x, 1) for x in res]} | t1auction mean {a[:, :, 13].mean():.1f} p90 {np.percentile(a[:, :, 13], 90):.1f} max {a[:, :, 13].max():.1f} | chain: mean {a[:, :, 10].mean():.1f}, mean of per-frame max {a[:, :, 10].max(1).mean():.1f}")
+print(f"variant {os.environ.get('PB_VARIANT', '0')}: pipelined us/step {[round(x, 1) for x in res]} | t1auction mean {a[:, :, 13].mean():.1f} p90 {np.percentile(a[:, :, 13], 90):.1f} max {a[:, :, 13].max():.1f} | chain: mean {a[:, :, 10].mean():.1f}, mean of per-frame max {a[:, :, 10].max(1).mean():.1f}")
