@@ -30,6 +30,53 @@ def test_auction_batch(pb, orc, cuda):
         assert np.array_equal(d_row[0].cpu().numpy(), r)
 
 
+def _tracker_like_problem(rng, R, C, na, kind):
+    """Cost tables shaped like the tracker's: few active rows, one cheap cell per row, everything else a tie
+    at exactly 1.0 or locked at 1e9 (the states in which the auction runs to its iteration limit)."""
+    cost = np.full((R, C), 1.0, np.float32)
+    act = np.zeros(R, np.int32)
+    rows = np.sort(rng.choice(R, na, replace=False))
+    act[rows] = 1
+    for i, r in enumerate(rows):
+        if kind == "locked":
+            cost[r] = 1e9
+            for c in rng.choice(C, min(C, 3), replace=False):
+                cost[r, c] = np.float32(rng.uniform(0.6, 1.0))
+        elif kind == "ties":
+            cost[r, rng.uniform(size=C) < 0.3] = np.float32(0.5)
+        elif kind == "zero":
+            cost[r, rng.uniform(size=C) < 0.2] = np.float32(0.0)
+            cost[r, rng.uniform(size=C) < 0.1] = np.float32(-0.0)
+        if i < C and kind != "ties":
+            cost[r, i % C] = np.float32(rng.uniform(0.02, 0.4))
+    if kind == "nan":
+        cost[rows[0], :] = np.nan
+        cost[rows[-1], C // 2] = np.nan
+    return cost, act
+
+
+def test_auction_few_active_rows(pb, orc, cuda):
+    """At most 32 active rows: pb_auction_solve takes the single-warp hybrid solve (lane = column for up to four
+    bidders, lane = row above); assignments must equal the checker's on over-subscribed, tied and locked tables."""
+    torch = cuda
+    rng = np.random.default_rng(17)
+    st = torch.cuda.current_stream().cuda_stream
+    shapes = [(128, 20, 21), (128, 20, 20), (128, 64, 32), (128, 33, 30), (64, 1, 5), (40, 100, 32), (32, 32, 32), (128, 19, 24),
+              (16, 300, 16), (128, 5, 1)]
+    for R, C, na in shapes:
+        for kind in ("plain", "locked", "ties", "zero", "nan"):
+            batch = 6
+            costs, acts = zip(*[_tracker_like_problem(rng, R, C, na, kind) for _ in range(batch)])
+            cost, act = np.stack(costs), np.stack(acts)
+            d_cost, d_act = torch.from_numpy(cost).cuda(), torch.from_numpy(act).cuda()
+            d_row = torch.empty(batch, R, dtype=torch.int32, device="cuda"); d_col = torch.empty(batch, C, dtype=torch.int32, device="cuda")
+            pb.check(pb.lib().pb_auction_solve(d_cost.data_ptr(), batch, R, C, d_row.data_ptr(), d_col.data_ptr(), d_act.data_ptr(), st))
+            row, col = d_row.cpu().numpy(), d_col.cpu().numpy()
+            for b in range(batch):
+                r, c = orc.auction(cost[b], act[b])
+                assert np.array_equal(row[b], r) and np.array_equal(col[b], c), (R, C, na, kind, b)
+
+
 def test_kf3(pb, orc, cuda):
     torch = cuda
     L = pb.lib()

@@ -16,7 +16,7 @@ for f in range(32, 96):
     cur = pipe.stream_stage_ns().astype(np.int64)
     rows.append(cur - prev); prev = cur
 a = np.stack(rows) / 1e3            # [frames, B, 20] us
-names = {15: "longrows", 16: "sumlen", 17: "iters", 18: "bidders", 19: "longbid", 0: "prologue", 2: "gate", 12: "t1cost", 13: "t1auction", 4: "tier2", 5: "tier3", 9: "dedup", 10: "total"}
+names = {0: "prologue", 1: "predict", 2: "gate", 12: "t1cost", 13: "t1auction", 14: "t1lock", 3: "tier1", 4: "tier2", 5: "tier3", 6: "update", 7: "age", 8: "newtracks", 9: "dedup", 10: "total"}
 for i, n in names.items():
     x = a[:, :, i]
     print(f"{n:10s} mean {x.mean():6.2f}  p50 {np.percentile(x, 50):6.2f}  p90 {np.percentile(x, 90):6.2f}  p99 {np.percentile(x, 99):6.2f}  max {x.max():6.2f} | mean over frames of max over streams {x.max(1).mean():6.2f}")
@@ -24,11 +24,6 @@ tot = a[:, :, 10]
 worst = np.unravel_index(tot.argmax(), tot.shape)
 print("worst stream-frame:", worst, {n: round(float(a[worst[0], worst[1], i]), 2) for i, n in names.items()})
 na = pipe.get_num_active()
-raw = a * 1e3      # counters were scaled like nanoseconds
-slow = tot > np.percentile(tot, 85)
-for nm, sel in (("all stream-frames", np.ones_like(slow)), ("slowest 15%", slow)):
-    print(f"{nm}: per frame (3 solves): rows with >8 usable cells {raw[:,:,15][sel].mean():.2f}, usable cells per row-set {raw[:,:,16][sel].mean():.1f}, "
-          f"iterations {raw[:,:,17][sel].mean():.1f}, bidders/iteration {raw[:,:,18][sel].sum()/raw[:,:,17][sel].sum():.2f}, long-row bidders/iteration {raw[:,:,19][sel].sum()/raw[:,:,17][sel].sum():.2f}")
 print("num_active per stream: min", na.min(), "max", na.max())
 tot = a[:, :, 10]                       # [frames, B] us
 for K in (1, 2, 4, 8, 16):

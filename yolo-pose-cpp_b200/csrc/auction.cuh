@@ -289,4 +289,431 @@ static __device__ __noinline__ void auction_solve_rows32(const float* cost_s, in
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Hybrid single-warp solve (the tracker's default for at most 32 active rows).
+//
+// The bidder set is a warp-UNIFORM bitmask `ub` (bit i = i-th active row is unassigned), so no
+// ballot is needed to find it.  Per iteration one of two mappings is chosen by the number of
+// bidders:
+//   * many bidders (> HY_COLPAR_MAX, the first iterations of a solve): lane = row, every bidder
+//     scans its own cost row (the row-parallel scan of auction_solve_rows32);
+//   * few bidders (the long tail: an eviction chain of one to four rows that runs to the
+//     iteration limit whenever a stream has one active row more than it has detections):
+//     lane = column.  For each bidder the 32 lanes evaluate value = -cost - price of their columns
+//     in one step and three warp reductions on order-preserving integer keys give the best value,
+//     the lowest column holding it (hungarian.cu:63) and the second value (multiset second
+//     maximum, floor -1e9; :67-69).  All lanes then hold the same (column, bid) and update the
+//     per-column highest bid (ascending rows + strict '>' = lowest row among equal bids, :100),
+//     owner, price and `ub` redundantly — no broadcast, no atomics.
+// An iteration of the tail costs ~1/4 of a row scan.  Results are those of auction_solve_cta
+// bit for bit (tests compare the three implementations on random and degenerate problems).
+// ---------------------------------------------------------------------------------------
+constexpr int HY_COLPAR_MAX = 4;
+
+__device__ __forceinline__ unsigned hy_ord(float f) {            // float order -> unsigned order (-0.0 == +0.0)
+    unsigned b = __float_as_uint(f);
+    b = (b == 0x80000000u) ? 0u : b;
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float hy_unord(unsigned u) {
+    return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u));
+}
+
+static __device__ __noinline__ void auction_solve_hybrid32(const float* cost_s, int R, int C, const int* act_list, int na,
+                                                           int* row, int* col, float* price, int* owner,
+                                                           unsigned* colbid, int* colrow,
+                                                           unsigned long long* tele = nullptr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < R; t += 32) row[t] = -1;
+    for (int d = lane; d < C; d += 32) { col[d] = -1; price[d] = 0.0f; owner[d] = -1; colbid[d] = 0u; colrow[d] = 0x7fffffff; }
+    if (na <= 0 || C <= 0) return;
+    const bool mine = lane < na;
+    const float* cr = cost_s + (size_t)(mine ? act_list[lane] : 0) * C;
+    unsigned ub = (na >= 32) ? FULL : ((1u << na) - 1u);
+    __syncwarp();
+    float eps = 1.0f / (float)(R + 1);                                                     // :378
+    const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
+    const int C4 = C & ~3;
+    const unsigned ORD_FLOOR = hy_ord(-1e9f);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        if (ub == 0u) break;                                                               // fixed point
+        if (tele && lane == 0) { const int n = __popc(ub); tele[n == 1 ? 15 : (n == 2 ? 16 : (n <= 4 ? 17 : (n <= 8 ? 18 : 19)))] += 1000ull; }
+        if (__popc(ub) <= HY_COLPAR_MAX) {
+            // ---- lane = column ----
+            unsigned long long bcs = 0ull;                                                 // bid columns, 16 bits each
+            int nbids = 0;
+            unsigned rem = ub;
+#pragma unroll 1
+            while (rem) {
+                const int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const float* crj = cost_s + (size_t)act_list[j] * C;
+                float bv = -1e9f, sv = -1e9f;
+                int bc = 0x7fffffff;
+#pragma unroll 1
+                for (int d = lane; d < C; d += 32) {
+                    const float v = -crj[d] - price[d];                                    // :61
+                    if (v > bv) { sv = bv; bv = v; bc = d; } else if (v > sv) sv = v;
+                }
+                const unsigned kb = hy_ord(bv);
+                const unsigned m = __reduce_max_sync(FULL, kb);
+                if (m == ORD_FLOOR) continue;                                              // no column above -1e9: no bid
+                const int bcj = __reduce_min_sync(FULL, (kb == m) ? bc : 0x7fffffff);      // lowest column among the best
+                const unsigned m2 = __reduce_max_sync(FULL, hy_ord(bc == bcj ? sv : bv));  // best of the other columns
+                const unsigned bits = __float_as_uint(hy_unord(m) - hy_unord(m2) + eps);   // :99 (positive)
+                const unsigned cur = colbid[bcj];
+                if (bits > cur) { colbid[bcj] = bits; colrow[bcj] = j; }                   // ascending j: lowest row on ties
+                bcs |= (unsigned long long)bcj << (16 * nbids);
+                ++nbids;
+            }
+            if (nbids == 0) break;                                                         // no bid: fixed point
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < nbids; ++k) {                                              // :107-121
+                const int bc = (int)((bcs >> (16 * k)) & 0xffffull);
+                const unsigned wb = colbid[bc];
+                const int w = colrow[bc], prev = owner[bc];
+                const float p = price[bc];
+                __syncwarp();
+                if (wb != 0u) {
+                    owner[bc] = w; price[bc] = p + __uint_as_float(wb);
+                    colbid[bc] = 0u; colrow[bc] = 0x7fffffff;
+                    ub &= ~(1u << w);
+                    if (prev >= 0) ub |= 1u << prev;
+                }
+                __syncwarp();
+            }
+        } else {
+            // ---- lane = row ----
+            const bool unas = (ub >> lane) & 1u;
+            int bc = -1;
+            unsigned bid = 0u;
+            if (unas) {
+                float bv = -1e9f, sv = -1e9f;
+#pragma unroll 1
+                for (int d = 0; d < C4; d += 4) {
+                    const float v0 = -cr[d] - price[d], v1 = -cr[d + 1] - price[d + 1];    // :61
+                    const float v2 = -cr[d + 2] - price[d + 2], v3 = -cr[d + 3] - price[d + 3];
+                    if (v0 > bv) { sv = bv; bv = v0; bc = d; } else if (v0 > sv) sv = v0;  // ascending d: lowest column on ties (:63)
+                    if (v1 > bv) { sv = bv; bv = v1; bc = d + 1; } else if (v1 > sv) sv = v1;
+                    if (v2 > bv) { sv = bv; bv = v2; bc = d + 2; } else if (v2 > sv) sv = v2;
+                    if (v3 > bv) { sv = bv; bv = v3; bc = d + 3; } else if (v3 > sv) sv = v3;
+                }
+#pragma unroll 1
+                for (int d = C4; d < C; ++d) {
+                    const float v = -cr[d] - price[d];
+                    if (v > bv) { sv = bv; bv = v; bc = d; } else if (v > sv) sv = v;
+                }
+                if (bc >= 0) bid = __float_as_uint(bv - sv + eps);                         // :99
+            }
+            const unsigned pm = __ballot_sync(FULL, bc >= 0);
+            if (pm == 0u) break;                                                           // no bid: fixed point
+            if (bc >= 0) atomicMax(&colbid[bc], bid);
+            __syncwarp();
+            if (bc >= 0 && colbid[bc] == bid) atomicMin(&colrow[bc], lane);
+            __syncwarp();
+            const bool win = bc >= 0 && colbid[bc] == bid && colrow[bc] == lane;
+            __syncwarp();
+            int prev = -1;
+            if (win) {                                                                     // :107-121
+                colbid[bc] = 0u; colrow[bc] = 0x7fffffff;
+                prev = owner[bc];
+                owner[bc] = lane;
+                price[bc] += __uint_as_float(bid);
+            }
+            const unsigned wm = __ballot_sync(FULL, win);
+            const unsigned em = __reduce_or_sync(FULL, prev >= 0 ? (1u << prev) : 0u);     // evicted owners bid again
+            ub = (ub & ~wm) | em;
+            __syncwarp();
+        }
+        eps *= 0.9f;                                                                       // :402
+    }
+    __syncwarp();
+    for (int d = lane; d < C; d += 32) {
+        const int o = owner[d];
+        if (o >= 0) { const int slot = act_list[o]; col[d] = slot; row[slot] = d; }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Lean single-warp solve: at most 32 active rows, at most 64 columns (the tracker's own case:
+// max_detections = 64).  Same decisions as auction_solve_cta bit for bit.
+//
+// lane = column for every iteration with up to eight bidders (all but the first iteration of a
+// solve in practice).  Each lane keeps the price and the owner of its NC columns in REGISTERS;
+// the cost rows of the active rows were compacted to cc[i*C + d] (i = position in act_list) by
+// the whole CTA, so a bidder's row is one conflict-free load.  A bidder is evaluated by all
+// lanes at once: value = -cost - price of the lane's columns, then three CREDUX reductions on
+// order-preserving integer keys: the best value, the lowest column holding it packed with that
+// column's owner (hungarian.cu:63), the best of the other columns (multiset second maximum,
+// floor -1e9; :67-69).  Every lane then holds the same (column, bid, evicted owner) for every
+// bidder, so who wins a column (highest bid, lowest row among equal bids, :100), the price and
+// owner update (by the lane owning the column) and the next bidder set are plain warp-uniform
+// arithmetic: no ballot, no shuffle, no atomics, no shared-memory traffic inside the loop.
+//   * 1 bidder: the eviction chain.  The next bidder is the evicted owner, known right after
+//     the second reduction, so consecutive iterations overlap.
+//   * 2-4 bidders: independent instruction chains, evaluated together.
+//   * 5-8 bidders: one after the other, per-lane best bid, one REDUX.OR of toggle bits.
+// Rows that find no column above -1e9 leave the bidder set for good (prices only rise, so they
+// can never bid again; they stay unassigned exactly as upstream).
+// With more than eight bidders (iteration 0 of a solve) lane = row scans the compacted rows.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lean_ord(float f) {          // f is never -0.0 here (callers add +0.0f)
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+
+// value of the lane's columns for bidder row j: fmaxf drops NaN and everything at or below the -1e9 floor
+// (never best, never second: :55-69); + 0.0f folds -0.0 into +0.0 so the integer keys order like the floats
+template <int NC>
+__device__ __forceinline__ void lean_values(const float* cc, int C, int j, const float (&p)[NC], int lane,
+                                            float& bv, float& sv, int& bsel) {
+    float v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int d = lane + 32 * c;
+        v[c] = (d < C) ? (fmaxf(-cc[j * C + d] - p[c], -1e9f) + 0.0f) : -1e9f;             // :61
+    }
+    bv = v[0]; sv = -1e9f; bsel = 0;
+    if (NC == 2) {
+        if (v[NC - 1] > bv) { sv = bv; bv = v[NC - 1]; bsel = 1; } else sv = v[NC - 1];
+    }
+}
+
+#ifdef LEAN_PROFILE
+__device__ unsigned long long g_prof[8];
+#define LEAN_T(x) const long long x = clock64();
+#else
+#define LEAN_T(x)
+#endif
+struct LeanBid { unsigned m; int rk; unsigned bits; };   // warp-uniform: best-value key, (column << 8 | owner + 1), bid bits
+
+template <int NC>
+__device__ __forceinline__ LeanBid lean_bid(float bv, float sv, int bsel, const int (&own)[NC], int lane, float eps) {
+    const unsigned FULL = 0xffffffffu;
+    LeanBid r;
+    const unsigned kb = lean_ord(bv);
+    r.m = __reduce_max_sync(FULL, kb);                                                     // best value
+    const int osel = (NC == 2 && bsel) ? own[NC - 1] : own[0];
+    const int key = (kb == r.m) ? (((lane + 32 * bsel) << 8) | (osel + 1)) : 0x7fffffff;
+    r.rk = __reduce_min_sync(FULL, key);                                                   // lowest column holding it (:63) + its owner
+    const unsigned m2 = __reduce_max_sync(FULL, (key == r.rk) ? lean_ord(sv) : kb);        // best of the other columns
+    r.bits = __float_as_uint(hy_unord(r.m) - hy_unord(m2) + eps);                          // :99 (positive)
+    return r;
+}
+
+// one iteration with NB (2..4) bidders given as isolated bits of ub (ascending rows); returns false when nobody bid.
+// Branch-free warp-uniform resolution: a bidder without a column gets a unique negative column and bid 0.
+template <int NB, int NC>
+__device__ __forceinline__ bool lean_iter(const float* cc, int C, unsigned& ub, const unsigned (&bit)[NB], float eps,
+                                          float (&p)[NC], int (&own)[NC], int lane) {
+    const unsigned ORD_FLOOR = lean_ord(-1e9f);
+    LEAN_T(t0)
+    int j[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) j[b] = 31 - __clz(bit[b]);
+    float bv[NB], sv[NB];
+    int bsel[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) lean_values<NC>(cc, C, j[b], p, lane, bv[b], sv[b], bsel[b]);
+    LEAN_T(t1)
+    LeanBid q[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) q[b] = lean_bid<NC>(bv[b], sv[b], bsel[b], own, lane, eps);
+    LEAN_T(t2)
+    int bc[NB];
+    unsigned vm[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        vm[b] = (q[b].m != ORD_FLOOR) ? 0xffffffffu : 0u;                                  // bids at all
+        bc[b] = (q[b].m != ORD_FLOOR) ? (q[b].rk >> 8) : (-1 - b);
+    }
+    unsigned nub = ub, anym = 0u;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        unsigned lose = 0u;                                                                // highest bid, lowest row (:100)
+#pragma unroll
+        for (int o = 0; o < NB; ++o) {
+            if (o < b) lose |= (bc[o] == bc[b] && q[o].bits >= q[b].bits) ? 0xffffffffu : 0u;
+            if (o > b) lose |= (bc[o] == bc[b] && q[o].bits > q[b].bits) ? 0xffffffffu : 0u;
+        }
+        const unsigned wm = vm[b] & ~lose;
+        const int ow = q[b].rk & 0xff;                                                     // owner + 1
+        const unsigned evict = ow ? (1u << (ow - 1)) : 0u;
+        nub ^= bit[b] & (wm | ~vm[b]);                                                     // winners and rows without a column leave
+        nub |= evict & wm;                                                                 // evicted owners enter (:109-111)
+        anym |= wm;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (wm != 0u && bc[b] == lane + 32 * c) { p[c] += __uint_as_float(q[b].bits); own[c] = j[b]; }   // :113-118
+    }
+    ub = nub;
+#ifdef LEAN_PROFILE
+    const long long t3 = clock64();
+    if (lane == 0) { g_prof[0] += t1 - t0; g_prof[1] += t2 - t1; g_prof[2] += t3 - t2; g_prof[3] += 1; }
+#endif
+    return anym != 0u;
+}
+
+template <int NC>
+static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R, int C, const int* act_list, int na,
+                                                         int* row, int* col, float* price, int* owner,
+                                                         unsigned* colbid, int* colrow) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned ORD_FLOOR = lean_ord(-1e9f);
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < R; t += 32) row[t] = -1;
+    for (int d = lane; d < C; d += 32) { col[d] = -1; colbid[d] = 0u; colrow[d] = 0x7fffffff; }
+    if (na <= 0 || C <= 0) return;
+    float p[NC];
+    int own[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p[c] = 0.0f; own[c] = -1; }
+    unsigned ub = (na >= 32) ? FULL : ((1u << na) - 1u);                                   // unassigned rows that may still bid
+    __syncwarp();
+    float eps = 1.0f / (float)(R + 1);                                                     // :378
+    const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
+    const int C4 = C & ~3;
+    int it = 0;
+#pragma unroll 1
+    while (it < iters && ub != 0u) {
+#ifdef LEAN_PROFILE
+        { static __device__ long long last; const long long now = clock64(); if (lane == 0) { if (it > 1) g_prof[4] += now - last; last = now; } }
+#endif
+        // peel the lowest bidders off the mask (no bidder count, no jump table on the way to the common cases)
+        unsigned bit[4];
+        bit[0] = ub & (0u - ub);
+        const unsigned r1 = ub ^ bit[0];
+        bit[1] = r1 & (0u - r1);
+        const unsigned r2 = r1 ^ bit[1];
+        bit[2] = r2 & (0u - r2);
+        const unsigned r3 = r2 ^ bit[2];
+        bit[3] = r3 & (0u - r3);
+        const unsigned r4 = r3 ^ bit[3];
+        bool any = true;
+        if (r1 == 0u) {
+            // ---- the eviction chain: one bidder per iteration until the limit or the first free column ----
+            int j = 31 - __clz(ub);
+#pragma unroll 1
+            for (; it < iters; ++it) {
+                float bv, sv;
+                int bsel;
+                lean_values<NC>(cc, C, j, p, lane, bv, sv, bsel);
+                const LeanBid q = lean_bid<NC>(bv, sv, bsel, own, lane, eps);
+                if (q.m == ORD_FLOOR) break;                                               // cannot bid: fixed point
+                const int bc = q.rk >> 8;
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (bc == lane + 32 * c) { p[c] += __uint_as_float(q.bits); own[c] = j; }
+                j = (q.rk & 0xff) - 1;                                                     // the evicted owner bids next
+                eps *= 0.9f;                                                               // :402
+                if (j < 0) break;                                                          // everybody is assigned
+            }
+            break;
+        } else if (r2 == 0u) {
+            const unsigned b2[2] = {bit[0], bit[1]};
+            any = lean_iter<2, NC>(cc, C, ub, b2, eps, p, own, lane);
+        } else if (r3 == 0u) {
+            const unsigned b3[3] = {bit[0], bit[1], bit[2]};
+            any = lean_iter<3, NC>(cc, C, ub, b3, eps, p, own, lane);
+        } else if (r4 == 0u) {
+            any = lean_iter<4, NC>(cc, C, ub, bit, eps, p, own, lane);
+        } else if (__popc(ub) <= 8) {
+            // ---- one bidder after the other: per-lane highest bid, toggle bits through one REDUX.OR ----
+            unsigned best[NC];
+            int w[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { best[c] = 0u; w[c] = -1; }
+            unsigned rem = ub, drop = 0u;
+#pragma unroll 1
+            while (rem) {
+                const int jb = __ffs(rem) - 1;
+                rem &= rem - 1;
+                float bv, sv;
+                int bsel;
+                lean_values<NC>(cc, C, jb, p, lane, bv, sv, bsel);
+                const LeanBid q = lean_bid<NC>(bv, sv, bsel, own, lane, eps);
+                if (q.m == ORD_FLOOR) { drop |= 1u << jb; continue; }
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if ((q.rk >> 8) == lane + 32 * c && q.bits > best[c]) { best[c] = q.bits; w[c] = jb; }   // ascending rows + '>'
+            }
+            unsigned tog = 0u;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (w[c] >= 0) {                                                           // :107-121
+                    tog |= 1u << w[c];
+                    if (own[c] >= 0) tog |= 1u << own[c];
+                    own[c] = w[c];
+                    p[c] += __uint_as_float(best[c]);
+                }
+            tog = __reduce_or_sync(FULL, tog);
+            any = tog != 0u;
+            ub = (ub & ~drop) ^ tog;                                                       // winners leave, evicted owners enter
+        } else {
+            // ---- lane = row ----
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (lane + 32 * c < C) { price[lane + 32 * c] = p[c]; owner[lane + 32 * c] = own[c]; }
+            __syncwarp();
+            const bool unas = (ub >> lane) & 1u;
+            const float* cr = cc + lane * C;
+            int bc = -1;
+            unsigned bid = 0u;
+            if (unas) {
+                float bv = -1e9f, sv = -1e9f;
+#pragma unroll 1
+                for (int d = 0; d < C4; d += 4) {
+                    const float v0 = -cr[d] - price[d], v1 = -cr[d + 1] - price[d + 1];    // :61
+                    const float v2 = -cr[d + 2] - price[d + 2], v3 = -cr[d + 3] - price[d + 3];
+                    if (v0 > bv) { sv = bv; bv = v0; bc = d; } else if (v0 > sv) sv = v0;  // ascending d: lowest column on ties (:63)
+                    if (v1 > bv) { sv = bv; bv = v1; bc = d + 1; } else if (v1 > sv) sv = v1;
+                    if (v2 > bv) { sv = bv; bv = v2; bc = d + 2; } else if (v2 > sv) sv = v2;
+                    if (v3 > bv) { sv = bv; bv = v3; bc = d + 3; } else if (v3 > sv) sv = v3;
+                }
+#pragma unroll 1
+                for (int d = C4; d < C; ++d) {
+                    const float v = -cr[d] - price[d];
+                    if (v > bv) { sv = bv; bv = v; bc = d; } else if (v > sv) sv = v;
+                }
+                if (bc >= 0) bid = __float_as_uint(bv - sv + eps);                         // :99
+            }
+            const unsigned pm = __ballot_sync(FULL, bc >= 0);
+            any = pm != 0u;
+            if (any) {
+                if (bc >= 0) atomicMax(&colbid[bc], bid);
+                __syncwarp();
+                if (bc >= 0 && colbid[bc] == bid) atomicMin(&colrow[bc], lane);
+                __syncwarp();
+                const bool win = bc >= 0 && colbid[bc] == bid && colrow[bc] == lane;
+                __syncwarp();
+                int prev = -1;
+                if (win) {                                                                 // :107-121
+                    colbid[bc] = 0u; colrow[bc] = 0x7fffffff;
+                    prev = owner[bc];
+                    owner[bc] = lane;
+                    price[bc] += __uint_as_float(bid);
+                }
+                const unsigned wm = __ballot_sync(FULL, win);
+                const unsigned em = __reduce_or_sync(FULL, prev >= 0 ? (1u << prev) : 0u); // evicted owners bid again
+                ub = (pm & ~wm) | em;                                                      // rows without a column leave for good
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (lane + 32 * c < C) { p[c] = price[lane + 32 * c]; own[c] = owner[lane + 32 * c]; }
+            }
+        }
+        if (!any) break;                                                                   // no bid: fixed point
+        eps *= 0.9f;                                                                       // :402
+        ++it;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (own[c] >= 0) { const int slot = act_list[own[c]]; col[lane + 32 * c] = slot; row[slot] = lane + 32 * c; }
+}
+
 }  // namespace pb

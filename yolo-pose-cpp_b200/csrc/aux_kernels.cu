@@ -93,18 +93,52 @@ __global__ void kf3_cov_kernel(const float* diag, int track, float* cov) {
 // Stand-alone auction: one CTA per problem, cost rows streamed from global/L2.
 // =======================================================================================
 __global__ void __launch_bounds__(256)
-auction_batch_kernel(const float* cost, int R, int C, int* row_out, int* col_out, const int* active) {
+auction_batch_kernel(const float* cost, int R, int C, int* row_out, int* col_out, const int* active, int stage_cost) {
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned long long* colbid = reinterpret_cast<unsigned long long*>(sm);
     float* price = reinterpret_cast<float*>(colbid + C);
     int* col = reinterpret_cast<int*>(price + C);
     int* row = col + C;
     int* act = row + R;
-    int* flags = act + R;
+    int* flags = act + R;          // [4]: 0-1 iteration flags, 2 active count
+    int* owner = flags + 4;        // [C]   (stage_cost only)
+    int* act_list = owner + C;     // [R]
+    float* cost_s = reinterpret_cast<float*>(act_list + R);   // [R*C]
     const int b = blockIdx.x;
+    const float* cb = cost + (size_t)b * R * C;
     for (int t = threadIdx.x; t < R; t += blockDim.x) act[t] = active ? active[(size_t)b * R + t] : 1;
+    if (stage_cost) for (int i = threadIdx.x; i < R * C; i += blockDim.x) cost_s[i] = cb[i];
     __syncthreads();
-    auction_solve_cta(cost + (size_t)b * R * C, R, C, act, row, col, price, colbid, flags, threadIdx.x, blockDim.x);
+    int na = 33;
+    if (stage_cost) {
+        // ordered list of the active rows; the single-warp solve takes up to 32 of them
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int t = 0; t < R; ++t) if (act[t] != 0) act_list[n++] = t;
+            flags[2] = n;
+        }
+        __syncthreads();
+        na = flags[2];
+    }
+    if (na <= 32 && C <= 64) {
+        float* cc = cost_s + (size_t)R * C;      // [32*C] compacted active rows
+        for (int i = threadIdx.x; i < na * C; i += blockDim.x) { const int ai = i / C; cc[i] = cost_s[act_list[ai] * C + (i - ai * C)]; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned* cb32 = reinterpret_cast<unsigned*>(colbid);
+            int* cr32 = reinterpret_cast<int*>(colbid) + C;
+            if (C <= 32) auction_solve_lean32<1>(cc, R, C, act_list, na, row, col, price, owner, cb32, cr32);
+            else auction_solve_lean32<2>(cc, R, C, act_list, na, row, col, price, owner, cb32, cr32);
+        }
+        __syncthreads();
+    } else if (na <= 32) {
+        if (threadIdx.x < 32)
+            auction_solve_hybrid32(cost_s, R, C, act_list, na, row, col, price, owner,
+                                   reinterpret_cast<unsigned*>(colbid), reinterpret_cast<int*>(colbid) + C);
+        __syncthreads();
+    } else {
+        auction_solve_cta(cb, R, C, act, row, col, price, colbid, flags, threadIdx.x, blockDim.x);
+    }
     for (int t = threadIdx.x; t < R; t += blockDim.x) row_out[(size_t)b * R + t] = row[t];
     for (int d = threadIdx.x; d < C; d += blockDim.x) col_out[(size_t)b * C + d] = col[d];
 }
@@ -342,14 +376,19 @@ int pb_nms_legacy(const void* d_dets, const int* d_offsets, int num_images, int 
 int pb_auction_solve(const float* d_cost, int batch, int num_rows, int num_cols, int* d_row_assign,
                      int* d_col_assign, const int* d_row_active, pb_stream_t stream) {
     if (batch <= 0 || num_rows <= 0 || num_cols <= 0) return PB_OK;          // hungarian.cu:368
-    const size_t smem = (size_t)num_cols * 16 + (size_t)num_rows * 8 + 16;
+    size_t smem = (size_t)num_cols * 16 + (size_t)num_rows * 8 + 16;
+    // small tables are staged in shared memory; problems with at most 32 active rows then take the
+    // single-warp hybrid solve the tracker uses (auction.cuh), the others the CTA-wide one
+    const size_t staged = smem + (size_t)num_cols * 4 + (size_t)num_rows * 4 + (size_t)num_rows * num_cols * 4 + (num_cols <= 64 ? (size_t)32 * num_cols * 4 : 0);
+    const int stage_cost = (staged <= 96 * 1024 && num_cols <= 65535) ? 1 : 0;
+    if (stage_cost) smem = staged;
     if (smem > 200 * 1024) { pb_set_error("pb_auction_solve: problem too large"); return PB_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(auction_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { pb_set_error("pb_auction_solve: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     }
     auction_batch_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(d_cost, num_rows, num_cols, d_row_assign,
-                                                                     d_col_assign, d_row_active);
+                                                                     d_col_assign, d_row_active, stage_cost);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { pb_set_error("pb_auction_solve: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }

@@ -196,7 +196,7 @@ __device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
 
 struct Ctx {
     TkSmem s;
-    int T, D, Dw, tid, nthreads, lane, warp, nwarps;
+    int T, D, Dw, tid, nthreads, lane, warp, nwarps, variant;
     bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
     int term_floats;
     float* cost;        // shared or global, flat [t*D + d]
@@ -207,9 +207,29 @@ struct Ctx {
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
 __device__ __forceinline__ void auction_solve(Ctx& c, int na) {
     TkSmem& s = c.s;
-    if (c.warp_auction && na <= 32) {
-        if (c.tid < 32) auction_solve_rows32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
-                                              reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D);
+    if (c.warp_auction && na <= 32 && c.D <= 64 && c.variant == 2) {
+        // compact the active rows (cc[i*D + d], i = position in act_list) into the term buffer, which is idle
+        // between cost passes: the single-warp solve then reads a bidder's row with one conflict-free load
+        float* cc = s.terms;
+        const int D = c.D;
+        for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = i / D; cc[i] = s.cost[s.act_list[ai] * D + (i - ai * D)]; }
+        __syncthreads();
+        if (c.tid < 32) {
+            unsigned* cb = reinterpret_cast<unsigned*>(s.colbid);
+            int* cr = reinterpret_cast<int*>(s.colbid) + c.D;
+            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr);
+            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr);
+        }
+        __syncthreads();
+    } else if (c.warp_auction && na <= 32) {
+        if (c.tid < 32) {
+            if (c.variant == 0)
+                auction_solve_rows32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
+                                     reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D);
+            else
+                auction_solve_hybrid32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
+                                       reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D, s.acc);
+        }
         __syncthreads();
     } else if (c.warp_auction) {
         // colbid (8 B per column) doubles as the 32-bit bid array + the lowest-row array
@@ -370,6 +390,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     Ctx c;
     tk_carve(smem_raw, P.T, P.Dm, P.cost_in_smem, P.det_in_smem, P.pred_in_smem, P.term_floats, &c.s);
     c.term_floats = P.term_floats;
+    c.variant = P.auction_variant;
     TkSmem& s = c.s;
     const int b = blockIdx.x;
     const int T = P.T, Dm = P.Dm;
@@ -818,6 +839,8 @@ cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSourc
     }
     p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
     p.term_floats = plan.term_floats;
+    static const int variant = [] { const char* e = getenv("PB_AUCTION"); return e ? atoi(e) : 2; }();
+    p.auction_variant = variant;
     if (v == 0) pb_tracker_kernel<256><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
     else if (v == 1) pb_tracker_kernel<512><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
     else pb_tracker_kernel<1024><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
