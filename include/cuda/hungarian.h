@@ -5,8 +5,9 @@
 // iterations, eps *= 0.9, lowest column on equal value and lowest row on equal bid.  `threshold`
 // is accepted and ignored, as upstream.  One launch per solve instead of 100 kernels + 53
 // memsets.  GreedyMatcherCUDA (hungarian.cu:407-543) is provided with the deterministic rule of
-// its own host path.  The host-side legacy LinearAssignmentCUDA::solve() (hungarian.cu:235-339) is
-// not part of the hot path and is not provided.
+// its own host path.  The host-side legacy LinearAssignmentCUDA::solve() (hungarian.cu:235-339:
+// greedy below 100 cells, else 3*rows auction iterations and a host threshold filter) runs as one
+// launch of pb_assign_legacy; solveDevice() (:412-434) is the synchronous device-pointer form.
 #pragma once
 
 #include <utility>
@@ -20,6 +21,45 @@ namespace cuda {
 class LinearAssignmentCUDA {
 public:
     explicit LinearAssignmentCUDA(int max_size = 256) : max_size_(max_size) {}
+    ~LinearAssignmentCUDA() { cudaFree(d_buf_); }
+    LinearAssignmentCUDA(const LinearAssignmentCUDA&) = delete;
+    LinearAssignmentCUDA& operator=(const LinearAssignmentCUDA&) = delete;
+
+    // Legacy entry point (hungarian.cu:235-339): host cost matrix in, host assignments out, returns the
+    // number of assignments with cost <= threshold.  Blocking, like upstream.
+    int solve(const float* cost_matrix, int num_rows, int num_cols, int* row_assignments, int* col_assignments,
+              float threshold = 1.0f) {
+        if (num_rows == 0 || num_cols == 0) return 0;                          // :243
+        const size_t cells = (size_t)num_rows * num_cols;
+        const size_t bytes = cells * sizeof(float) + ((size_t)num_rows + num_cols + 1) * sizeof(int);
+        if (bytes > buf_bytes_) {
+            cudaFree(d_buf_); d_buf_ = nullptr; buf_bytes_ = 0;
+            detail::cu_check(cudaMalloc(&d_buf_, bytes), "cudaMalloc");
+            buf_bytes_ = bytes;
+        }
+        float* d_cost = static_cast<float*>(d_buf_);
+        int* d_row = reinterpret_cast<int*>(d_cost + cells);
+        int* d_col = d_row + num_rows;
+        int* d_cnt = d_col + num_cols;
+        detail::cu_check(cudaMemcpy(d_cost, cost_matrix, cells * sizeof(float), cudaMemcpyHostToDevice), "upload");
+        detail::pb_check(pb_assign_legacy(d_cost, 1, num_rows, num_cols, threshold, d_row, d_col, d_cnt, nullptr), "pb_assign_legacy");
+        int count = 0;
+        detail::cu_check(cudaMemcpy(row_assignments, d_row, (size_t)num_rows * sizeof(int), cudaMemcpyDeviceToHost), "download");
+        detail::cu_check(cudaMemcpy(col_assignments, d_col, (size_t)num_cols * sizeof(int), cudaMemcpyDeviceToHost), "download");
+        detail::cu_check(cudaMemcpy(&count, d_cnt, sizeof(int), cudaMemcpyDeviceToHost), "download");
+        return count;
+    }
+
+    // Synchronous device-pointer solve (hungarian.cu:412-434): returns the number of assigned rows.
+    int solveDevice(float* d_cost_matrix, int num_rows, int num_cols, int* d_row_assignments, int* d_col_assignments,
+                    float threshold = 1.0f) {
+        solveDeviceAsync(d_cost_matrix, num_rows, num_cols, d_row_assignments, d_col_assignments, threshold, nullptr);
+        std::vector<int> h_row((size_t)num_rows);
+        detail::cu_check(cudaMemcpy(h_row.data(), d_row_assignments, h_row.size() * sizeof(int), cudaMemcpyDeviceToHost), "download");
+        int count = 0;
+        for (int v : h_row) count += (v >= 0);
+        return count;
+    }
 
     void solveDeviceAsync(const float* d_cost_matrix, int num_rows, int num_cols, int* d_row_assignments,
                           int* d_col_assignments, float threshold, cudaStream_t stream = 0) {
@@ -44,6 +84,8 @@ public:
 
 private:
     int max_size_;
+    void* d_buf_ = nullptr;       // staging of solve(): cost matrix + assignments + count
+    size_t buf_bytes_ = 0;
 };
 
 // GreedyMatcherCUDA: cells below the threshold in ascending (cost, row, col) order, each taken when

@@ -218,6 +218,21 @@ int pb_pose_distance(const float* d_tracks, const float* d_dets, int batch, int 
 int pb_greedy_match(const float* d_cost, int batch, int num_rows, int num_cols, float threshold,
                     int* d_row_matched, pb_stream_t stream);
 
+/* LinearAssignmentCUDA::solve (hungarian.cu:235-339), the legacy host-threshold entry point, for `batch`
+ * problems on the device: fewer than 100 cells -> greedyAssign (:198-233); otherwise the auction over all
+ * rows with at most 3*rows iterations (:283) and the convergence exit of :317, then assignments with
+ * cost > threshold are cleared (:328-336).  d_count [batch] (may be NULL) = solve()'s return value. */
+int pb_assign_legacy(const float* d_cost, int batch, int num_rows, int num_cols, float threshold,
+                     int* d_row_assign, int* d_col_assign, int* d_count, pb_stream_t stream);
+
+/* PreprocessorCUDA::preprocess (preprocess.cu:19-153) for a batch of frames in one launch:
+ * d_frames = BGR u8 HWC images, frame f at d_frames + f*frame_stride_bytes with size d_sizes[2f] x
+ * d_sizes[2f+1] (width, height); d_out [batch, 3, target_height, target_width] fp32 RGB in [0,1],
+ * gray 114/255 letterbox bars; d_xform [batch, 4] (may be NULL) = {scale_x, scale_y, pad_x, pad_y} as
+ * preprocess() returns them — the layout pb_set_output_transform takes to undo the letterbox. */
+int pb_letterbox_batch(const unsigned char* d_frames, size_t frame_stride_bytes, const int* d_sizes, int batch,
+                       int target_width, int target_height, float* d_out, float* d_xform, pb_stream_t stream);
+
 /* ---- stage-level entry points ------------------------------------------------------ */
 
 /* nms.h:48-60 declares this symbol and never defines it.  Device pointers; keep[i] in

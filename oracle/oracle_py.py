@@ -51,6 +51,9 @@ def lib() -> C.CDLL:
         L.orc_pose_distance.restype = None
         L.orc_greedy_match.argtypes = [vp, ip, ip, fp, vp]
         L.orc_greedy_match.restype = None
+        L.orc_assign_legacy.argtypes = [vp, ip, ip, fp, vp, vp]
+        L.orc_letterbox.argtypes = [vp, ip, ip, ip, ip, vp, vp]
+        L.orc_letterbox.restype = None
         L.orc_tracker_create.argtypes = [C.POINTER(TrackerConfig)]
         L.orc_tracker_create.restype = vp
         L.orc_tracker_destroy.argtypes = [vp]
@@ -166,6 +169,24 @@ def greedy_match(cost, threshold) -> np.ndarray:
     out = np.full(R, -1, np.int32)
     lib().orc_greedy_match(c.ctypes.data, R, Cc, threshold, out.ctypes.data)
     return out
+
+
+def assign_legacy(cost, threshold):
+    """LinearAssignmentCUDA::solve (hungarian.cu:235-339) -> (row, col, count)."""
+    c = _f32(cost)
+    R, Cc = c.shape
+    row = np.full(R, -1, np.int32); col = np.full(Cc, -1, np.int32)
+    n = lib().orc_assign_legacy(c.ctypes.data, R, Cc, threshold, row.ctypes.data, col.ctypes.data)
+    return row, col, int(n)
+
+
+def letterbox(bgr: np.ndarray, tw=640, th=640):
+    """PreprocessorCUDA::preprocess (preprocess.cu:19-153): bgr [h,w,3] u8 -> ([3,th,tw] fp32, xform[4])."""
+    img = np.ascontiguousarray(bgr, dtype=np.uint8)
+    h, w, _ = img.shape
+    out = np.empty((3, th, tw), np.float32); xf = np.empty(4, np.float32)
+    lib().orc_letterbox(img.ctypes.data, w, h, tw, th, out.ctypes.data, xf.ctypes.data)
+    return out, xf
 
 
 class Tracker:

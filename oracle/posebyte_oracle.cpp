@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -297,14 +298,14 @@ bool literal_auction() {
 
 void auction(const float* cost, int R, int C, int* row, int* col, const int* row_active,
              std::vector<float>& price, std::vector<float>& bestv, std::vector<float>& secv,
-             std::vector<int>& bestc) {
+             std::vector<int>& bestc, int max_iters = -1) {
     if (R == 0 || C == 0) return;                                  // :368
     for (int r = 0; r < R; ++r) row[r] = -1;                       // :373-375
     for (int c = 0; c < C; ++c) col[c] = -1;
     price.assign(C, 0.0f);
     bestv.resize(R); secv.resize(R); bestc.resize(R);
     float eps = 1.0f / (R + 1);                                    // :378
-    int iters = std::min(R * 3, 50);                               // :379
+    int iters = max_iters >= 0 ? max_iters : std::min(R * 3, 50);  // :379 (legacy solve: 3R, :283)
     const bool literal = literal_auction();
     for (int it = 0; it < iters; ++it) {
         bool any = false;
@@ -962,6 +963,75 @@ void orc_auction(const float* cost, int R, int C, int* row, int* col, const int*
     std::vector<float> p, bv, sv;
     std::vector<int> bc;
     auction(cost, R, C, row, col, row_active, p, bv, sv, bc);
+}
+
+// LinearAssignmentCUDA::solve, hungarian.cu:235-339 (the host-threshold legacy entry point).
+// Fewer than 100 cells: greedyAssign (:198-233) — rows in order, each takes its cheapest unused column
+// below the threshold (strict '<': lowest column on ties).  Otherwise the auction with ALL rows active,
+// 3*rows iterations at most (:283), the convergence exit of :317 (an iteration without a bid — the same
+// fixed point the early stop above uses), then assignments whose cost exceeds the threshold are
+// cleared (:328-336).  Returns the number of assignments kept.
+int orc_assign_legacy(const float* cost, int R, int C, float threshold, int* row, int* col) {
+    if (R == 0 || C == 0) return 0;                                    // :243
+    int count = 0;
+    if (R * C < 100) {                                                 // :246
+        std::vector<char> used(C, 0);
+        for (int r = 0; r < R; ++r) row[r] = -1;
+        for (int c = 0; c < C; ++c) col[c] = -1;
+        for (int r = 0; r < R; ++r) {
+            float best = threshold;
+            int bc = -1;
+            for (int c = 0; c < C; ++c)
+                if (!used[c]) { const float v = cost[(size_t)r * C + c]; if (v < best) { best = v; bc = c; } }
+            if (bc >= 0) { row[r] = bc; col[bc] = r; used[bc] = 1; ++count; }
+        }
+        return count;
+    }
+    std::vector<float> p, bv, sv;
+    std::vector<int> bc;
+    auction(cost, R, C, row, col, nullptr, p, bv, sv, bc, R * 3);
+    for (int r = 0; r < R; ++r) {                                      // :328-336
+        const int c = row[r];
+        if (c >= 0) {
+            if (cost[(size_t)r * C + c] <= threshold) ++count;
+            else { col[c] = -1; row[r] = -1; }
+        }
+    }
+    return count;
+}
+
+// PreprocessorCUDA::preprocess + kernelPreprocess, preprocess.cu:19-153: letterbox resize (bilinear),
+// BGR -> RGB, /255, HWC u8 -> CHW fp32, gray 114/255 padding.  xform4 = {scale_x, scale_y, pad_x, pad_y}
+// as returned upstream (scale_x = scale_y = 1/scale; the pads are integers) — the transform
+// scaleTrackOutputs (main.cpp:48-68) later undoes.
+void orc_letterbox(const unsigned char* bgr, int w, int h, int tw, int th, float* out, float* xform4) {
+    const float scale = std::min(static_cast<float>(tw) / w, static_cast<float>(th) / h);   // :109-112
+    const int new_w = static_cast<int>(w * scale), new_h = static_cast<int>(h * scale);      // :114-115
+    const int pad_x = (tw - new_w) / 2, pad_y = (th - new_h) / 2;                            // :117-118
+    if (xform4) { xform4[0] = 1.0f / scale; xform4[1] = 1.0f / scale; xform4[2] = (float)pad_x; xform4[3] = (float)pad_y; }
+    const size_t plane = (size_t)tw * th;
+    for (int ty = 0; ty < th; ++ty)
+        for (int tx = 0; tx < tw; ++tx) {
+            float* o = out + (size_t)ty * tw + tx;
+            if (tx < pad_x || tx >= pad_x + new_w || ty < pad_y || ty >= pad_y + new_h) {    // :39-47
+                const float gray = 114.0f / 255.0f;
+                o[0] = gray; o[plane] = gray; o[2 * plane] = gray;
+                continue;
+            }
+            float sx = (tx - pad_x) / scale, sy = (ty - pad_y) / scale;                     // :50-51
+            sx = std::fmin(std::fmax(sx, 0.0f), w - 1.001f);                                 // :54-55
+            sy = std::fmin(std::fmax(sy, 0.0f), h - 1.001f);
+            const int x0 = (int)sx, y0 = (int)sy;
+            const int x1 = std::min(x0 + 1, w - 1), y1 = std::min(y0 + 1, h - 1);
+            const float wx = sx - x0, wy = sy - y0;
+            for (int c = 0; c < 3; ++c) {                                                    // :66-80
+                const float v00 = bgr[((size_t)y0 * w + x0) * 3 + c], v01 = bgr[((size_t)y0 * w + x1) * 3 + c];
+                const float v10 = bgr[((size_t)y1 * w + x0) * 3 + c], v11 = bgr[((size_t)y1 * w + x1) * 3 + c];
+                const float v = (1 - wx) * (1 - wy) * v00 + wx * (1 - wy) * v01 + (1 - wx) * wy * v10 + wx * wy * v11;
+                const int oc = (c == 0) ? 2 : (c == 2) ? 0 : c;
+                o[oc * plane] = v / 255.0f;
+            }
+        }
 }
 
 void* orc_tracker_create(const orc_tracker_config* cfg) { return new Tracker(*cfg); }

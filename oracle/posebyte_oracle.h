@@ -69,6 +69,12 @@ void orc_auction(const float* cost, int num_rows, int num_cols,
 void orc_pose_distance(const float* tracks, const float* dets, int nt, int nd, int mode, float alpha, float* out);
 /* GreedyMatcherCUDA::match host rule, hungarian.cu:441-467; row_matched [R] = column or -1. */
 void orc_greedy_match(const float* cost, int R, int C, float threshold, int* row_matched);
+/* LinearAssignmentCUDA::solve (hungarian.cu:235-339): greedy below 100 cells, else auction with 3*rows
+ * iterations and the host threshold filter.  Returns the number of assignments kept. */
+int orc_assign_legacy(const float* cost, int R, int C, float threshold, int* row, int* col);
+/* PreprocessorCUDA::preprocess (preprocess.cu:19-153): bgr [h,w,3] u8 -> out [3,th,tw] fp32,
+ * xform4 = {scale_x, scale_y, pad_x, pad_y}. */
+void orc_letterbox(const unsigned char* bgr, int w, int h, int tw, int th, float* out, float* xform4);
 
 /* A5-A16  gpu_tracker.cu:102-919,1057-1639. */
 void* orc_tracker_create(const orc_tracker_config* cfg);

@@ -23,6 +23,7 @@
 #include "cuda/hungarian.h"
 #include "cuda/gpu_postprocess.h"
 #include "cuda/nms.h"
+#include "cuda/preprocess.h"
 #define private public
 #include "cuda/gpu_tracker.h"
 #undef private
@@ -126,6 +127,22 @@ void ref_auction(const float* h_cost, int R, int C, int* h_row, int* h_col, cons
     cudaMemcpy(h_row, d_row, R * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(h_col, d_col, C * 4, cudaMemcpyDeviceToHost);
     cudaFree(d_cost); cudaFree(d_row); cudaFree(d_col); if (d_act) cudaFree(d_act);
+}
+
+// LinearAssignmentCUDA::solve (legacy host entry point, hungarian.cu:235-339); returns the count.
+int ref_assign_solve(const float* h_cost, int R, int C, float threshold, int* h_row, int* h_col) {
+    LinearAssignmentCUDA la(std::max(std::max(R, C), 1));
+    return la.solve(h_cost, R, C, h_row, h_col, threshold);
+}
+
+// ---- PreprocessorCUDA (preprocess.cu) -----------------------------------------------------------
+// h_bgr [h,w,3] u8 -> h_out [3,th,tw] fp32, xform4 = {scale_x, scale_y, pad_x, pad_y}
+void ref_preprocess(const unsigned char* h_bgr, int w, int h, int tw, int th, float* h_out, float* xform4) {
+    PreprocessorCUDA pp(w, h, tw, th);
+    float sx = 0, sy = 0; int px = 0, py = 0;
+    pp.preprocess(h_bgr, w, h, pp.getDeviceOutput(), sx, sy, px, py);
+    cudaMemcpy(h_out, pp.getDeviceOutput(), (size_t)3 * tw * th * 4, cudaMemcpyDeviceToHost);
+    xform4[0] = sx; xform4[1] = sy; xform4[2] = (float)px; xform4[3] = (float)py;
 }
 
 // ---- OKSDistanceCUDA / GreedyMatcherCUDA -------------------------------------------------------

@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         L.ref_auction.argtypes = [vp, ip, ip, vp, vp, vp]; L.ref_auction.restype = None
         L.ref_pose_distance.argtypes = [vp, vp, ip, ip, ip, fp, vp]; L.ref_pose_distance.restype = None
         L.ref_greedy_match.argtypes = [vp, ip, ip, fp, vp]
+        L.ref_assign_solve.argtypes = [vp, ip, ip, fp, vp, vp]
+        L.ref_preprocess.argtypes = [vp, ip, ip, ip, ip, vp, vp]; L.ref_preprocess.restype = None
         L.ref_kf3_create.argtypes = [ip]; L.ref_kf3_create.restype = vp
         L.ref_kf3_destroy.argtypes = [vp]; L.ref_kf3_destroy.restype = None
         L.ref_kf3_initiate.argtypes = [vp, vp, vp, ip]; L.ref_kf3_initiate.restype = None
@@ -111,6 +113,24 @@ def pose_distance(tracks, dets, mode=0, alpha=0.7) -> np.ndarray:
     with quiet():
         lib().ref_pose_distance(t.ctypes.data, d.ctypes.data, len(t), len(d), mode, alpha, out.ctypes.data)
     return out
+
+
+def assign_solve(cost, threshold):
+    """LinearAssignmentCUDA::solve (host entry point) -> (row, col, count)."""
+    c = _f32(cost)
+    R, Cc = c.shape
+    row = np.full(R, -1, np.int32); col = np.full(Cc, -1, np.int32)
+    n = lib().ref_assign_solve(c.ctypes.data, R, Cc, threshold, row.ctypes.data, col.ctypes.data)
+    return row, col, int(n)
+
+
+def preprocess(bgr, tw=640, th=640):
+    """PreprocessorCUDA::preprocess -> ([3,th,tw] fp32, xform[4])."""
+    img = np.ascontiguousarray(bgr, dtype=np.uint8)
+    h, w, _ = img.shape
+    out = np.empty((3, th, tw), np.float32); xf = np.empty(4, np.float32)
+    lib().ref_preprocess(img.ctypes.data, w, h, tw, th, out.ctypes.data, xf.ctypes.data)
+    return out, xf
 
 
 def greedy_match(cost, threshold) -> np.ndarray:

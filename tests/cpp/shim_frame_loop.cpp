@@ -12,6 +12,7 @@
 #include "cuda/gpu_postprocess.h"
 #include "cuda/gpu_tracker.h"
 #include "cuda/hungarian.h"
+#include "cuda/preprocess.h"
 #include "cuda/kalman_filter.h"
 #include "cuda/nms.h"
 
@@ -83,6 +84,20 @@ int main(int argc, char** argv) {
         int row[3];
         cudaMemcpy(row, d_row, 12, cudaMemcpyDeviceToHost);
         std::printf("auction %d %d %d\n", row[0], row[1], row[2]);
+        // legacy host entry point: 9 cells -> greedy rows below the threshold (row 1 finds only 0.7 and 0.9 left? no: 0.2)
+        int hrow[3], hcol[3];
+        const int nsolved = la.solve(cost, 3, 3, hrow, hcol, 0.25f);
+        std::printf("solve %d : %d %d %d\n", nsolved, hrow[0], hrow[1], hrow[2]);
+
+        // PreprocessorCUDA: a 4x2 BGR frame into a 8x8 letterbox
+        PreprocessorCUDA pp(16, 16, 8, 8);
+        std::vector<uint8_t> img(4 * 2 * 3);
+        for (size_t i = 0; i < img.size(); ++i) img[i] = (uint8_t)(10 * i);
+        float sx, sy; int px, py;
+        pp.preprocess(img.data(), 4, 2, pp.getDeviceOutput(), sx, sy, px, py);
+        std::vector<float> chw(3 * 8 * 8);
+        cudaMemcpy(chw.data(), pp.getDeviceOutput(), chw.size() * 4, cudaMemcpyDeviceToHost);
+        std::printf("letterbox scale %.3f pad %d %d corner %.4f centre_r %.4f\n", sx, px, py, chw[0], chw[(0 * 8 + 2) * 8 + 0]);
 
         // KalmanFilterCUDA: initiate, predict, read back
         KalmanFilterCUDA kf(4);

@@ -70,6 +70,14 @@ def test_reference_frame_loop_through_shims_equals_checker(pb, orc, cuda, tmp_pa
     assert rest["nms_apply"].strip() == (f"nms_apply {len(want_keep)} of {2 * n} :" + "".join(f" {i}" for i in want_keep)).strip()
     assert all(i % 2 == 0 for i in want_keep) and len(want_keep) >= n - 2      # every shifted copy loses to its original
     assert rest["auction"] == "auction 0 1 2"
+    # LinearAssignmentCUDA::solve on the same 3x3 table, threshold 0.25: greedy rows (9 cells < 100)
+    cost3 = np.array([[0.1, 0.9, 0.8], [0.7, 0.2, 0.9], [0.9, 0.8, 0.3]], np.float32)
+    wr, _, wn = orc.assign_legacy(cost3, 0.25)
+    assert rest["solve"] == f"solve {wn} : {wr[0]} {wr[1]} {wr[2]}", rest["solve"]
+    # PreprocessorCUDA on a 4x2 frame: scale 2, bars of 2 rows above and below
+    img = (10 * np.arange(24)).astype(np.uint8).reshape(2, 4, 3)
+    lb, xf = orc.letterbox(img, 8, 8)
+    assert rest["letterbox"] == f"letterbox scale {xf[0]:.3f} pad {int(xf[2])} {int(xf[3])} corner {lb[0, 0, 0]:.4f} centre_r {lb[0, 2, 0]:.4f}", rest["letterbox"]
     # KF3: initiate at (100, 200), one predict with zero velocity keeps the position; confidence 1.0;
     # variance 10 (conf > 0) + process noise 1; off-diagonal 0
     assert rest["kf3"] == "kf3 nose 100.000 200.000 conf 1.0 var_x 11.000 offdiag 0.000", rest["kf3"]

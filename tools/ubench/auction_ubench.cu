@@ -24,8 +24,7 @@ __global__ void k(const float* cost, int R, int C, int na, int variant, int* row
     for (int i = threadIdx.x; i < na * C; i += 32) cc[i] = cost_s[act_list[i / C] * C + i % C];
     __syncwarp();
     long long t0 = clock64();
-    if (variant == 0) auction_solve_rows32(cost_s, R, C, act_list, na, row, col, price, owner, colbid, colrow);
-    else if (variant == 1) auction_solve_hybrid32(cost_s, R, C, act_list, na, row, col, price, owner, colbid, colrow);
+    if (variant == 0) auction_solve_hybrid32(cost_s, R, C, act_list, na, row, col, price, owner, colbid, colrow);
     else if (C <= 32) auction_solve_lean32<1>(cc, R, C, act_list, na, row, col, price, owner, colbid, colrow);
     else auction_solve_lean32<2>(cc, R, C, act_list, na, row, col, price, owner, colbid, colrow);
     long long t1 = clock64();
@@ -52,7 +51,7 @@ int main() {
         const size_t smem = (size_t)(R * C + 32 * C + 6 * C + 2 * R + 2) * 4 + 160;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         std::vector<int> ref;
-        for (int variant = 0; variant < 3; ++variant) {
+        for (int variant = 0; variant < 2; ++variant) {   // 0 hybrid (generic C), 1 lean (C <= 64)
             long long h = 0;
             for (int rep = 0; rep < 3; ++rep) { k<<<1, 32, smem>>>(d, R, C, na, variant, dr, dc, dcy, dt); cudaDeviceSynchronize(); }
             cudaMemcpy(&h, dcy, 8, cudaMemcpyDeviceToHost);
@@ -62,7 +61,7 @@ int main() {
             printf("C %2d extra %d variant %d: %7lld cycles per solve (%5.0f per iteration of 50)  %s", C, extra, variant, h, h / 50.0, col == ref ? "same" : "DIFFERENT");
             if (variant == 3) printf("  iters nb1 %llu nb2 %llu nb>2 %llu loop %llu | eval %llu apply %llu redux-or %llu", t[15] / 1000, t[16] / 1000, t[17] / 1000, t[18], t[0], t[1], t[2]);
 #ifdef LEAN_PROFILE
-            if (variant == 2) { unsigned long long g[8]; cudaMemcpyFromSymbol(g, g_prof, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_prof, z, 64);
+            if (variant == 1) { unsigned long long g[8]; cudaMemcpyFromSymbol(g, g_prof, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_prof, z, 64);
                 if (g[3]) printf("  | per multi-bidder iteration: values %llu bids %llu logic %llu, whole loop trip %llu (%llu its)", g[0] / g[3], g[1] / g[3], g[2] / g[3], g[4] / g[3], g[3]); }
 #endif
             printf("\n");

@@ -73,6 +73,7 @@ ABI_SYMBOLS = [
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
     "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_set_output_transform", "pb_state_size", "pb_state_save", "pb_state_load", "pb_pose_distance", "pb_greedy_match",
+    "pb_assign_legacy", "pb_letterbox_batch",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
 ]
 
@@ -125,6 +126,8 @@ def lib() -> C.CDLL:
         L.pb_state_load.argtypes = [vp, vp, C.c_size_t]
         L.pb_pose_distance.argtypes = [vp, vp, ip, ip, ip, ip, fp, vp, vp]
         L.pb_greedy_match.argtypes = [vp, ip, ip, ip, fp, vp, vp]
+        L.pb_assign_legacy.argtypes = [vp, ip, ip, ip, fp, vp, vp, vp, vp]
+        L.pb_letterbox_batch.argtypes = [vp, C.c_size_t, vp, ip, ip, ip, vp, vp, vp]
         L.pb_kf3_initiate.argtypes = [vp, vp, vp, vp, ip, vp]
         L.pb_kf3_predict.argtypes = [vp, vp, ip, fp, fp, vp]
         L.pb_kf3_update.argtypes = [vp, vp, vp, vp, ip, vp]
@@ -353,6 +356,29 @@ def greedy_match(cost, threshold, stream=None):
     out = torch.empty(batch, R, device=cost.device, dtype=torch.int32)
     check(lib().pb_greedy_match(cost.data_ptr(), batch, R, Cc, threshold, out.data_ptr(), _stream_ptr(stream)))
     return out
+
+
+def assign_legacy(cost, threshold, stream=None):
+    """cost [batch, R, C] CUDA tensor -> (row [batch, R], col [batch, C], count [batch]) int32 (LinearAssignmentCUDA::solve)."""
+    import torch
+    batch, R, Cc = cost.shape
+    row = torch.empty(batch, R, device=cost.device, dtype=torch.int32)
+    col = torch.empty(batch, Cc, device=cost.device, dtype=torch.int32)
+    cnt = torch.zeros(batch, device=cost.device, dtype=torch.int32)
+    check(lib().pb_assign_legacy(cost.data_ptr(), batch, R, Cc, threshold, row.data_ptr(), col.data_ptr(), cnt.data_ptr(), _stream_ptr(stream)))
+    return row, col, cnt
+
+
+def letterbox_batch(frames, sizes, tw=640, th=640, stream=None):
+    """frames [batch, stride] uint8 CUDA tensor (BGR HWC images at the start of each row), sizes [batch, 2] int32
+    (width, height) -> (out [batch, 3, th, tw] fp32, xform [batch, 4])."""
+    import torch
+    batch = frames.shape[0]
+    out = torch.empty(batch, 3, th, tw, device=frames.device, dtype=torch.float32)
+    xf = torch.empty(batch, 4, device=frames.device, dtype=torch.float32)
+    check(lib().pb_letterbox_batch(frames.data_ptr(), frames.stride(0), sizes.data_ptr(), batch, tw, th, out.data_ptr(), xf.data_ptr(),
+                                   _stream_ptr(stream)))
+    return out, xf
 
 
 def launch_count() -> int:

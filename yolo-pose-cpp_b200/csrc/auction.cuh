@@ -23,14 +23,14 @@ namespace pb {
 __device__ __forceinline__ void auction_solve_cta(const float* cost, int R, int C, const int* active,
                                                   int* row, int* col, float* price,
                                                   unsigned long long* colbid, int* flags,
-                                                  int tid, int nthreads) {
+                                                  int tid, int nthreads, int max_iters = -1) {
     const unsigned FULL = 0xffffffffu;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     for (int t = tid; t < R; t += nthreads) row[t] = -1;
     for (int d = tid; d < C; d += nthreads) { col[d] = -1; price[d] = 0.0f; colbid[d] = 0ull; }
     if (tid == 0) { flags[0] = 0; flags[1] = 0; }
     float eps = 1.0f / (float)(R + 1);                                     // :378
-    const int iters = (R * 3 < 50) ? R * 3 : 50;                           // :379
+    const int iters = max_iters >= 0 ? max_iters : ((R * 3 < 50) ? R * 3 : 50);   // :379 (legacy solve: 3R, :283)
     __syncthreads();
     if (R == 0 || C == 0) return;                                          // :368
     for (int it = 0; it < iters; ++it) {
@@ -188,116 +188,14 @@ __device__ __forceinline__ void auction_solve_warp(const float* cost, int R, int
 
 
 // ---------------------------------------------------------------------------------------
-// Row-parallel single-warp solve for the tracker's common case: at most 32 ACTIVE rows, cost
-// matrix in shared memory.  Same results as auction_solve_cta (tests compare them).
-//
-// Lane i owns the i-th active row (act_list, ascending slots) and one "unassigned" flag;
-// prices and owners live in shared memory.  All bidders of an iteration scan their rows in
-// parallel (SIMT over rows; a rolled, 4-way software-pipelined loop).  A single bidder applies
-// its bid directly; several bidders are grouped by column with match.any, the group's highest
-// bid found with one redux and the lowest row among equal bids with one ballot
-// (hungarian.cu:100) — no shared-memory atomics (a 64-bit shared atomicMax compiles to a CAS
-// spin loop on sm_100a and serialises when many rows want one column).
-// The cost of an iteration is ~constant instead of proportional to the number of bidders,
-// which bounds the slowest stream of a batch — the tail that sets the kernel time.  The loop
-// body is kept small on purpose: it runs up to 150 times per stream-frame and has to stay
-// inside the instruction cache (an unrolled multi-path version of this loop ran 3x slower).
-// ---------------------------------------------------------------------------------------
-struct AucScratch {          // shared memory
-    float* price;            // [C]
-    int* owner;              // [C] row INDEX (position in act_list), -1 = free
-};
-
-static __device__ __noinline__ void auction_solve_rows32(const float* cost_s, int R, int C, const int* act_list, int na,
-                                                  int* row, int* col, float* price, int* owner,
-                                                  unsigned* colbid, int* colrow) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    for (int t = lane; t < R; t += 32) row[t] = -1;
-    for (int d = lane; d < C; d += 32) { col[d] = -1; price[d] = 0.0f; owner[d] = -1; colbid[d] = 0u; colrow[d] = 0x7fffffff; }
-    if (na <= 0 || C <= 0) return;
-    const bool mine = lane < na;
-    const float* cr = cost_s + (size_t)(mine ? act_list[lane] : 0) * C;
-    bool unas = mine;
-    __syncwarp();
-    float eps = 1.0f / (float)(R + 1);                                                     // :378
-    const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
-    const int C4 = C & ~3;
-#pragma unroll 1
-    for (int it = 0; it < iters; ++it) {
-        const unsigned ub = __ballot_sync(FULL, unas);
-        if (ub == 0u) break;                                                               // fixed point
-        int bc = -1;
-        unsigned bid = 0u;
-        if (unas) {
-            float bv = -1e9f, sv = -1e9f;
-#pragma unroll 1
-            for (int d = 0; d < C4; d += 4) {                                              // loads first, then the compare chain
-                const float v0 = -cr[d] - price[d], v1 = -cr[d + 1] - price[d + 1];        // :61
-                const float v2 = -cr[d + 2] - price[d + 2], v3 = -cr[d + 3] - price[d + 3];
-                if (v0 > bv) { sv = bv; bv = v0; bc = d; } else if (v0 > sv) sv = v0;      // ascending d: lowest column on ties (:63)
-                if (v1 > bv) { sv = bv; bv = v1; bc = d + 1; } else if (v1 > sv) sv = v1;
-                if (v2 > bv) { sv = bv; bv = v2; bc = d + 2; } else if (v2 > sv) sv = v2;
-                if (v3 > bv) { sv = bv; bv = v3; bc = d + 3; } else if (v3 > sv) sv = v3;
-            }
-#pragma unroll 1
-            for (int d = C4; d < C; ++d) {
-                const float v = -cr[d] - price[d];
-                if (v > bv) { sv = bv; bv = v; bc = d; } else if (v > sv) sv = v;
-            }
-            if (bc >= 0) bid = __float_as_uint(bv - sv + eps);                             // :99 (positive: bits order like the floats)
-        }
-        const unsigned pm = __ballot_sync(FULL, bc >= 0);
-        if (pm == 0u) break;                                                               // no bid: fixed point
-        bool win = bc >= 0;
-        const int nbid = __popc(pm);
-        if (nbid > 1 && nbid <= 8) {
-            // few bidders: every bidder compares itself with the others (highest bid, lowest row, :100)
-            unsigned rem = pm;
-            while (rem) {
-                const int j = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const int obc = __shfl_sync(FULL, bc, j);
-                const unsigned obid = __shfl_sync(FULL, bid, j);
-                if (obc == bc && (obid > bid || (obid == bid && j < lane))) win = false;
-            }
-        } else if (nbid > 8) {
-            if (bc >= 0) atomicMax(&colbid[bc], bid);
-            __syncwarp();
-            if (bc >= 0 && colbid[bc] == bid) atomicMin(&colrow[bc], lane);
-            __syncwarp();
-            win = bc >= 0 && colbid[bc] == bid && colrow[bc] == lane;
-            __syncwarp();
-            if (win) { colbid[bc] = 0u; colrow[bc] = 0x7fffffff; }
-        }
-        int prev = -1;
-        if (win) {                                                                         // :107-121
-            prev = owner[bc];
-            owner[bc] = lane;
-            price[bc] += __uint_as_float(bid);
-            unas = false;
-        }
-        const unsigned em = __reduce_or_sync(FULL, prev >= 0 ? (1u << prev) : 0u);         // evicted owners bid again
-        if ((em >> lane) & 1u) unas = true;
-        __syncwarp();
-        eps *= 0.9f;                                                                       // :402
-    }
-    __syncwarp();
-    for (int d = lane; d < C; d += 32) {
-        const int o = owner[d];
-        if (o >= 0) { const int slot = act_list[o]; col[d] = slot; row[slot] = d; }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------
-// Hybrid single-warp solve (the tracker's default for at most 32 active rows).
+// Hybrid single-warp solve: at most 32 active rows, any number of columns (the lean solve below takes the
+// tracker's own case of at most 64 columns).
 //
 // The bidder set is a warp-UNIFORM bitmask `ub` (bit i = i-th active row is unassigned), so no
 // ballot is needed to find it.  Per iteration one of two mappings is chosen by the number of
 // bidders:
 //   * many bidders (> HY_COLPAR_MAX, the first iterations of a solve): lane = row, every bidder
-//     scans its own cost row (the row-parallel scan of auction_solve_rows32);
+//     scans its own cost row;
 //   * few bidders (the long tail: an eviction chain of one to four rows that runs to the
 //     iteration limit whenever a stream has one active row more than it has detections):
 //     lane = column.  For each bidder the 32 lanes evaluate value = -cost - price of their columns
@@ -322,8 +220,7 @@ __device__ __forceinline__ float hy_unord(unsigned u) {
 
 static __device__ __noinline__ void auction_solve_hybrid32(const float* cost_s, int R, int C, const int* act_list, int na,
                                                            int* row, int* col, float* price, int* owner,
-                                                           unsigned* colbid, int* colrow,
-                                                           unsigned long long* tele = nullptr) {
+                                                           unsigned* colbid, int* colrow) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     for (int t = lane; t < R; t += 32) row[t] = -1;
@@ -340,7 +237,6 @@ static __device__ __noinline__ void auction_solve_hybrid32(const float* cost_s, 
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         if (ub == 0u) break;                                                               // fixed point
-        if (tele && lane == 0) { const int n = __popc(ub); tele[n == 1 ? 15 : (n == 2 ? 16 : (n <= 4 ? 17 : (n <= 8 ? 18 : 19)))] += 1000ull; }
         if (__popc(ub) <= HY_COLPAR_MAX) {
             // ---- lane = column ----
             unsigned long long bcs = 0ull;                                                 // bid columns, 16 bits each
@@ -562,7 +458,12 @@ __device__ __forceinline__ bool lean_iter(const float* cc, int C, unsigned& ub, 
 template <int NC>
 static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R, int C, const int* act_list, int na,
                                                          int* row, int* col, float* price, int* owner,
-                                                         unsigned* colbid, int* colrow) {
+                                                         unsigned* colbid, int* colrow, unsigned long long* tele = nullptr) {
+#ifdef PB_AUCTION_TELE
+#define LEAN_COUNT(slot) if (tele && lane == 0) tele[slot] += 1000ull;
+#else
+#define LEAN_COUNT(slot)
+#endif
     const unsigned FULL = 0xffffffffu;
     const unsigned ORD_FLOOR = lean_ord(-1e9f);
     const int lane = threadIdx.x & 31;
@@ -602,6 +503,7 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
             for (; it < iters; ++it) {
                 float bv, sv;
                 int bsel;
+                LEAN_COUNT(15)
                 lean_values<NC>(cc, C, j, p, lane, bv, sv, bsel);
                 const LeanBid q = lean_bid<NC>(bv, sv, bsel, own, lane, eps);
                 if (q.m == ORD_FLOOR) break;                                               // cannot bid: fixed point
@@ -615,15 +517,19 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
             }
             break;
         } else if (r2 == 0u) {
+            LEAN_COUNT(16)
             const unsigned b2[2] = {bit[0], bit[1]};
             any = lean_iter<2, NC>(cc, C, ub, b2, eps, p, own, lane);
         } else if (r3 == 0u) {
+            LEAN_COUNT(17)
             const unsigned b3[3] = {bit[0], bit[1], bit[2]};
             any = lean_iter<3, NC>(cc, C, ub, b3, eps, p, own, lane);
         } else if (r4 == 0u) {
+            LEAN_COUNT(17)
             any = lean_iter<4, NC>(cc, C, ub, bit, eps, p, own, lane);
         } else if (__popc(ub) <= 8) {
             // ---- one bidder after the other: per-lane highest bid, toggle bits through one REDUX.OR ----
+            LEAN_COUNT(18)
             unsigned best[NC];
             int w[NC];
 #pragma unroll
@@ -656,6 +562,7 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
             ub = (ub & ~drop) ^ tog;                                                       // winners leave, evicted owners enter
         } else {
             // ---- lane = row ----
+            LEAN_COUNT(19)
 #pragma unroll
             for (int c = 0; c < NC; ++c)
                 if (lane + 32 * c < C) { price[lane + 32 * c] = p[c]; owner[lane + 32 * c] = own[c]; }

@@ -10,7 +10,14 @@
 //                      (kernelGreedyMatch :126-157) races on the columns, its outcome depends on thread
 //                      timing; the class's own host path (:441-467) is deterministic — all cells below the
 //                      threshold sorted by (cost, row, col), taken greedily — and is the rule used here.
+//   pb_assign_legacy   reference src/cuda/hungarian.cu:235-339, LinearAssignmentCUDA::solve: greedy rows below
+//                      100 cells (:198-233), else the auction over all rows with 3*rows iterations (:283) and
+//                      the threshold filter of :328-336 — upstream one host round trip per iteration.
+//   pb_letterbox_batch reference src/cuda/preprocess.cu:19-153: letterbox + BGR->RGB +
+//                      /255 + HWC->CHW for a batch of frames of individual sizes, one launch; the letterbox
+//                      parameters come out in the layout pb_set_output_transform takes.
 #include "pb_common.cuh"
+#include "auction.cuh"
 
 namespace pb {
 
@@ -172,6 +179,136 @@ greedy_match_kernel(const float* __restrict__ cost, int R, int C, float threshol
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// LinearAssignmentCUDA::solve.  One CTA per problem.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+assign_legacy_kernel(const float* cost, int R, int C, float threshold, int* row_out, int* col_out, int* count_out) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned long long* colbid = reinterpret_cast<unsigned long long*>(sm);
+    float* price = reinterpret_cast<float*>(colbid + C);
+    int* col = reinterpret_cast<int*>(price + C);
+    int* row = col + C;
+    int* flags = row + R;          // [4]
+    const int b = blockIdx.x;
+    const float* cb = cost + (size_t)b * R * C;
+    if (R * C < 100) {                                                 // greedyAssign, :198-233 (sequential by definition)
+        if (threadIdx.x == 0) {
+            unsigned long long used_lo = 0ull, used_hi = 0ull;         // C < 100
+            int n = 0;
+            for (int c = 0; c < C; ++c) col[c] = -1;
+            for (int r = 0; r < R; ++r) {
+                float best = threshold;
+                int bc = -1;
+                for (int c = 0; c < C; ++c) {
+                    const bool used = c < 64 ? ((used_lo >> c) & 1ull) : ((used_hi >> (c - 64)) & 1ull);
+                    if (!used) { const float v = cb[r * C + c]; if (v < best) { best = v; bc = c; } }
+                }
+                row[r] = bc;
+                if (bc >= 0) { col[bc] = r; if (bc < 64) used_lo |= 1ull << bc; else used_hi |= 1ull << (bc - 64); ++n; }
+            }
+            flags[2] = n;
+        }
+        __syncthreads();
+    } else {
+        auction_solve_cta(cb, R, C, nullptr, row, col, price, colbid, flags, threadIdx.x, blockDim.x, R * 3);
+        if (threadIdx.x == 0) flags[2] = 0;
+        __syncthreads();
+        int n = 0;
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {            // :328-336
+            const int c = row[r];
+            if (c >= 0) {
+                if (cb[(size_t)r * C + c] <= threshold) ++n;
+                else { col[c] = -1; row[r] = -1; }
+            }
+        }
+        if (n) atomicAdd(&flags[2], n);
+        __syncthreads();
+    }
+    for (int r = threadIdx.x; r < R; r += blockDim.x) row_out[(size_t)b * R + r] = row[r];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) col_out[(size_t)b * C + c] = col[c];
+    if (threadIdx.x == 0 && count_out) count_out[b] = flags[2];
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched letterbox pre-processing.  HBM-bound: 3 B read per source pixel touched, 12 B written per
+// target pixel.  One thread produces four consecutive target pixels of one row (three 128-bit
+// stores, one per colour plane); source taps go through the read-only path (neighbouring threads
+// share their sectors).  Arithmetic as kernelPreprocess (:36-80) expression by expression.
+// ---------------------------------------------------------------------------------------
+struct LetterboxGeom { float scale; int new_w, new_h, pad_x, pad_y; };
+
+__device__ __forceinline__ LetterboxGeom letterbox_geom(int w, int h, int tw, int th) {
+    LetterboxGeom g;
+    g.scale = pb_min(static_cast<float>(tw) / w, static_cast<float>(th) / h);              // :109-112
+    g.new_w = static_cast<int>(w * g.scale);                                                // :114-115
+    g.new_h = static_cast<int>(h * g.scale);
+    g.pad_x = (tw - g.new_w) / 2;                                                           // :117-118
+    g.pad_y = (th - g.new_h) / 2;
+    return g;
+}
+
+__device__ __forceinline__ void letterbox_pixel(const unsigned char* __restrict__ img, int w, int h, const LetterboxGeom& g,
+                                                int tx, int ty, float& r, float& gch, float& b) {
+    if (tx < g.pad_x || tx >= g.pad_x + g.new_w || ty < g.pad_y || ty >= g.pad_y + g.new_h) {   // :39-47
+        r = gch = b = 114.0f / 255.0f;
+        return;
+    }
+    float sx = (tx - g.pad_x) / g.scale, sy = (ty - g.pad_y) / g.scale;                    // :50-51
+    sx = fminf(fmaxf(sx, 0.0f), w - 1.001f);                                                // :54-55
+    sy = fminf(fmaxf(sy, 0.0f), h - 1.001f);
+    const int x0 = (int)sx, y0 = (int)sy;
+    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+    const float wx = sx - x0, wy = sy - y0;
+    const unsigned char* p00 = img + ((size_t)y0 * w + x0) * 3;
+    const unsigned char* p01 = img + ((size_t)y0 * w + x1) * 3;
+    const unsigned char* p10 = img + ((size_t)y1 * w + x0) * 3;
+    const unsigned char* p11 = img + ((size_t)y1 * w + x1) * 3;
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                                                           // :66-80
+        const float v00 = __ldg(p00 + c), v01 = __ldg(p01 + c), v10 = __ldg(p10 + c), v11 = __ldg(p11 + c);
+        const float v = (1 - wx) * (1 - wy) * v00 + wx * (1 - wy) * v01 + (1 - wx) * wy * v10 + wx * wy * v11;
+        o[c] = v / 255.0f;
+    }
+    r = o[2]; gch = o[1]; b = o[0];                                                         // BGR -> RGB
+}
+
+__global__ void __launch_bounds__(256)
+letterbox_batch_kernel(const unsigned char* __restrict__ frames, size_t frame_stride, const int* __restrict__ wh,
+                       int tw, int th, float* __restrict__ out, float* __restrict__ xform) {
+    const int f = blockIdx.y;
+    const int w = wh[2 * f], h = wh[2 * f + 1];
+    const LetterboxGeom g = letterbox_geom(w, h, tw, th);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && xform) {                                     // :121-122
+        xform[4 * f] = 1.0f / g.scale; xform[4 * f + 1] = 1.0f / g.scale;
+        xform[4 * f + 2] = (float)g.pad_x; xform[4 * f + 3] = (float)g.pad_y;
+    }
+    const unsigned char* img = frames + (size_t)f * frame_stride;
+    const size_t plane = (size_t)tw * th;
+    float* o = out + (size_t)f * 3 * plane;
+    const int quads_per_row = (tw + 3) >> 2;
+    const int nquads = quads_per_row * th;
+    const bool vec = (tw & 3) == 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += gridDim.x * blockDim.x) {
+        const int ty = q / quads_per_row, tx0 = (q - ty * quads_per_row) << 2;
+        float r[4], gg[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = gg[i] = bb[i] = 0.0f;
+            if (tx0 + i < tw) letterbox_pixel(img, w, h, g, tx0 + i, ty, r[i], gg[i], bb[i]);
+        }
+        const size_t off = (size_t)ty * tw + tx0;
+        if (vec) {
+            __stcs(reinterpret_cast<float4*>(o + off), make_float4(r[0], r[1], r[2], r[3]));
+            __stcs(reinterpret_cast<float4*>(o + plane + off), make_float4(gg[0], gg[1], gg[2], gg[3]));
+            __stcs(reinterpret_cast<float4*>(o + 2 * plane + off), make_float4(bb[0], bb[1], bb[2], bb[3]));
+        } else {
+            for (int i = 0; i < 4 && tx0 + i < tw; ++i) { o[off + i] = r[i]; o[plane + off + i] = gg[i]; o[2 * plane + off + i] = bb[i]; }
+        }
+    }
+}
+
 void count_launch(int n);
 
 }  // namespace pb
@@ -210,6 +347,44 @@ int pb_greedy_match(const float* d_cost, int batch, int num_rows, int num_cols, 
     pb::count_launch(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { pb_set_error("pb_greedy_match: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    return PB_OK;
+}
+
+int pb_assign_legacy(const float* d_cost, int batch, int num_rows, int num_cols, float threshold, int* d_row_assign,
+                     int* d_col_assign, int* d_count, pb_stream_t stream) {
+    if (batch <= 0 || num_rows <= 0 || num_cols <= 0) return PB_OK;                  // hungarian.cu:243
+    if (!d_cost || !d_row_assign || !d_col_assign) { pb_set_error("pb_assign_legacy: bad argument"); return PB_ERR_INVALID; }
+    const size_t smem = (size_t)num_cols * 16 + (size_t)num_rows * 4 + 16;
+    if (smem > 200 * 1024) { pb_set_error("pb_assign_legacy: problem too large"); return PB_ERR_UNSUPPORTED; }
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(pb::assign_legacy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { pb_set_error("pb_assign_legacy: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+        configured = smem;
+    }
+    pb::assign_legacy_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(d_cost, num_rows, num_cols, threshold, d_row_assign, d_col_assign, d_count);
+    pb::count_launch(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { pb_set_error("pb_assign_legacy: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
+    return PB_OK;
+}
+
+int pb_letterbox_batch(const unsigned char* d_frames, size_t frame_stride_bytes, const int* d_sizes, int batch, int target_width,
+                       int target_height, float* d_out, float* d_xform, pb_stream_t stream) {
+    if (batch <= 0) return PB_OK;
+    if (!d_frames || !d_sizes || !d_out || target_width <= 0 || target_height <= 0) { pb_set_error("pb_letterbox_batch: bad argument"); return PB_ERR_INVALID; }
+    if (batch > 65535) { pb_set_error("pb_letterbox_batch: batch > 65535"); return PB_ERR_UNSUPPORTED; }
+    const long long quads = (long long)((target_width + 3) / 4) * target_height;
+    if (quads > 0x7fffffffLL) { pb_set_error("pb_letterbox_batch: target too large"); return PB_ERR_UNSUPPORTED; }
+    int bx = (int)((quads + 255) / 256);
+    // enough CTAs per frame to cover the 148 SMs several times over when the batch is small
+    const int cap = batch >= 32 ? 64 : (2 * 148 * 8 + batch - 1) / batch;
+    if (bx > cap) bx = cap;
+    pb::letterbox_batch_kernel<<<dim3(bx, batch), 256, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, d_sizes, target_width,
+                                                                                 target_height, d_out, d_xform);
+    pb::count_launch(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { pb_set_error("pb_letterbox_batch: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     return PB_OK;
 }
 

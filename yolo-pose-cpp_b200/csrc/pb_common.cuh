@@ -72,7 +72,6 @@ struct TrackParams {
     int frame_id;
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
     int cost_in_smem, det_in_smem, pred_in_smem, term_floats;
-    int auction_variant;   // 0 row-parallel, 1 hybrid (see auction.cuh)
 };
 
 struct DetSource {

@@ -14,9 +14,9 @@
 //   (:141-189, :612-648) -> ageing (:651-688) -> new tracks (:695-780, rules R3/R4) ->
 //   IoU de-duplication (:788-895, rule R5) -> TrackOutput assembly (:1594-1636).
 // The auction (hungarian.cu:27-123, 358-405) keeps the reference's bid arithmetic and
-// tie-breaks (R6): a warp scans one bidder row (shuffle top-2 reduction), bids meet in a
-// packed 64-bit shared atomicMax (bid bits | ~row), and the loop stops at the first
-// iteration without bidders — a fixed point of the reference's 50 fixed iterations.
+// tie-breaks (R6); one warp runs the whole solve with lane = column, prices and owners in
+// registers (auction.cuh), and the loop stops at the first iteration without a bid — a
+// fixed point of the reference's 50 fixed iterations.
 #include <cstdlib>
 #include "pb_common.cuh"
 #include "auction.cuh"
@@ -196,7 +196,7 @@ __device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
 
 struct Ctx {
     TkSmem s;
-    int T, D, Dw, tid, nthreads, lane, warp, nwarps, variant;
+    int T, D, Dw, tid, nthreads, lane, warp, nwarps;
     bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
     int term_floats;
     float* cost;        // shared or global, flat [t*D + d]
@@ -207,7 +207,7 @@ struct Ctx {
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
 __device__ __forceinline__ void auction_solve(Ctx& c, int na) {
     TkSmem& s = c.s;
-    if (c.warp_auction && na <= 32 && c.D <= 64 && c.variant == 2) {
+    if (c.warp_auction && na <= 32 && c.D <= 64) {
         // compact the active rows (cc[i*D + d], i = position in act_list) into the term buffer, which is idle
         // between cost passes: the single-warp solve then reads a bidder's row with one conflict-free load
         float* cc = s.terms;
@@ -217,19 +217,14 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na) {
         if (c.tid < 32) {
             unsigned* cb = reinterpret_cast<unsigned*>(s.colbid);
             int* cr = reinterpret_cast<int*>(s.colbid) + c.D;
-            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr);
-            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr);
+            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, s.acc);
+            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, s.acc);
         }
         __syncthreads();
     } else if (c.warp_auction && na <= 32) {
-        if (c.tid < 32) {
-            if (c.variant == 0)
-                auction_solve_rows32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
-                                     reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D);
-            else
-                auction_solve_hybrid32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
-                                       reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D, s.acc);
-        }
+        if (c.tid < 32)
+            auction_solve_hybrid32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
+                                   reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D);
         __syncthreads();
     } else if (c.warp_auction) {
         // colbid (8 B per column) doubles as the 32-bit bid array + the lowest-row array
@@ -390,7 +385,6 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     Ctx c;
     tk_carve(smem_raw, P.T, P.Dm, P.cost_in_smem, P.det_in_smem, P.pred_in_smem, P.term_floats, &c.s);
     c.term_floats = P.term_floats;
-    c.variant = P.auction_variant;
     TkSmem& s = c.s;
     const int b = blockIdx.x;
     const int T = P.T, Dm = P.Dm;
@@ -839,8 +833,6 @@ cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSourc
     }
     p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
     p.term_floats = plan.term_floats;
-    static const int variant = [] { const char* e = getenv("PB_AUCTION"); return e ? atoi(e) : 2; }();
-    p.auction_variant = variant;
     if (v == 0) pb_tracker_kernel<256><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
     else if (v == 1) pb_tracker_kernel<512><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
     else pb_tracker_kernel<1024><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
