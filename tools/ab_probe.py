@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import posebyte_b200 as pb
-B, F = 64, 16
+B, F = int(os.environ.get("PB_B", "64")), 16
 scfg = pb.synth_config(canvas=640, persons=20, period=32)
 d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()
 pp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=3)

@@ -16,7 +16,7 @@ for f in range(32, 96):
     cur = pipe.stream_stage_ns().astype(np.int64)
     rows.append(cur - prev); prev = cur
 a = np.stack(rows) / 1e3            # [frames, B, 20] us
-names = {0: "prologue", 1: "predict", 2: "gate", 12: "t1cost", 13: "t1auction", 14: "t1lock", 3: "tier1", 4: "tier2", 5: "tier3", 6: "update", 7: "age", 8: "newtracks", 9: "dedup", 10: "total"}
+names = {15: "flagwait", 16: "detprolog", 0: "prologue", 1: "predict", 2: "gate", 12: "t1cost", 13: "t1auction", 14: "t1lock", 3: "tier1", 4: "tier2", 5: "tier3", 6: "update", 7: "age", 8: "newtracks", 9: "dedup", 10: "total"}
 for i, n in names.items():
     x = a[:, :, i]
     print(f"{n:10s} mean {x.mean():6.2f}  p50 {np.percentile(x, 50):6.2f}  p90 {np.percentile(x, 90):6.2f}  p99 {np.percentile(x, 99):6.2f}  max {x.max():6.2f} | mean over frames of max over streams {x.max(1).mean():6.2f}")

@@ -46,7 +46,10 @@ struct pb_handle_st {
     std::vector<PipeSlot> ring;    // cfg.pipeline_depth slots
     int cur = 0;
     bool inflight = false;         // work of a pipelined pb_step may still run on the internal streams
-    cudaStream_t s_nms = nullptr, s_trk = nullptr;
+    cudaStream_t s_nms = nullptr, s_nms2 = nullptr, s_trk = nullptr, s_trk2 = nullptr;   // tracker launches alternate between s_trk and s_trk2
+    int trk_seq = 0;               // sequence number of the last tracker launch (TrackParams::seq)
+    cudaStream_t last_trk_stream = nullptr;
+    bool last_was_readback = false;
     DecodePlan dplan{};
     TrackBuffers trk{};
     TrackerPlan plan{};
@@ -165,7 +168,9 @@ static int build_handle(pb_handle_st* h) {
     h->cur = 0; h->post = h->ring[0].post; h->cand = h->ring[0].cand;
     if (c.pipeline_depth > 1) {
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_nms, cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_nms2, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk, cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk2, cudaStreamNonBlocking));
     }
     TrackBuffers& t = h->trk;
     PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
@@ -189,12 +194,14 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &t.num_outputs, B));
     PB_TRY(dev_alloc(h, &t.det_poses_scratch, B * Dm * POSE_F));
     PB_TRY(dev_alloc(h, &t.stage_ns, B * 20));
+    PB_TRY(dev_alloc(h, &t.seq_done, B));
+    PB_TRY(dev_alloc(h, &t.error_flag, 1));
     unsigned char* outp = nullptr;
     PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
     t.outputs = outp;
     h->plan = tracker_plan(c.max_tracks, c.max_detections);
     PB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    PB_CUDA(launch_tracker_reset(h->trk, c.num_streams, c.max_tracks, c.max_detections, h->own_stream));
+    PB_CUDA(launch_tracker_reset(h->trk, c.num_streams, c.max_tracks, c.max_detections, h->trk_seq, h->own_stream));
     PB_CUDA(cudaStreamSynchronize(h->own_stream));
     return PB_OK;
 }
@@ -248,7 +255,9 @@ int pb_destroy(pb_handle_t h) {
     if (h->h_cnt_pinned) cudaFreeHost(h->h_cnt_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->s_nms) cudaStreamDestroy(h->s_nms);
+    if (h->s_nms2) cudaStreamDestroy(h->s_nms2);
     if (h->s_trk) cudaStreamDestroy(h->s_trk);
+    if (h->s_trk2) cudaStreamDestroy(h->s_trk2);
     for (PipeSlot& sl : h->ring) {
         if (sl.ev_gather) cudaEventDestroy(sl.ev_gather);
         if (sl.ev_nms) cudaEventDestroy(sl.ev_nms);
@@ -271,7 +280,7 @@ static int join_on(pb_handle_st* h, cudaStream_t stream) {
 int pb_reset(pb_handle_t h, pb_stream_t stream) {
     if (!h) { pb_set_error("pb_reset: null handle"); return PB_ERR_INVALID; }
     PB_TRY(join_on(h, (cudaStream_t)stream));
-    PB_CUDA(launch_tracker_reset(h->trk, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, (cudaStream_t)stream));
+    PB_CUDA(launch_tracker_reset(h->trk, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, h->trk_seq, (cudaStream_t)stream));
     h->frames = 0;
     return PB_OK;
 }
@@ -300,8 +309,10 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
     return PB_OK;
 }
 
-static TrackParams track_params(const pb_config& c, int frame_id) {
+static TrackParams track_params(pb_handle_st* h, int frame_id) {
+    const pb_config& c = h->cfg;
     TrackParams p{};
+    p.seq = ++h->trk_seq;
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
@@ -323,7 +334,7 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
         }
         src = {d_det_poses, d_det_scores, d_num_dets, det_stride};
     }
-    TrackParams p = track_params(c, frame_id);
+    TrackParams p = track_params(h, frame_id);
     int e0 = -1, e1 = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_tracker(h->trk, p, src, h->plan, (cudaStream_t)stream));
@@ -357,18 +368,31 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));          // scratch still being read
     PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, sl.cand, stream));
     PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
-    PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_gather, 0));
-    if (sl.used) PB_CUDA(cudaStreamWaitEvent(h->s_nms, sl.ev_trk, 0));        // kept detections still being read
-    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, h->s_nms));
-    PB_CUDA(cudaEventRecord(sl.ev_nms, h->s_nms));
-    // the NMS kernel fetches keypoints from the borrowed head tensor: later work on the caller's
-    // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it
-    PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));
-    PB_CUDA(cudaStreamWaitEvent(h->s_trk, sl.ev_nms, 0));
+    // consecutive NMS launches are independent of each other: two streams, so that they may overlap
+    cudaStream_t ns = (getenv("PB_ONE_NMS_STREAM") || (h->frames & 1)) ? h->s_nms : h->s_nms2;
+    PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
+    if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
+    PB_CUDA(cudaEventRecord(sl.ev_nms, ns));
+    // the lazy NMS sweep fetches keypoints from the borrowed head tensor: later work on the caller's
+    // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it then.
+    // With complete records the decode+gather kernel is the only reader of the head and nothing is needed.
+    if (h->lazy_keypoints) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));
+    // Tracker launches alternate between two streams: launch i may start while launch i-1 is still
+    // running, the per-stream sequence flags inside the kernel keep every video stream's frames in
+    // order (tracker.cu).  With a read-back of the records behind every launch (pb_submit_host) the
+    // output buffer of step i must not be overwritten before it is copied: one stream then.
+    const TrackParams tp = track_params(h, frame_id);
+    cudaStream_t ts = (h->rb_tracks || (tp.seq & 1)) ? h->s_trk : h->s_trk2;
+    if ((h->rb_tracks || h->last_was_readback) && h->last_trk_stream && h->last_trk_stream != ts)
+        PB_CUDA(cudaStreamWaitEvent(ts, h->ring[h->cur].ev_trk, 0));   // the previous step's records are still being copied out
+    PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_nms, 0));
     DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
-    PB_CUDA(launch_tracker(h->trk, track_params(c, frame_id), src, h->plan, h->s_trk));
-    PB_TRY(enqueue_readback(h, h->s_trk));
-    PB_CUDA(cudaEventRecord(sl.ev_trk, h->s_trk));
+    PB_CUDA(launch_tracker(h->trk, tp, src, h->plan, ts));
+    PB_TRY(enqueue_readback(h, ts));
+    PB_CUDA(cudaEventRecord(sl.ev_trk, ts));
+    h->last_trk_stream = ts;
+    h->last_was_readback = h->rb_tracks != nullptr;
     sl.used = true;
     h->cur = pos; h->post = sl.post; h->cand = sl.cand;
     h->inflight = true;
@@ -509,16 +533,25 @@ int pb_submit_host(pb_handle_t h, const float* h_heads, float conf, float nms, i
     return rc;
 }
 
+// After a synchronisation: did a tracker CTA give up waiting for its predecessor (tracker.cu)?
+static int check_order_flag(pb_handle_st* h) {
+    int f = 0;
+    PB_CUDA(cudaMemcpy(&f, h->trk.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f) { pb_set_error("tracker: a stream's previous frame did not complete within the time-out; results are invalid"); return PB_ERR_CUDA; }
+    return PB_OK;
+}
+
 int pb_wait(pb_handle_t h) {
     if (!h) { pb_set_error("pb_wait: null handle"); return PB_ERR_INVALID; }
     PB_TRY(join_on(h, h->own_stream));
     PB_CUDA(cudaStreamSynchronize(h->own_stream));
-    return PB_OK;
+    return check_order_flag(h);
 }
 
 int pb_get_tracks(pb_handle_t h, int b, void* out, int cap, int* n_out) {
     if (!h || b < 0 || b >= h->cfg.num_streams || !n_out) { pb_set_error("pb_get_tracks: bad argument"); return PB_ERR_INVALID; }
     PB_CUDA(cudaDeviceSynchronize());
+    PB_TRY(check_order_flag(h));
     int n = 0;
     PB_CUDA(cudaMemcpy(&n, h->trk.num_outputs + b, sizeof(int), cudaMemcpyDeviceToHost));
     if (n > cap) n = cap;
@@ -532,6 +565,7 @@ int pb_get_tracks(pb_handle_t h, int b, void* out, int cap, int* n_out) {
 int pb_get_tracks_all(pb_handle_t h, void* out, int* counts) {
     if (!h || !out || !counts) { pb_set_error("pb_get_tracks_all: bad argument"); return PB_ERR_INVALID; }
     PB_CUDA(cudaDeviceSynchronize());
+    PB_TRY(check_order_flag(h));
     const size_t B = h->cfg.num_streams;
     PB_CUDA(cudaMemcpy(counts, h->trk.num_outputs, B * sizeof(int), cudaMemcpyDeviceToHost));
     PB_CUDA(cudaMemcpy(out, h->trk.outputs, B * h->cfg.max_detections * 228, cudaMemcpyDeviceToHost));

@@ -63,6 +63,8 @@ struct TrackBuffers {
     int* num_outputs;    // [B]
     float* det_poses_scratch;  // [B, Dm, 51]  used when the detections do not fit in shared memory
     unsigned long long* stage_ns;  // [B, 12] globaltimer stamps per stage (telemetry)
+    int* seq_done;       // [B] sequence number of the last tracker launch this stream has completed (see pb_tracker_kernel)
+    int* error_flag;     // [1] set when a stream's predecessor did not finish within the time-out
 };
 
 struct TrackParams {
@@ -70,6 +72,7 @@ struct TrackParams {
     float new_track_thresh;
     int max_age, min_hits, gating_enabled;
     int frame_id;
+    int seq;             // sequence number of this launch; the CTA of stream b starts once seq_done[b] == seq - 1
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
     int cost_in_smem, det_in_smem, pred_in_smem, term_floats;
 };
@@ -114,7 +117,7 @@ struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_sm
 TrackerPlan tracker_plan(int T, int Dm);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);
-cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, cudaStream_t stream);
+cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, int seq, cudaStream_t stream);
 
 void count_launch(int n = 1);
 

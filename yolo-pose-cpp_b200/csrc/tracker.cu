@@ -425,7 +425,35 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     const float* src_score = src.scores + (size_t)b * src.stride;
     float* det_w = P.det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
     for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
-    for (int d = tid; d < D; d += NT) { const float sc = src_score[d]; s.dscore[d] = sc; g_dscore[d] = sc; s.col[d] = -1; }
+    for (int d = tid; d < D; d += NT) { s.dscore[d] = src_score[d]; s.col[d] = -1; }
+    if (tid < 32) s.misc[tid] = 0;
+    if (tid < 20) s.acc[tid] = 0ull;
+    if (tid < KP) s.sig[tid] = kSigmas[tid];
+    // ---- per-stream ordering across launches ----
+    // Consecutive tracker launches run on two alternating CUDA streams and may overlap: the CTA of
+    // stream b only needs the state ITS predecessor (the previous frame of the same video stream) left
+    // behind, not the whole previous grid, so a video stream whose auction ran to the iteration limit
+    // delays nobody but itself.  Everything above reads this frame's detections only; from here on
+    // the CTA touches the stream's persistent state and waits for seq_done[b] == seq - 1 (release by the
+    // predecessor's last instruction, acquire here).  Launches are issued in sequence order and a launch
+    // is submitted only after the one before its predecessor has completed, so at most one grid can be
+    // waiting and the grid it waits for never waits itself; the time-out only guards against misuse.
+    if (tid == 0) {
+        const int want = P.seq - 1;
+        const int* flag = tb.seq_done + b;
+        const unsigned long long w0 = globaltimer_ns();
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v - want >= 0) break;
+            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); break; }
+            __nanosleep(64);
+        }
+        s.acc[15] += globaltimer_ns() - w0;          // telemetry: time spent waiting for the predecessor
+        s.acc[16] += w0 - t_begin;                   // telemetry: detection-only prologue
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
     int na_local = 0;
     for (int t = tid; t < T; t += NT) {
         const int a = g_active[t];
@@ -439,9 +467,6 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     c.warp_auction = P.cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
     c.pred = P.pred_in_smem ? s.pred : g_pred;
     if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
-    if (tid < 32) s.misc[tid] = 0;
-    if (tid < 20) s.acc[tid] = 0ull;
-    if (tid < KP) s.sig[tid] = kSigmas[tid];
     __syncthreads();
     {   // active count + ordered active list (ascending t)
         for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
@@ -785,9 +810,15 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     }
     __syncthreads();
     if (tid < 20 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
+    // release the stream's state to its successor (see the wait in the prologue)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
+    }
 }
 
-__global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm) {
+__global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm, int seq) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nT = (size_t)B * T, nD = (size_t)B * Dm;
     if (i < nT * POSE_F) { tb.poses[i] = 0.f; tb.predicted[i] = 0.f; }
@@ -803,17 +834,19 @@ __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm) {
     if (i < (size_t)B) {
         tb.scalars[i * 4 + 0] = 1; tb.scalars[i * 4 + 1] = 0; tb.scalars[i * 4 + 2] = 0; tb.scalars[i * 4 + 3] = 0;
         tb.num_outputs[i] = 0;
+        tb.seq_done[i] = seq;
     }
+    if (i == 0) *tb.error_flag = 0;
     if (i < (size_t)B * 20) tb.stage_ns[i] = 0ull;
 }
 
-cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, cudaStream_t stream) {
+cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, int seq, cudaStream_t stream) {
     size_t n = (size_t)B * T * (size_t)(Dm > POSE_F ? Dm : POSE_F);
     if (n < (size_t)B * Dm * 4) n = (size_t)B * Dm * 4;
     if (n < (size_t)B * 20) n = (size_t)B * 20;
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    pb_tracker_reset_kernel<<<blocks, threads, 0, stream>>>(tb, B, T, Dm);
+    pb_tracker_reset_kernel<<<blocks, threads, 0, stream>>>(tb, B, T, Dm, seq);
     count_launch();
     return cudaGetLastError();
 }
