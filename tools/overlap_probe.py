@@ -8,7 +8,7 @@ import posebyte_b200 as pb
 B, F = int(os.environ.get("PB_B", "64")), 16
 scfg = pb.synth_config(canvas=640, persons=20, period=32)
 d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()
-pp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=3)
+pp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=int(os.environ.get("PB_DEPTH", "3")))
 for i in range(40): pp.step(d[i % F], i)
 pp.join(); torch.cuda.synchronize()
 a0 = pp.stream_stage_ns().astype(np.int64)

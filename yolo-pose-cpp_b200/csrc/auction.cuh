@@ -455,10 +455,33 @@ __device__ __forceinline__ bool lean_iter(const float* cc, int C, unsigned& ub, 
     return anym != 0u;
 }
 
+// Runs iterations while exactly NB rows bid (an eviction chase usually keeps its number of bidders for many
+// iterations): the next bidders are peeled off the new mask with 2*NB operations, no dispatch in between.
+// Returns false at a fixed point (nobody bid); otherwise `it`/`eps` are advanced past the iterations done.
+template <int NB, int NC>
+__device__ __forceinline__ bool lean_regime(const float* cc, int C, unsigned& ub, float& eps, int& it, int iters,
+                                            float (&p)[NC], int (&own)[NC], int lane) {
+    unsigned bit[NB];
+    unsigned rest = ub;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { bit[b] = rest & (0u - rest); rest ^= bit[b]; }
+#pragma unroll 1
+    for (;;) {
+        if (!lean_iter<NB, NC>(cc, C, ub, bit, eps, p, own, lane)) return false;
+        eps *= 0.9f;                                                                       // :402
+        ++it;
+        rest = ub;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { bit[b] = rest & (0u - rest); rest ^= bit[b]; }
+        if (it >= iters || rest != 0u || bit[NB - 1] == 0u) return true;                   // limit reached or another bidder count
+    }
+}
+
 template <int NC>
 static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R, int C, const int* act_list, int na,
                                                          int* row, int* col, float* price, int* owner,
-                                                         unsigned* colbid, int* colrow, unsigned long long* tele = nullptr) {
+                                                         unsigned* colbid, int* colrow, unsigned ub0 = 0xffffffffu,
+                                                         unsigned long long* tele = nullptr) {
 #ifdef PB_AUCTION_TELE
 #define LEAN_COUNT(slot) if (tele && lane == 0) tele[slot] += 1000ull;
 #else
@@ -474,7 +497,9 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
     int own[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) { p[c] = 0.0f; own[c] = -1; }
-    unsigned ub = (na >= 32) ? FULL : ((1u << na) - 1u);                                   // unassigned rows that may still bid
+    // unassigned rows that may still bid; ub0 lets the caller leave out rows it knows to hold no cell below 1e9
+    // (they would scan their row, find nothing and never bid: hungarian.cu:55-69)
+    unsigned ub = ((na >= 32) ? FULL : ((1u << na) - 1u)) & ub0;
     __syncwarp();
     float eps = 1.0f / (float)(R + 1);                                                     // :378
     const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
@@ -485,16 +510,8 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
 #ifdef LEAN_PROFILE
         { static __device__ long long last; const long long now = clock64(); if (lane == 0) { if (it > 1) g_prof[4] += now - last; last = now; } }
 #endif
-        // peel the lowest bidders off the mask (no bidder count, no jump table on the way to the common cases)
-        unsigned bit[4];
-        bit[0] = ub & (0u - ub);
-        const unsigned r1 = ub ^ bit[0];
-        bit[1] = r1 & (0u - r1);
-        const unsigned r2 = r1 ^ bit[1];
-        bit[2] = r2 & (0u - r2);
-        const unsigned r3 = r2 ^ bit[2];
-        bit[3] = r3 & (0u - r3);
-        const unsigned r4 = r3 ^ bit[3];
+        // how many bidders?  (peeling the mask: no bidder count, no jump table on the way to the common cases)
+        const unsigned r1 = ub & (ub - 1u), r2 = r1 & (r1 - 1u), r3 = r2 & (r2 - 1u), r4 = r3 & (r3 - 1u);
         bool any = true;
         if (r1 == 0u) {
             // ---- the eviction chain: one bidder per iteration until the limit or the first free column ----
@@ -516,17 +533,11 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
                 if (j < 0) break;                                                          // everybody is assigned
             }
             break;
-        } else if (r2 == 0u) {
-            LEAN_COUNT(16)
-            const unsigned b2[2] = {bit[0], bit[1]};
-            any = lean_iter<2, NC>(cc, C, ub, b2, eps, p, own, lane);
-        } else if (r3 == 0u) {
-            LEAN_COUNT(17)
-            const unsigned b3[3] = {bit[0], bit[1], bit[2]};
-            any = lean_iter<3, NC>(cc, C, ub, b3, eps, p, own, lane);
         } else if (r4 == 0u) {
-            LEAN_COUNT(17)
-            any = lean_iter<4, NC>(cc, C, ub, bit, eps, p, own, lane);
+            if (r2 == 0u) { if (!lean_regime<2, NC>(cc, C, ub, eps, it, iters, p, own, lane)) break; }
+            else if (r3 == 0u) { if (!lean_regime<3, NC>(cc, C, ub, eps, it, iters, p, own, lane)) break; }
+            else { if (!lean_regime<4, NC>(cc, C, ub, eps, it, iters, p, own, lane)) break; }
+            continue;                                                                      // it and eps are already advanced
         } else if (__popc(ub) <= 8) {
             // ---- one bidder after the other: per-lane highest bid, toggle bits through one REDUX.OR ----
             LEAN_COUNT(18)

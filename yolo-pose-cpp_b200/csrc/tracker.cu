@@ -205,7 +205,7 @@ struct Ctx {
 };
 
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
-__device__ __forceinline__ void auction_solve(Ctx& c, int na) {
+__device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
     TkSmem& s = c.s;
     if (c.warp_auction && na <= 32 && c.D <= 64) {
         // compact the active rows (cc[i*D + d], i = position in act_list) into the term buffer, which is idle
@@ -217,8 +217,11 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na) {
         if (c.tid < 32) {
             unsigned* cb = reinterpret_cast<unsigned*>(s.colbid);
             int* cr = reinterpret_cast<int*>(s.colbid) + c.D;
-            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, s.acc);
-            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, s.acc);
+            // rows matched in an earlier tier are locked: all their cells are 1e9 (lock_pairs), they can never bid
+            const bool may_bid = c.tid < na && !(after_lock && s.rowb[s.act_list[c.tid]] >= 0);
+            const unsigned ub0 = __ballot_sync(FULLM, may_bid);
+            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc);
+            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc);
         }
         __syncthreads();
     } else if (c.warp_auction && na <= 32) {
@@ -577,7 +580,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
                 lock_pairs(c, s.lgate, na);
                 cost_pass_oks(c, s.lgate, na, 0.2f);
             }
-            auction_solve(c, na);
+            auction_solve(c, na, tier > 0);
             if (tier == 0) stamp(13);
             if (tier > 0) merge_assign(c);
             if (tier < 2) lock_pairs(c, s.gate, na);
