@@ -169,6 +169,10 @@ int pb_get_timing(pb_handle_t h, pb_timing* out);
  * 0 prologue, 1 predict, 2 gate, 3 tier-1 rest, 4 tier 2, 5 tier 3, 6 update, 7 age, 8 new,
  * 9 dedup, 10 total, 11 frame count, 12 tier-1 cost, 13 tier-1 auction, 14 tier-1 lock. */
 int pb_get_stream_stage_ns(pb_handle_t h, unsigned long long* out);
+/* Development aid (handle created with PB_TIMELINE=1 in the environment): absolute globaltimer stamps of the last
+ * 64 steps, out [64][num_streams][6] = tracker CTA begin, state acquired, end, NMS CTA begin, end, unused;
+ * slot = tracker launch sequence number mod 64. */
+int pb_debug_timeline(pb_handle_t h, unsigned long long* out);
 /* Number of kernels this library has launched since process start (bench bookkeeping). */
 long long pb_launch_count(void);
 /* Per-kernel device timing for benchmarks: when enabled, every pb_postprocess /

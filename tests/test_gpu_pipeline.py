@@ -134,6 +134,39 @@ def test_pipelined_steps_equal_serial_steps(pb, orc, cuda, depth):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,depth", [(64, 3), (74, 6), (96, 3)])
+def test_overlapping_tracker_launches_keep_every_stream_in_frame_order(pb, cuda, B, depth):
+    """Consecutive tracker launches overlap (two streams, per-stream sequence flags) when two grids fit the
+    device (2*B <= 148); streams with occlusions run into the auction's iteration limit and fall behind the
+    others.  120 steps without a join, a reset and a stand-alone tracker update in between: states and
+    records must equal the serial handle's bit for bit (B = 96: the non-overlapping fallback)."""
+    torch = cuda
+    F = 48
+    scfg = pb.synth_config(canvas=640, persons=12, period=48, occlusion=1)
+    heads = torch.from_numpy(pb.synth_heads(scfg, 7, B, 0, F, frame_major=True)).cuda()
+    serial = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=4)
+    piped = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=4, pipeline_depth=depth)
+    def compare(tag):
+        o1, c1 = serial.get_tracks_all(); o2, c2 = piped.get_tracks_all()
+        assert np.array_equal(c1, c2) and c1.sum() > 0, tag
+        assert o1.tobytes() == o2.tobytes(), tag
+        for b in (0, B // 2, B - 1):
+            s1, s2 = serial.get_state(b), piped.get_state(b)
+            for k in s1:
+                assert s1[k].tobytes() == s2[k].tobytes(), (tag, b, k)
+    for f in range(70):
+        serial.step(heads[f % F], f); piped.step(heads[f % F], f)
+    compare("after 70 steps")
+    serial.reset(); piped.reset()
+    for f in range(50):
+        serial.step(heads[(f + 5) % F], f); piped.step(heads[(f + 5) % F], f)
+        if f == 20:                                   # a stage-level call in the middle of the pipelined steps
+            serial.postprocess(heads[3]); piped.postprocess(heads[3])
+            serial.tracker_update(100); piped.tracker_update(100)
+    compare("after reset + 50 steps")
+
+
+@pytest.mark.gpu
 def test_submit_host_pipelined_equals_serial_device_path(pb, cuda):
     """pb_submit_host / pb_wait: page-locked heads read in place, lazy NMS sweep, records copied into
     per-step page-locked buffers, consecutive steps overlapping; results = the plain device path."""

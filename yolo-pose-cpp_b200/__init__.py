@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
     "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
-    "pb_get_timing", "pb_get_stream_stage_ns", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
+    "pb_get_timing", "pb_get_stream_stage_ns", "pb_debug_timeline", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_set_output_transform", "pb_state_size", "pb_state_save", "pb_state_load", "pb_pose_distance", "pb_greedy_match",
     "pb_assign_legacy", "pb_letterbox_batch",
     "pb_kf3_initiate", "pb_kf3_predict", "pb_kf3_update", "pb_kf3_extract", "pb_kf3_materialize_cov",
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         L.pb_get_device_views.argtypes = [vp, C.POINTER(PbDeviceViews)]
         L.pb_get_timing.argtypes = [vp, C.POINTER(PbTiming)]
         L.pb_get_stream_stage_ns.argtypes = [vp, vp]
+        L.pb_debug_timeline.argtypes = [vp, vp]
         L.pb_get_post_stage_us.argtypes = [vp, C.POINTER(C.c_double * 5)]
         L.pb_set_profiling.argtypes = [vp, ip]
         L.pb_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip), C.POINTER(C.c_double), C.POINTER(ip)]
@@ -313,6 +314,11 @@ class Pipeline:
         pm, tm, pn, tn = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
         check(lib().pb_get_kernel_ms(self._h, C.byref(pm), C.byref(pn), C.byref(tm), C.byref(tn)))
         return dict(post_ms=pm.value, post_launches=pn.value, track_ms=tm.value, track_launches=tn.value)
+
+    def debug_timeline(self) -> np.ndarray:
+        out = np.zeros((64, self.cfg.num_streams, 6), np.uint64)
+        check(lib().pb_debug_timeline(self._h, out.ctypes.data))
+        return out
 
     def stream_stage_ns(self) -> np.ndarray:
         """[B,20] per-stream nanosecond accumulators of the tracker stages (see the header)."""

@@ -384,6 +384,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
 
     unsigned long long t_stamp = 0;
     if (tid == 0) t_stamp = globaltimer_ns();
+    if (tid == 0 && out.dbg) out.dbg[((size_t)out.dbg_slot * gridDim.x + b) * 6 + 3] = t_stamp;
     auto stamp = [&](int slot) {   // thread 0 accumulates in shared memory, flushed once at the end
         if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
     };
@@ -820,6 +821,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     }
     stamp(4);
     if (tid == 0) { out.num_keep[b] = nkeep; out.num_cand[b] = C; s.acc[7] = 1ull; }
+    if (tid == 0 && out.dbg) out.dbg[((size_t)out.dbg_slot * gridDim.x + b) * 6 + 4] = globaltimer_ns();
     __syncthreads();
     if (tid < 16 && s.acc[tid] != 0ull) out.stage_ns[(size_t)b * 16 + tid] += s.acc[tid];
 }

@@ -50,6 +50,7 @@ struct pb_handle_st {
     int trk_seq = 0;               // sequence number of the last tracker launch (TrackParams::seq)
     cudaStream_t last_trk_stream = nullptr;
     bool last_was_readback = false;
+    bool overlap_trackers = false; // two tracker grids (one CTA per SM each) always fit the device: 2 * num_streams <= SM count
     DecodePlan dplan{};
     TrackBuffers trk{};
     TrackerPlan plan{};
@@ -196,6 +197,11 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &t.stage_ns, B * 20));
     PB_TRY(dev_alloc(h, &t.seq_done, B));
     PB_TRY(dev_alloc(h, &t.error_flag, 1));
+    if (getenv("PB_TIMELINE")) {                       // development aid: absolute begin/end times of the last 64 launches
+        PB_TRY(dev_alloc(h, &t.dbg, (size_t)64 * B * 6));
+        for (PipeSlot& sl : h->ring) sl.post.dbg = t.dbg;
+        h->post.dbg = t.dbg;
+    }
     unsigned char* outp = nullptr;
     PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
     t.outputs = outp;
@@ -239,6 +245,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     if (!h) { pb_set_error("pb_create: out of host memory"); return PB_ERR_INVALID; }
     h->cfg = c;
     h->lazy_keypoints = (c.keypoint_fetch == 1);
+    h->overlap_trackers = 2 * c.num_streams <= prop.multiProcessorCount && !getenv("PB_NO_TRACKER_OVERLAP");
     int r = build_handle(h);
     if (r != PB_OK) { pb_destroy(h); return r; }
     *out = h;
@@ -372,6 +379,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     cudaStream_t ns = (getenv("PB_ONE_NMS_STREAM") || (h->frames & 1)) ? h->s_nms : h->s_nms2;
     PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
+    sl.post.dbg_slot = (h->trk_seq + 1) & 63;
     PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
     PB_CUDA(cudaEventRecord(sl.ev_nms, ns));
     // the lazy NMS sweep fetches keypoints from the borrowed head tensor: later work on the caller's
@@ -380,10 +388,11 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     if (h->lazy_keypoints) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));
     // Tracker launches alternate between two streams: launch i may start while launch i-1 is still
     // running, the per-stream sequence flags inside the kernel keep every video stream's frames in
-    // order (tracker.cu).  With a read-back of the records behind every launch (pb_submit_host) the
+    // order (tracker.cu).  Only when both grids are guaranteed to be resident together (a waiting CTA
+    // must never keep the CTA it waits for from getting an SM): 2 * num_streams <= SM count.  With a read-back of the records behind every launch (pb_submit_host) the
     // output buffer of step i must not be overwritten before it is copied: one stream then.
     const TrackParams tp = track_params(h, frame_id);
-    cudaStream_t ts = (h->rb_tracks || (tp.seq & 1)) ? h->s_trk : h->s_trk2;
+    cudaStream_t ts = (h->rb_tracks || !h->overlap_trackers || (tp.seq & 1)) ? h->s_trk : h->s_trk2;
     if ((h->rb_tracks || h->last_was_readback) && h->last_trk_stream && h->last_trk_stream != ts)
         PB_CUDA(cudaStreamWaitEvent(ts, h->ring[h->cur].ev_trk, 0));   // the previous step's records are still being copied out
     PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_nms, 0));
@@ -716,6 +725,14 @@ int pb_get_stream_stage_ns(pb_handle_t h, unsigned long long* out) {
     if (!h || !out) { pb_set_error("pb_get_stream_stage_ns: bad argument"); return PB_ERR_INVALID; }
     PB_CUDA(cudaDeviceSynchronize());
     PB_CUDA(cudaMemcpy(out, h->trk.stage_ns, (size_t)h->cfg.num_streams * 20 * 8, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+int pb_debug_timeline(pb_handle_t h, unsigned long long* out) {
+    if (!h || !out) { pb_set_error("pb_debug_timeline: bad argument"); return PB_ERR_INVALID; }
+    if (!h->trk.dbg) { pb_set_error("pb_debug_timeline: create the handle with PB_TIMELINE=1 in the environment"); return PB_ERR_UNSUPPORTED; }
+    PB_CUDA(cudaDeviceSynchronize());
+    PB_CUDA(cudaMemcpy(out, h->trk.dbg, (size_t)64 * h->cfg.num_streams * 6 * 8, cudaMemcpyDeviceToHost));
     return PB_OK;
 }
 

@@ -28,6 +28,8 @@ struct PostBuffers {
     int* num_keep;       // [B]
     int* num_cand;       // [B]
     unsigned long long* stage_ns;  // [B, 16] list, rank, load, nms, output (ns sums), [7] = launches
+    unsigned long long* dbg;       // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [3] NMS begin, [4] NMS end
+    int dbg_slot;
 };
 
 // ---- candidate scratch between the decode+gather kernel and the NMS kernel (L2 resident) ----
@@ -65,6 +67,7 @@ struct TrackBuffers {
     unsigned long long* stage_ns;  // [B, 12] globaltimer stamps per stage (telemetry)
     int* seq_done;       // [B] sequence number of the last tracker launch this stream has completed (see pb_tracker_kernel)
     int* error_flag;     // [1] set when a stream's predecessor did not finish within the time-out
+    unsigned long long* dbg;   // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [0] begin, [1] state acquired, [2] end
 };
 
 struct TrackParams {

@@ -450,10 +450,14 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v - want >= 0) break;
             if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); break; }
-            __nanosleep(64);
         }
-        s.acc[15] += globaltimer_ns() - w0;          // telemetry: time spent waiting for the predecessor
+        const unsigned long long w1 = globaltimer_ns();
+        if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(P.seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
+        s.acc[15] += w1 - w0;                        // telemetry: time spent waiting for the predecessor
         s.acc[16] += w0 - t_begin;                   // telemetry: detection-only prologue
+        const unsigned long long prev_end = g_ns[18];   // absolute time at which the predecessor released the stream
+        if (prev_end != 0ull && w1 > prev_end) s.acc[17] += w1 - prev_end;              // predecessor's release -> this CTA goes on
+        if (prev_end != 0ull && t_begin > prev_end) s.acc[19] += t_begin - prev_end;    // ... of which: this CTA had not started yet
     }
     __syncthreads();
     for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
@@ -462,6 +466,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         const int a = g_active[t];
         s.active[t] = a; s.states[t] = g_states[t]; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
         s.row[t] = -1;
+        s.rowbc[t] = g_dirty[t];            // predicted pose changed since its centre was derived (idle auction scratch)
         na_local += (a == 1);
     }
     for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
@@ -476,6 +481,8 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
             const int t = base + c.lane;
             const bool a = (t < T) && (s.active[t] == 1);
             const unsigned bm = __ballot_sync(FULLM, a);
+            const unsigned lm = __ballot_sync(FULLM, a && s.states[t] == ST_LOST);
+            if (c.lane == 0 && lm) atomicAdd(&s.misc[6], __popc(lm));          // LOST rows at frame start
             int start = 0;
             if (c.lane == 0 && bm) start = atomicAdd(&s.misc[0], __popc(bm));
             start = __shfl_sync(FULLM, start, 0);
@@ -512,7 +519,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         // track centres: every slot whose predicted pose changed since its centre was derived
         // (== the reference recomputing all T slots: unchanged slots give unchanged centres)
         for (int t = tid; t < T; t += NT) {
-            if (g_dirty[t]) {
+            if (s.rowbc[t] || (s.active[t] == 1)) {     // predict marks every active slot dirty (below)
                 const float* pp = (P.pred_in_smem && s.active[t] == 1) ? (s.pred + (size_t)t * POSE_F) : (g_pred + (size_t)t * POSE_F);
                 float area;
                 pose_box(pp, &s.tcent[t * 4], &area);
@@ -578,7 +585,8 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
             } else {
                 cost_inactive_rows(c);
                 lock_pairs(c, s.lgate, na);
-                cost_pass_oks(c, s.lgate, na, 0.2f);
+                // the lost-tier gate holds bits of LOST rows only (gate stage): without such a row it is empty
+                if (s.misc[6] > 0) cost_pass_oks(c, s.lgate, na, 0.2f);
             }
             auction_solve(c, na, tier > 0);
             if (tier == 0) stamp(13);
@@ -812,10 +820,13 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         s.acc[11] = 1ull;
     }
     __syncthreads();
-    if (tid < 20 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
+    if (tid < 18 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
+    if (tid == 19 && s.acc[19] != 0ull) g_ns[19] += s.acc[19];
     // release the stream's state to its successor (see the wait in the prologue)
     __syncthreads();
     if (tid == 0) {
+        g_ns[18] = globaltimer_ns();
+        if (tb.dbg) tb.dbg[((size_t)(P.seq & 63) * P.B + b) * 6 + 2] = g_ns[18];
         __threadfence();
         asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
     }
