@@ -8,8 +8,8 @@
 // equal value), every column takes its highest bid (lowest row on equal bid), evicts its
 // owner and raises its price by the bid.  The `threshold` argument is ignored upstream.
 //
-// Mapping: one warp scans one bidder row (lanes stride the columns, shuffle top-2
-// reduction); bids meet in a packed 64-bit shared-memory atomicMax
+// Mapping: one warp scans one bidder row (lanes stride the columns, then three CREDUX
+// reductions on order-preserving keys); bids meet in a packed 64-bit shared-memory atomicMax
 // (bid bits << 32 | ~row: bids are > 0, so their bit patterns order like the floats);
 // two block barriers per iteration.  The loop stops at the first iteration in which no
 // row bids: prices and assignments are then a fixed point of all remaining iterations.
@@ -17,6 +17,16 @@
 #include "pb_common.cuh"
 
 namespace pb {
+
+// float order -> unsigned order and back (warp reductions on values run on these keys)
+__device__ __forceinline__ unsigned hy_ord(float f) {            // float order -> unsigned order (-0.0 == +0.0)
+    unsigned b = __float_as_uint(f);
+    b = (b == 0x80000000u) ? 0u : b;
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float hy_unord(unsigned u) {
+    return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u));
+}
 
 // cost: flat [rows, cols] (shared or global).  active may be nullptr (all rows active).
 // row/col/price/colbid/flags(2 ints) must be shared memory.  Ends with a block barrier.
@@ -56,23 +66,21 @@ __device__ __forceinline__ void auction_solve_cta(const float* cost, int R, int 
                     if (v > bv) { sv = bv; bv = v; bc = d; }
                     else if (v > sv) { sv = v; }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ob = __shfl_xor_sync(FULL, bv, off);
-                    const float os = __shfl_xor_sync(FULL, sv, off);
-                    const int oc = __shfl_xor_sync(FULL, bc, off);
-                    // lowest column wins ties (strict '>' in ascending column order, :63);
-                    // a lane without candidate (bc = -1, bv = -1e9) never wins.
-                    const bool other = (oc >= 0) && ((bc < 0) || (ob > bv) || (ob == bv && oc < bc));
-                    if (other) { sv = pb_max(os, bv); bv = ob; bc = oc; }
-                    else { sv = pb_max(sv, ob); }
-                }
-                if (lane == 0 && bc >= 0) {
-                    const float bid = bv - sv + eps;                       // :99
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(bid) << 32) |
-                                                   (unsigned long long)(0xffffffffu - (unsigned)rb);
-                    atomicMax(&colbid[bc], key);                           // highest bid, lowest row (:100)
-                    flags[it & 1] = 1;
+                // warp-level top-2 with three CREDUX reductions on order-preserving integer keys (see the lean
+                // solve below): best value, lowest column holding it (:63), best of the other columns (:67-69)
+                const unsigned kb = hy_ord(bv);
+                const unsigned m = __reduce_max_sync(FULL, kb);
+                if (m != hy_ord(-1e9f)) {                                  // some column is above the -1e9 floor
+                    const int key = (kb == m) ? bc : 0x7fffffff;
+                    const int bcw = __reduce_min_sync(FULL, key);
+                    const unsigned m2 = __reduce_max_sync(FULL, (key == bcw) ? hy_ord(sv) : kb);
+                    if (lane == 0) {
+                        const float bid = hy_unord(m) - hy_unord(m2) + eps;    // :99
+                        const unsigned long long kk = ((unsigned long long)__float_as_uint(bid) << 32) |
+                                                      (unsigned long long)(0xffffffffu - (unsigned)rb);
+                        atomicMax(&colbid[bcw], kk);                       // highest bid, lowest row (:100)
+                        flags[it & 1] = 1;
+                    }
                 }
             }
         }
@@ -208,15 +216,6 @@ __device__ __forceinline__ void auction_solve_warp(const float* cost, int R, int
 // bit for bit (tests compare the three implementations on random and degenerate problems).
 // ---------------------------------------------------------------------------------------
 constexpr int HY_COLPAR_MAX = 4;
-
-__device__ __forceinline__ unsigned hy_ord(float f) {            // float order -> unsigned order (-0.0 == +0.0)
-    unsigned b = __float_as_uint(f);
-    b = (b == 0x80000000u) ? 0u : b;
-    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ float hy_unord(unsigned u) {
-    return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u));
-}
 
 static __device__ __noinline__ void auction_solve_hybrid32(const float* cost_s, int R, int C, const int* act_list, int na,
                                                            int* row, int* col, float* price, int* owner,

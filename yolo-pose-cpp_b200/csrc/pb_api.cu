@@ -46,7 +46,7 @@ struct pb_handle_st {
     std::vector<PipeSlot> ring;    // cfg.pipeline_depth slots
     int cur = 0;
     bool inflight = false;         // work of a pipelined pb_step may still run on the internal streams
-    cudaStream_t s_nms = nullptr, s_nms2 = nullptr, s_trk = nullptr, s_trk2 = nullptr;   // tracker launches alternate between s_trk and s_trk2
+    cudaStream_t s_nms = nullptr, s_trk = nullptr, s_trk2 = nullptr;   // tracker launches alternate between s_trk and s_trk2
     int trk_seq = 0;               // sequence number of the last tracker launch (TrackParams::seq)
     cudaStream_t last_trk_stream = nullptr;
     bool last_was_readback = false;
@@ -169,7 +169,6 @@ static int build_handle(pb_handle_st* h) {
     h->cur = 0; h->post = h->ring[0].post; h->cand = h->ring[0].cand;
     if (c.pipeline_depth > 1) {
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_nms, cudaStreamNonBlocking));
-        PB_CUDA(cudaStreamCreateWithFlags(&h->s_nms2, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk2, cudaStreamNonBlocking));
     }
@@ -262,7 +261,6 @@ int pb_destroy(pb_handle_t h) {
     if (h->h_cnt_pinned) cudaFreeHost(h->h_cnt_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->s_nms) cudaStreamDestroy(h->s_nms);
-    if (h->s_nms2) cudaStreamDestroy(h->s_nms2);
     if (h->s_trk) cudaStreamDestroy(h->s_trk);
     if (h->s_trk2) cudaStreamDestroy(h->s_trk2);
     for (PipeSlot& sl : h->ring) {
@@ -375,8 +373,9 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));          // scratch still being read
     PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, sl.cand, stream));
     PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
-    // consecutive NMS launches are independent of each other: two streams, so that they may overlap
-    cudaStream_t ns = (getenv("PB_ONE_NMS_STREAM") || (h->frames & 1)) ? h->s_nms : h->s_nms2;
+    // NMS launches stay on one stream: two of them in flight (128 CTAs, one SM each) starve the tracker
+    // grids of SMs (measured: 39.4 us per batch against 37.2)
+    cudaStream_t ns = h->s_nms;
     PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
     sl.post.dbg_slot = (h->trk_seq + 1) & 63;
