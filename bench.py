@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-per-gpu", type=int, default=STREAMS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--pipeline-depth", type=int, default=3)
+    ap.add_argument("--pipeline-depth", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

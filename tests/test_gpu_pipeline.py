@@ -195,3 +195,37 @@ def test_submit_host_pipelined_equals_serial_device_path(pb, cuda):
     assert total > 500
     with pytest.raises(pb.PbError):                       # pageable buffers are refused
         piped.submit_host(host[0], 0, outs[0].numpy(), cnts[0].numpy())
+
+
+@pytest.mark.gpu
+def test_long_run_equals_checker_and_pipelined_lanes(pb, orc, cuda):
+    """Long runs (32 streams x 300 frames, heads rotating with period 20).  Regression test for a race
+    that needed ~5000 stream-frames to show: the tracker's active-row list was compacted through an
+    atomic counter, so its order — which breaks ties between equal auction bids (lowest row) — depended
+    on which warp arrived first.  Serial path, a second serial handle, the pipelined path with three
+    lanes (pipeline_depth 5) and the CPU checker must agree bit for bit on every stream's final state."""
+    torch = cuda
+    B, F, STEPS = 32, 20, 300
+    scfg = pb.synth_config(canvas=640, persons=20, period=F)
+    host = pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)
+    heads = torch.from_numpy(host).cuda()
+    a = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+    a2 = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+    p = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=5)
+    for f in range(STEPS):
+        a.step(heads[f % F], f); a2.step(heads[f % F], f); p.step(heads[f % F], f)
+    p.join(); torch.cuda.synchronize()
+    oa, ca = a.get_tracks_all(); o2, c2 = a2.get_tracks_all(); op, cp = p.get_tracks_all()
+    assert np.array_equal(ca, c2) and oa.tobytes() == o2.tobytes(), "two serial handles differ: a race"
+    assert np.array_equal(ca, cp) and oa.tobytes() == op.tobytes(), "pipelined (lanes) differs from serial"
+    assert a.state_save()[24:] == a2.state_save()[24:] == p.state_save()[24:]
+    # the checker on a quarter of the streams (kept detections repeat with the head period)
+    for b in range(0, B, 4):
+        dets = [orc.postprocess(host[f, b]) for f in range(F)]
+        trk = orc.Tracker()
+        for f in range(STEPS):
+            trk.update(dets[f % F]["poses"], dets[f % F]["scores"], f)
+        assert trk.get_tracks().tobytes() == oa[b, :ca[b]].tobytes(), b
+        s1, s2 = trk.get_state(), a.get_state(b)
+        for k in ("ids", "hits", "ages", "states", "active", "row_assign", "col_assign", "poses", "vel"):
+            assert s1[k].tobytes() == s2[k].tobytes(), (b, k)

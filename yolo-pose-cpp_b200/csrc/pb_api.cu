@@ -46,7 +46,8 @@ struct pb_handle_st {
     std::vector<PipeSlot> ring;    // cfg.pipeline_depth slots
     int cur = 0;
     bool inflight = false;         // work of a pipelined pb_step may still run on the internal streams
-    cudaStream_t s_nms = nullptr, s_trk = nullptr, s_trk2 = nullptr;   // tracker launches alternate between s_trk and s_trk2
+    cudaStream_t s_nms = nullptr, s_trk = nullptr, s_trk2 = nullptr, s_trk3 = nullptr;   // lanes: step i's NMS and tracker run on lane i % lanes
+    int lanes = 0;                 // number of lanes (0: NMS on s_nms, trackers alternate between s_trk and s_trk2)
     int trk_seq = 0;               // sequence number of the last tracker launch (TrackParams::seq)
     cudaStream_t last_trk_stream = nullptr;
     bool last_was_readback = false;
@@ -171,6 +172,7 @@ static int build_handle(pb_handle_st* h) {
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_nms, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk2, cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk3, cudaStreamNonBlocking));
     }
     TrackBuffers& t = h->trk;
     PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
@@ -245,6 +247,16 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     h->cfg = c;
     h->lazy_keypoints = (c.keypoint_fetch == 1);
     h->overlap_trackers = 2 * c.num_streams <= prop.multiProcessorCount && !getenv("PB_NO_TRACKER_OVERLAP");
+    // Lanes: the oldest tracker grid in flight never waits, the younger ones may spin on their predecessors and
+    // hold one SM per CTA while they do: (lanes - 1) * num_streams must stay below the SM count.
+    h->lanes = 0;
+    // Measured at 64 streams: three lanes 37.0 us per batch, two lanes 44.8 (a step's NMS then waits for the tracker two
+    // steps back), the separate NMS stream 38-40.
+    if (h->overlap_trackers && 2 * c.num_streams < prop.multiProcessorCount && c.pipeline_depth >= 4) h->lanes = 3;
+    if (const char* e = getenv("PB_LANES")) {
+        const int l = atoi(e);
+        if (l >= 0 && l <= 3 && (l <= 1 || (l - 1) * c.num_streams < prop.multiProcessorCount)) h->lanes = l;
+    }
     int r = build_handle(h);
     if (r != PB_OK) { pb_destroy(h); return r; }
     *out = h;
@@ -263,6 +275,7 @@ int pb_destroy(pb_handle_t h) {
     if (h->s_nms) cudaStreamDestroy(h->s_nms);
     if (h->s_trk) cudaStreamDestroy(h->s_trk);
     if (h->s_trk2) cudaStreamDestroy(h->s_trk2);
+    if (h->s_trk3) cudaStreamDestroy(h->s_trk3);
     for (PipeSlot& sl : h->ring) {
         if (sl.ev_gather) cudaEventDestroy(sl.ev_gather);
         if (sl.ev_nms) cudaEventDestroy(sl.ev_nms);
@@ -373,28 +386,32 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));          // scratch still being read
     PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, sl.cand, stream));
     PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
-    // NMS launches stay on one stream: two of them in flight (128 CTAs, one SM each) starve the tracker
-    // grids of SMs (measured: 39.4 us per batch against 37.2)
-    cudaStream_t ns = h->s_nms;
+    const TrackParams tp = track_params(h, frame_id);
+    // Lanes: the NMS and the tracker launch of step i run back to back on internal stream i % lanes, so a
+    // step's tracker follows its NMS without an event hop and `lanes` steps are in flight with one kernel
+    // each (at most lanes * num_streams CTAs, one SM each: NMS launches of consecutive steps overlap
+    // without starving the tracker grids).  Inside the tracker kernel the per-stream sequence flags keep
+    // every video stream's frames in order (tracker.cu): the oldest grid never waits, so the spin cannot
+    // deadlock while (lanes - 1) * num_streams < SM count.  lanes == 0: NMS launches on one stream,
+    // tracker launches alternating between two.  With a read-back of the records behind every launch
+    // (pb_submit_host) the output buffer of step i must not be overwritten before it is copied: one lane then.
+    cudaStream_t lane[3] = {h->s_trk, h->s_trk2, h->s_trk3};
+    const bool single = h->rb_tracks || !h->overlap_trackers;
+    cudaStream_t ts, ns;
+    if (h->lanes > 0) { ts = single ? h->s_trk : lane[tp.seq % h->lanes]; ns = ts; }
+    else { ts = (single || (tp.seq & 1)) ? h->s_trk : h->s_trk2; ns = h->s_nms; }
     PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
-    sl.post.dbg_slot = (h->trk_seq + 1) & 63;
+    sl.post.dbg_slot = tp.seq & 63;
     PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
     PB_CUDA(cudaEventRecord(sl.ev_nms, ns));
     // the lazy NMS sweep fetches keypoints from the borrowed head tensor: later work on the caller's
     // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it then.
     // With complete records the decode+gather kernel is the only reader of the head and nothing is needed.
     if (h->lazy_keypoints) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));
-    // Tracker launches alternate between two streams: launch i may start while launch i-1 is still
-    // running, the per-stream sequence flags inside the kernel keep every video stream's frames in
-    // order (tracker.cu).  Only when both grids are guaranteed to be resident together (a waiting CTA
-    // must never keep the CTA it waits for from getting an SM): 2 * num_streams <= SM count.  With a read-back of the records behind every launch (pb_submit_host) the
-    // output buffer of step i must not be overwritten before it is copied: one stream then.
-    const TrackParams tp = track_params(h, frame_id);
-    cudaStream_t ts = (h->rb_tracks || !h->overlap_trackers || (tp.seq & 1)) ? h->s_trk : h->s_trk2;
     if ((h->rb_tracks || h->last_was_readback) && h->last_trk_stream && h->last_trk_stream != ts)
         PB_CUDA(cudaStreamWaitEvent(ts, h->ring[h->cur].ev_trk, 0));   // the previous step's records are still being copied out
-    PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_nms, 0));
+    if (ns != ts) PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_nms, 0));
     DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
     PB_CUDA(launch_tracker(h->trk, tp, src, h->plan, ts));
     PB_TRY(enqueue_readback(h, ts));

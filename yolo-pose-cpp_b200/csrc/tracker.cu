@@ -476,17 +476,20 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     c.pred = P.pred_in_smem ? s.pred : g_pred;
     if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
     __syncthreads();
-    {   // active count + ordered active list (ascending t)
+    {   // active count + ordered active list (ascending t).  The list position of a row is its rank among the
+        // active rows — the auction breaks ties between equal bids by it (lowest row, hungarian.cu:100) — so
+        // it must not depend on which warp gets here first: every warp derives the number of active rows
+        // in front of its block from ballots over the preceding blocks instead of from an atomic counter.
         for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
+            int start = 0;
+            for (int pb = 0; pb < base; pb += 32) start += __popc(__ballot_sync(FULLM, s.active[pb + c.lane] == 1));
             const int t = base + c.lane;
             const bool a = (t < T) && (s.active[t] == 1);
             const unsigned bm = __ballot_sync(FULLM, a);
             const unsigned lm = __ballot_sync(FULLM, a && s.states[t] == ST_LOST);
-            if (c.lane == 0 && lm) atomicAdd(&s.misc[6], __popc(lm));          // LOST rows at frame start
-            int start = 0;
-            if (c.lane == 0 && bm) start = atomicAdd(&s.misc[0], __popc(bm));
-            start = __shfl_sync(FULLM, start, 0);
+            if (c.lane == 0 && lm) atomicAdd(&s.misc[6], __popc(lm));          // LOST rows at frame start (a sum: order-free)
             if (a) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
+            if (c.lane == 0 && base + 32 >= T) s.misc[0] = start + __popc(bm);
         }
     }
     __syncthreads();
@@ -693,16 +696,15 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     {
         if (tid == 0) { s.misc[1] = 0; s.misc[2] = 0; }
         __syncthreads();
-        for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {   // eligible list, ascending
+        for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {   // eligible list, ascending (ordered like act_list above)
+            auto elig = [&](int t) { return (t < T) && s.active[t] == 1 && s.states[t] != ST_LOST && s.hits[t] >= P.min_hits; };
+            int start = 0;
+            for (int pb = 0; pb < base; pb += 32) start += __popc(__ballot_sync(FULLM, elig(pb + c.lane)));
             const int t = base + c.lane;
-            const bool e = (t < T) && s.active[t] == 1 && s.states[t] != ST_LOST && s.hits[t] >= P.min_hits;
+            const bool e = elig(t);
             const unsigned bm = __ballot_sync(FULLM, e);
-            if (bm) {
-                int start = 0;
-                if (c.lane == 0) start = atomicAdd(&s.misc[1], __popc(bm));
-                start = __shfl_sync(FULLM, start, 0);
-                if (e) s.elig_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
-            }
+            if (e) s.elig_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
+            if (c.lane == 0 && base + 32 >= T) s.misc[1] = start + __popc(bm);
         }
         __syncthreads();
         const int ne = s.misc[1];
