@@ -401,12 +401,14 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     if (tid < KP) s.sig[tid] = kSigmas[tid];
     for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.sup[i] = 0u;
     for (int i = tid; i < Ccap; i += NM_THREADS) s.vis[i] = 0u;
-    for (int p = tid; p < 2016; p += NM_THREADS) {       // triangular pair table: row a holds 63-a pairs
-        int a = 0, base = 0;
-        while (p >= base + (63 - a)) { base += 63 - a; ++a; }
-        s.tri[p] = (unsigned short)((a << 8) | (a + 1 + (p - base)));
+    for (int p = tid; p < 2016; p += NM_THREADS) {       // triangular pair table: row a holds the 63-a pairs (a, b > a)
+        int a = (int)((127.0f - sqrtf(16129.0f - 8.0f * (float)p)) * 0.5f);    // first pair of row a is a*(127-a)/2
+        if (a < 0) a = 0;
+        while (a > 0 && a * (127 - a) / 2 > p) --a;
+        while ((a + 1) * (126 - a) / 2 <= p) ++a;
+        s.tri[p] = (unsigned short)((a << 8) | (a + 1 + (p - a * (127 - a) / 2)));
     }
-    __syncthreads();
+    int* segstart = reinterpret_cast<int*>(s.l1_key);    // [nseg + 1]; the pair list is idle until the sweep
     if (warp == 0) {
         int run = 0;
         for (int sg0 = 0; sg0 < nseg; sg0 += 32) {
@@ -415,15 +417,20 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             int incl = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-            const int start = run + incl - n;
-            for (int h = 0; h < n; ++h) { const int c = start + h; if (c < Ccap) s.recidx[c] = sg * segcap + h; }
+            if (sg < nseg) segstart[sg] = run + incl - n;
             run += __shfl_sync(FULL, incl, 31);
         }
-        if (lane == 0) s.misc[0] = run < Ccap ? run : Ccap;
+        if (lane == 0) { segstart[nseg] = run; s.misc[0] = run < Ccap ? run : Ccap; }
     }
     __syncthreads();
     const int C = s.misc[0];
-    for (int c = tid; c < C; c += NM_THREADS) s.score[c] = recs[(size_t)s.recidx[c] * HEAD_ROWS + 4];
+    for (int c = tid; c < C; c += NM_THREADS) {          // slot c -> record of its segment, and its score
+        int sg = 0;
+        while (segstart[sg + 1] <= c) ++sg;
+        const int ri = sg * segcap + (c - segstart[sg]);
+        s.recidx[c] = ri;
+        s.score[c] = recs[(size_t)ri * HEAD_ROWS + 4];
+    }
     __syncthreads();
     stamp(0);
 
