@@ -197,6 +197,7 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &t.det_poses_scratch, B * Dm * POSE_F));
     PB_TRY(dev_alloc(h, &t.stage_ns, B * 20));
     PB_TRY(dev_alloc(h, &t.seq_done, B));
+    PB_TRY(dev_alloc(h, &t.out_done, B));
     PB_TRY(dev_alloc(h, &t.error_flag, 1));
     if (getenv("PB_TIMELINE")) {                       // development aid: absolute begin/end times of the last 64 launches
         PB_TRY(dev_alloc(h, &t.dbg, (size_t)64 * B * 6));

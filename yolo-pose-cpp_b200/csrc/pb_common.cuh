@@ -65,7 +65,8 @@ struct TrackBuffers {
     int* num_outputs;    // [B]
     float* det_poses_scratch;  // [B, Dm, 51]  used when the detections do not fit in shared memory
     unsigned long long* stage_ns;  // [B, 12] globaltimer stamps per stage (telemetry)
-    int* seq_done;       // [B] sequence number of the last tracker launch this stream has completed (see pb_tracker_kernel)
+    int* seq_done;       // [B] sequence number of the last tracker launch whose STATE update this stream has completed (see pb_tracker_kernel)
+    int* out_done;       // [B] ... whose TrackOutput records are written as well (second release)
     int* error_flag;     // [1] set when a stream's predecessor did not finish within the time-out
     unsigned long long* dbg;   // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [0] begin, [1] state acquired, [2] end
 };

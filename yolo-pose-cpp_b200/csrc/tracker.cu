@@ -212,6 +212,7 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
         // between cost passes: the single-warp solve then reads a bidder's row with one conflict-free load
         float* cc = s.terms;
         const int D = c.D;
+#pragma unroll 1
         for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = i / D; cc[i] = s.cost[s.act_list[ai] * D + (i - ai * D)]; }
         __syncthreads();
         if (c.tid < 32) {
@@ -247,6 +248,7 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
 __device__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
+#pragma unroll 1
     for (int ai = c.warp; ai < na; ai += c.nwarps) {
         const int t = s.act_list[ai];
         const bool rowm = s.row[t] >= 0;
@@ -265,8 +267,10 @@ __device__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
 // for these rows (see lock_pairs), so this runs once per frame, in the lost-track tier.
 __device__ void cost_inactive_rows(Ctx& c) {
     TkSmem& s = c.s;
+#pragma unroll 1
     for (int t = c.warp; t < c.T; t += c.nwarps)
         if (s.active[t] == 0)
+#pragma unroll 1
             for (int d = c.lane; d < c.D; d += 32) c.cost[(size_t)t * c.D + d] = 1.0f;
 }
 
@@ -285,6 +289,7 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
         const int a1 = (a0 + rows_per_chunk < na) ? a0 + rows_per_chunk : na;
         if (c.tid == 0) s.misc[5] = 0;
         __syncthreads();
+#pragma unroll 1
         for (int ai = a0 + c.warp; ai < a1; ai += c.nwarps) {
             const int t = s.act_list[ai];
             for (int w = 0; w < words; ++w) {
@@ -305,6 +310,7 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
         const int ncell = s.misc[5] < CELL_LIST_CAP ? s.misc[5] : CELL_LIST_CAP;
         for (int cb = 0; cb < ncell; cb += cells_per_round) {
             const int ncur = (ncell - cb) < cells_per_round ? (ncell - cb) : cells_per_round;
+#pragma unroll 1
             for (int idx = c.tid; idx < ncur * KP; idx += c.nthreads) {
                 const int e = idx / KP, k = idx - e * KP;
                 const int key = s.cell_list[cb + e];
@@ -324,6 +330,7 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
                 s.terms[idx] = term;
             }
             __syncthreads();
+#pragma unroll 1
             for (int e = c.tid; e < ncur; e += c.nthreads) {
                 const int key = s.cell_list[cb + e];
                 const int t = key >> 16, d = key & 0xffff;
@@ -346,6 +353,7 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
 __device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw;
+#pragma unroll 1
     for (int i = c.tid; i < na * D; i += c.nthreads) {
         const int ai = i / D, d = i - ai * D;
         const int t = s.act_list[ai];
@@ -357,12 +365,16 @@ __device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
 
 __device__ void backup_assign(Ctx& c) {      // no barrier: callers synchronise before the next solve
     TkSmem& s = c.s;
+#pragma unroll 1
     for (int t = c.tid; t < c.T; t += c.nthreads) s.rowb[t] = s.row[t];
+#pragma unroll 1
     for (int d = c.tid; d < c.D; d += c.nthreads) s.colb[d] = s.col[d];
 }
 __device__ void merge_assign(Ctx& c) {   // kernelMergeAssignments :575-588
     TkSmem& s = c.s;
+#pragma unroll 1
     for (int t = c.tid; t < c.T; t += c.nthreads) if (s.rowb[t] >= 0) s.row[t] = s.rowb[t];
+#pragma unroll 1
     for (int d = c.tid; d < c.D; d += c.nthreads) if (s.colb[d] >= 0) s.col[d] = s.colb[d];
     __syncthreads();
 }
@@ -427,7 +439,9 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     const float* src_pose = src.poses + (size_t)b * src.stride * POSE_F;
     const float* src_score = src.scores + (size_t)b * src.stride;
     float* det_w = P.det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
+#pragma unroll 1
     for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
+#pragma unroll 1
     for (int d = tid; d < D; d += NT) { s.dscore[d] = src_score[d]; s.col[d] = -1; }
     if (tid < 32) s.misc[tid] = 0;
     if (tid < 20) s.acc[tid] = 0ull;
@@ -460,8 +474,10 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         if (prev_end != 0ull && t_begin > prev_end) s.acc[19] += t_begin - prev_end;    // ... of which: this CTA had not started yet
     }
     __syncthreads();
+#pragma unroll 1
     for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
     int na_local = 0;
+#pragma unroll 1
     for (int t = tid; t < T; t += NT) {
         const int a = g_active[t];
         s.active[t] = a; s.states[t] = g_states[t]; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
@@ -469,6 +485,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         s.rowbc[t] = g_dirty[t];            // predicted pose changed since its centre was derived (idle auction scratch)
         na_local += (a == 1);
     }
+#pragma unroll 1
     for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
     c.det = det_w;
     c.cost = P.cost_in_smem ? s.cost : g_cost;
@@ -499,6 +516,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
 
     // ---------------- predict (:1160-1175, kernel :102-138) ----------------
     if (na > 0) {
+#pragma unroll 1
         for (int i = tid; i < na * KP; i += NT) {
             const int ai = i / KP, k = i - ai * KP;
             const int t = s.act_list[ai];
@@ -521,6 +539,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     if (assoc12) {
         // track centres: every slot whose predicted pose changed since its centre was derived
         // (== the reference recomputing all T slots: unchanged slots give unchanged centres)
+#pragma unroll 1
         for (int t = tid; t < T; t += NT) {
             if (s.rowbc[t] || (s.active[t] == 1)) {     // predict marks every active slot dirty (below)
                 const float* pp = (P.pred_in_smem && s.active[t] == 1) ? (s.pred + (size_t)t * POSE_F) : (g_pred + (size_t)t * POSE_F);
@@ -532,6 +551,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
                 g_dirty[t] = 0;
             }
         }
+#pragma unroll 1
         for (int ai = tid; ai < na; ai += NT) {   // mean torso speed per active row (:287-298)
             const int t = s.act_list[ai];
             const int torso[4] = {5, 6, 11, 12};
@@ -545,11 +565,13 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         }
     }
     if (D > 0) {
+#pragma unroll 1
         for (int d = tid; d < D; d += NT) {
             float area;
             pose_box(c.det + (size_t)d * POSE_F, &s.dcent[d * 4], &area);
             s.darea[d] = area;
         }
+#pragma unroll 1
         for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = 0u; s.lgate[i] = 0u; }
     }
     __syncthreads();
@@ -557,6 +579,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         // gate (base 3.0) minus LOST rows (tier 1 mask, :1231) and lost-tier gate (base 3.0*1.3,
         // only LOST rows survive the two state masks, :1359-1387).  One warp per (row, 32 dets).
         const int words = (D + 31) / 32;
+#pragma unroll 1
         for (int i = c.warp; i < na * words; i += c.nwarps) {
             const int ai = i / words, w = i - ai * words;
             const int t = s.act_list[ai];
@@ -600,11 +623,26 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         stamp(3 + tier);
     }
 
+    // The predecessor's record assembly reads g_poses after it released the state (second release at its end):
+    // nothing before this point writes g_poses, tb.outputs or the telemetry slots; wait for it here (it finished
+    // long ago unless the launches ran far apart from the usual order).
+    if (tid == 0) {
+        const int want = P.seq - 1;
+        const unsigned long long w0 = globaltimer_ns();
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(tb.out_done + b) : "memory");
+            if (v - want >= 0) break;
+            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); break; }
+        }
+    }
+    __syncthreads();
     // ---------------- update matched (:1438-1472, kernels :141-189, :612-648) -------------
     if (D > 0) {
         const float process_noise = 0.1f, measurement_noise = 0.3f;
         const float K = measurement_noise / (measurement_noise + process_noise);
         const float alpha = 0.3f;
+#pragma unroll 1
         for (int i = tid; i < na * KP; i += NT) {
             const int ai = i / KP, k = i - ai * KP;
             const int t = s.act_list[ai];
@@ -621,6 +659,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
             g_vel[vo + 1] = alpha * dy + (1 - alpha) * g_vel[vo + 1];
             g_poses[to] = nx; g_poses[to + 1] = ny; g_poses[to + 2] = zc;
         }
+#pragma unroll 1
         for (int ai = tid; ai < na; ai += NT) {
             const int t = s.act_list[ai];
             const int d = s.row[t];
@@ -639,6 +678,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     stamp(6);
 
     // ---------------- age unmatched (:1474-1487, kernel :651-688) ----------------
+#pragma unroll 1
     for (int ai = tid; ai < na; ai += NT) {
         const int t = s.act_list[ai];
         if (s.row[t] >= 0) continue;
@@ -678,11 +718,13 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
             g_scal[1] = hint; g_scal[0] = next_id;
         }
         __syncthreads();
+#pragma unroll 1
         for (int i = tid; i < D * POSE_F; i += NT) {
             const int d = i / POSE_F, e = i - d * POSE_F;
             const int sl = s.slot_for_det[d];
             if (sl >= 0) g_poses[sl * POSE_F + e] = c.det[(size_t)d * POSE_F + e];
         }
+#pragma unroll 1
         for (int i = tid; i < D * 34; i += NT) {
             const int d = i / 34, e = i - d * 34;
             const int sl = s.slot_for_det[d];
@@ -708,6 +750,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         }
         __syncthreads();
         const int ne = s.misc[1];
+#pragma unroll 1
         for (int i = tid; i < ne * ne; i += NT) {
             const int ia = i / ne, ib = i - ia * ne;
             const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
@@ -744,6 +787,35 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     }
     stamp(9);
 
+    // ---------------- write back state ----------------
+    int cnt_local = 0;
+#pragma unroll 1
+    for (int t = tid; t < T; t += NT) {
+        g_active[t] = s.active[t]; g_states[t] = s.states[t]; g_hits[t] = s.hits[t]; g_ids[t] = s.ids[t];
+        g_ages[t] = s.ages[t];
+        tb.row_assign[(size_t)b * T + t] = s.row[t];
+        cnt_local += (s.active[t] == 1);
+    }
+#pragma unroll 1
+    for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
+    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
+    // block-wide sum of cnt_local (update()'s return value, :1130-1136)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt_local += __shfl_xor_sync(FULLM, cnt_local, off);
+    if (c.lane == 0 && cnt_local) atomicAdd(&s.misc[4], cnt_local);
+    __syncthreads();
+    if (tid == 0) {
+        // ---- first release: the stream's STATE is final; its next frame may go on (see the wait in the prologue).
+        // The TrackOutput records below read g_poses and write tb.outputs; the successor touches neither before its
+        // update stage, where it waits for the second flag (out_done).  The ~2 us of record assembly thus leave
+        // the chain of dependent frames.
+        g_scal[2] = D; g_scal[3] = s.misc[4];
+        g_ns[18] = globaltimer_ns();
+        if (tb.dbg) tb.dbg[((size_t)(P.seq & 63) * P.B + b) * 6 + 2] = g_ns[18];
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
+    }
+
     // ---------------- outputs: getActiveTracks (:1594-1636) on the device ------------------
     if (tid < 32) {
         int count = 0;
@@ -772,6 +844,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         const float sx = xf ? tb.out_xform[b * 4 + 0] : 1.0f, sy = xf ? tb.out_xform[b * 4 + 1] : 1.0f;
         const float px_ = xf ? tb.out_xform[b * 4 + 2] : 0.0f, py_ = xf ? tb.out_xform[b * 4 + 3] : 0.0f;
         float* outw = reinterpret_cast<float*>(tb.outputs) + (size_t)b * Dm * 57;
+#pragma unroll 1
         for (int o = c.warp; o < n_out; o += c.nwarps) {
             const int d = s.out_list[o];
             const int sl = s.col[d];
@@ -799,23 +872,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
         }
     }
 
-    // ---------------- write back state ----------------
-    int cnt_local = 0;
-    for (int t = tid; t < T; t += NT) {
-        g_active[t] = s.active[t]; g_states[t] = s.states[t]; g_hits[t] = s.hits[t]; g_ids[t] = s.ids[t];
-        g_ages[t] = s.ages[t];
-        tb.row_assign[(size_t)b * T + t] = s.row[t];
-        cnt_local += (s.active[t] == 1);
-    }
-    for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
-    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
-    // block-wide sum of cnt_local (update()'s return value, :1130-1136)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt_local += __shfl_xor_sync(FULLM, cnt_local, off);
-    if (c.lane == 0 && cnt_local) atomicAdd(&s.misc[4], cnt_local);
-    __syncthreads();
     if (tid == 0) {
-        g_scal[2] = D; g_scal[3] = s.misc[4];
         tb.num_outputs[b] = n_out;
         const unsigned long long now = globaltimer_ns();
         s.acc[10] = now - t_begin;
@@ -824,13 +881,11 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     __syncthreads();
     if (tid < 18 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
     if (tid == 19 && s.acc[19] != 0ull) g_ns[19] += s.acc[19];
-    // release the stream's state to its successor (see the wait in the prologue)
+    // second release: records and telemetry written, g_poses no longer read
     __syncthreads();
     if (tid == 0) {
-        g_ns[18] = globaltimer_ns();
-        if (tb.dbg) tb.dbg[((size_t)(P.seq & 63) * P.B + b) * 6 + 2] = g_ns[18];
         __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
     }
 }
 
@@ -850,7 +905,7 @@ __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm, i
     if (i < (size_t)B) {
         tb.scalars[i * 4 + 0] = 1; tb.scalars[i * 4 + 1] = 0; tb.scalars[i * 4 + 2] = 0; tb.scalars[i * 4 + 3] = 0;
         tb.num_outputs[i] = 0;
-        tb.seq_done[i] = seq;
+        tb.seq_done[i] = seq; tb.out_done[i] = seq;
     }
     if (i == 0) *tb.error_flag = 0;
     if (i < (size_t)B * 20) tb.stage_ns[i] = 0ull;
