@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import posebyte_b200 as pb
 
-def run(name, B, canvas, persons, T, Dm, max_age, clumps=0, occlusion=0, steps=200, depth=3, F=8):
+def run(name, B, canvas, persons, T, Dm, max_age, clumps=0, occlusion=0, steps=200, depth=5, F=8):
     scfg = pb.synth_config(canvas=canvas, persons=persons, period=64, clumps=clumps, occlusion=occlusion,
                            kp_drop_prob=0.15 if clumps else 0.05)
     d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()

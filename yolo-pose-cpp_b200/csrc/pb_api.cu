@@ -399,8 +399,14 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     cudaStream_t lane[3] = {h->s_trk, h->s_trk2, h->s_trk3};
     const bool single = h->rb_tracks || !h->overlap_trackers;
     cudaStream_t ts, ns;
-    if (h->lanes > 0) { ts = single ? h->s_trk : lane[tp.seq % h->lanes]; ns = ts; }
-    else { ts = (single || (tp.seq & 1)) ? h->s_trk : h->s_trk2; ns = h->s_nms; }
+    if (h->lanes > 0 && !single) { ts = lane[tp.seq % h->lanes]; ns = ts; }
+    else {
+        ts = (single || (tp.seq & 1)) ? h->s_trk : h->s_trk2;
+        // NMS launches of consecutive steps are independent.  With tracker launches on one stream they alternate
+        // between two streams (148 streams: 83 us per batch against 112); with two overlapping tracker grids a second
+        // NMS grid in flight would starve them of SMs (64 streams: 39.4 us against 37.2), so one stream then.
+        ns = (single && (tp.seq & 1)) ? h->s_trk2 : h->s_nms;
+    }
     PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
     sl.post.dbg_slot = tp.seq & 63;
