@@ -222,6 +222,63 @@ __host__ __device__ inline size_t nm_carve(unsigned char* base, int Ccap, int Kc
     return off;
 }
 
+
+// Layout as byte offsets, computed on the host and passed as a launch parameter (see tk_from_offsets in tracker.cu).
+__device__ __forceinline__ void nm_from_offsets(unsigned char* base, const SmemOffsets& o, NmSmem& s) {
+    s.tmask = reinterpret_cast<unsigned long long*>(base + o.off[0]);
+    s.acc = reinterpret_cast<unsigned long long*>(base + o.off[1]);
+    s.score = reinterpret_cast<float*>(base + o.off[2]);
+    s.recidx = reinterpret_cast<int*>(base + o.off[3]);
+    s.order = reinterpret_cast<int*>(base + o.off[4]);
+    s.kx = reinterpret_cast<float*>(base + o.off[5]);
+    s.ky = reinterpret_cast<float*>(base + o.off[6]);
+    s.vis = reinterpret_cast<unsigned*>(base + o.off[7]);
+    s.box = reinterpret_cast<float*>(base + o.off[8]);
+    s.area = reinterpret_cast<float*>(base + o.off[9]);
+    s.ext = reinterpret_cast<float*>(base + o.off[10]);
+    s.sup = reinterpret_cast<unsigned*>(base + o.off[11]);
+    s.keep = reinterpret_cast<int*>(base + o.off[12]);
+    s.tk = reinterpret_cast<int*>(base + o.off[13]);
+    s.misc = reinterpret_cast<int*>(base + o.off[14]);
+    s.l1_key = reinterpret_cast<unsigned*>(base + o.off[15]);
+    s.l2_key = reinterpret_cast<unsigned*>(base + o.off[16]);
+    s.terms = reinterpret_cast<float*>(base + o.off[17]);
+    s.sig = reinterpret_cast<float*>(base + o.off[18]);
+    s.tri = reinterpret_cast<unsigned short*>(base + o.off[19]);
+    s.have = reinterpret_cast<unsigned*>(base + o.off[20]);
+    s.fl = reinterpret_cast<int*>(base + o.off[21]);
+    s.spec = reinterpret_cast<unsigned long long*>(base + o.off[22]);
+}
+static SmemOffsets nm_offsets(int Ccap, int Kcap) {
+    SmemOffsets o{};
+    NmSmem t;
+    nm_carve(nullptr, Ccap, Kcap, &t);
+    o.off[0] = (unsigned)(uintptr_t)t.tmask;
+    o.off[1] = (unsigned)(uintptr_t)t.acc;
+    o.off[2] = (unsigned)(uintptr_t)t.score;
+    o.off[3] = (unsigned)(uintptr_t)t.recidx;
+    o.off[4] = (unsigned)(uintptr_t)t.order;
+    o.off[5] = (unsigned)(uintptr_t)t.kx;
+    o.off[6] = (unsigned)(uintptr_t)t.ky;
+    o.off[7] = (unsigned)(uintptr_t)t.vis;
+    o.off[8] = (unsigned)(uintptr_t)t.box;
+    o.off[9] = (unsigned)(uintptr_t)t.area;
+    o.off[10] = (unsigned)(uintptr_t)t.ext;
+    o.off[11] = (unsigned)(uintptr_t)t.sup;
+    o.off[12] = (unsigned)(uintptr_t)t.keep;
+    o.off[13] = (unsigned)(uintptr_t)t.tk;
+    o.off[14] = (unsigned)(uintptr_t)t.misc;
+    o.off[15] = (unsigned)(uintptr_t)t.l1_key;
+    o.off[16] = (unsigned)(uintptr_t)t.l2_key;
+    o.off[17] = (unsigned)(uintptr_t)t.terms;
+    o.off[18] = (unsigned)(uintptr_t)t.sig;
+    o.off[19] = (unsigned)(uintptr_t)t.tri;
+    o.off[20] = (unsigned)(uintptr_t)t.have;
+    o.off[21] = (unsigned)(uintptr_t)t.fl;
+    o.off[22] = (unsigned)(uintptr_t)t.spec;
+    return o;
+}
+
 size_t decode_nms_smem_bytes(int max_cand, int max_keep) { return nm_carve(nullptr, max_cand, max_keep, nullptr); }
 
 __device__ __forceinline__ bool is_sup(const unsigned* sup, int r) { return (sup[r >> 5] >> (r & 31)) & 1u; }
@@ -373,10 +430,10 @@ __device__ __forceinline__ void resolve_lists(const NmSmem& s, int CS, int t0, f
 
 __global__ void __launch_bounds__(NM_THREADS, 1)
 pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr,
-              PostBuffers out) {
+              PostBuffers out, SmemOffsets so) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmSmem s;
-    nm_carve(smem_raw, Ccap, Kcap, &s);
+    nm_from_offsets(smem_raw, so, s);
     const int CS = Ccap + 1;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -858,10 +915,10 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
 constexpr int NR_G = 8;
 
 __global__ void __launch_bounds__(NM_THREADS, 1)
-pb_nms_rounds_kernel(CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr, PostBuffers out) {
+pb_nms_rounds_kernel(CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr, PostBuffers out, SmemOffsets so) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmSmem s;
-    nm_carve(smem_raw, Ccap, Kcap, &s);
+    nm_from_offsets(smem_raw, so, s);
     const int CS = Ccap + 1;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1151,6 +1208,7 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
 cudaError_t launch_nms(const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream) {
     const size_t smem2 = decode_nms_smem_bytes(max_cand, max_keep);
+    const SmemOffsets so = nm_offsets(max_cand, max_keep);
     static size_t configured = 0;
     if (smem2 > configured) {
         cudaError_t e = cudaFuncSetAttribute(pb_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
@@ -1167,9 +1225,9 @@ cudaError_t launch_nms(const float* d_heads, int N, int sweep, int B, int max_ca
             if (e != cudaSuccess) return e;
             configured_r = smem2;
         }
-        pb_nms_rounds_kernel<<<B, NM_THREADS, smem2, stream>>>(cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out);
+        pb_nms_rounds_kernel<<<B, NM_THREADS, smem2, stream>>>(cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out, so);
     } else {
-        pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, sweep, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out);
+        pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, sweep, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out, so);
     }
     count_launch();
     return cudaGetLastError();

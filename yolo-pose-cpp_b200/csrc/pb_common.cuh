@@ -71,6 +71,9 @@ struct TrackBuffers {
     unsigned long long* dbg;   // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [0] begin, [1] state acquired, [2] end
 };
 
+// byte offsets of a kernel's shared-memory arrays, in the declaration order of its layout struct
+struct SmemOffsets { unsigned off[48]; };
+
 struct TrackParams {
     int B, T, Dm;
     float new_track_thresh;
@@ -79,6 +82,7 @@ struct TrackParams {
     int seq;             // sequence number of this launch; the CTA of stream b starts once seq_done[b] == seq - 1
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
     int cost_in_smem, det_in_smem, pred_in_smem, term_floats;
+    SmemOffsets so;      // shared-memory layout (tracker_plan)
 };
 
 struct DetSource {
@@ -117,7 +121,7 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
 cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 lazy, 2 deferred*/, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
-struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats; };
+struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats; SmemOffsets so; };
 TrackerPlan tracker_plan(int T, int Dm);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);
