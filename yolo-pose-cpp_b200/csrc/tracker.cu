@@ -477,9 +477,13 @@ __device__ __forceinline__ float center_iou(const float* a, const float* b) {   
     return (uni > 0) ? (inter / uni) : 0.0f;
 }
 
-template <int NTHREADS>
+// ALLSMEM: cost matrix, detections and predicted poses all live in shared memory (the plan's usual case); the
+// flags are then compile-time constants and every access to them is an LDS instead of a generic load.
+template <int NTHREADS, bool ALLSMEM>
 __global__ void __launch_bounds__(NTHREADS)
-pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
+pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
+    TrackParams P = P_;
+    if (ALLSMEM) { P.cost_in_smem = 1; P.det_in_smem = 1; P.pred_in_smem = 1; }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx c;
     tk_from_offsets(smem_raw, P.so, c.s);
@@ -1008,23 +1012,26 @@ cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, i
 
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream) {
-    static size_t configured[3] = {0, 0, 0};
-    const int v = plan.threads == 256 ? 0 : (plan.threads == 512 ? 1 : 2);
+    static size_t configured[4] = {0, 0, 0, 0};
+    const bool allsmem = plan.cost_in_smem && plan.det_in_smem && plan.pred_in_smem;
+    const int v = plan.threads == 256 ? 0 : (plan.threads == 512 ? 1 : (allsmem ? 3 : 2));
     if (plan.smem_bytes > configured[v]) {
         cudaError_t e;
         const int bytes = (int)plan.smem_bytes;
-        if (v == 0) e = cudaFuncSetAttribute(pb_tracker_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        else if (v == 1) e = cudaFuncSetAttribute(pb_tracker_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        else e = cudaFuncSetAttribute(pb_tracker_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (v == 0) e = cudaFuncSetAttribute(pb_tracker_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        else if (v == 1) e = cudaFuncSetAttribute(pb_tracker_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        else if (v == 2) e = cudaFuncSetAttribute(pb_tracker_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        else e = cudaFuncSetAttribute(pb_tracker_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured[v] = plan.smem_bytes;
     }
     p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
     p.term_floats = plan.term_floats;
     p.so = plan.so;
-    if (v == 0) pb_tracker_kernel<256><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
-    else if (v == 1) pb_tracker_kernel<512><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
-    else pb_tracker_kernel<1024><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
+    if (v == 0) pb_tracker_kernel<256, false><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
+    else if (v == 1) pb_tracker_kernel<512, false><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
+    else if (v == 2) pb_tracker_kernel<1024, false><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
+    else pb_tracker_kernel<1024, true><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, src);
     count_launch();
     return cudaGetLastError();
 }
