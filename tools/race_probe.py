@@ -5,12 +5,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import posebyte_b200 as pb
-B, F = int(os.environ.get("PB_B", "64")), 32
+B, F = int(os.environ.get("PB_B", "64")), int(os.environ.get("PB_PERIOD", "32"))
 NSTEP = int(os.environ.get("PB_STEPS", "400"))
-scfg = pb.synth_config(canvas=640, persons=20, period=32)
+CANVAS, PERSONS = int(os.environ.get("PB_CANVAS", "640")), int(os.environ.get("PB_PERSONS", "20"))
+kw = dict(max_tracks=int(os.environ.get("PB_T", "128")), max_detections=int(os.environ.get("PB_DM", "64")),
+          max_age=int(os.environ.get("PB_MAX_AGE", "10")), keypoint_fetch=int(os.environ.get("PB_KPF", "0")))
+scfg = pb.synth_config(canvas=CANVAS, persons=PERSONS, period=F, occlusion=int(os.environ.get("PB_OCC", "0")),
+                       clumps=int(os.environ.get("PB_CLUMPS", "0")), kp_drop_prob=0.15 if os.environ.get("PB_CLUMPS") else 0.05)
 d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()
-A = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
-Bp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+A = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, **kw)
+Bp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, **kw)
+print("config", dict(B=B, canvas=CANVAS, persons=PERSONS, period=F, steps=NSTEP, **kw))
 T, Dm = A.T, A.Dm
 slabs = [("poses", T * 51), ("vel", T * 34), ("scores", T), ("predicted", T * 51), ("tcent", T * 4), ("dcent", Dm * 4),
          ("cost", T * Dm), ("det_scores", Dm), ("states", T), ("ids", T), ("hits", T), ("ages", T), ("last_frame", T),
