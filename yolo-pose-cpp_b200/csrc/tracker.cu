@@ -534,6 +534,20 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
     if (tid < 32) s.misc[tid] = 0;
     if (tid < 20) s.acc[tid] = 0ull;
     if (tid < KP) s.sig[tid] = kSigmas[tid];
+    if (D > 0) {
+        // detection centres / areas (kernelComputeBboxCenters on the detections, :1180-1186) and the cleared gate
+        // words depend on this frame's detections only: done here, before the wait for the predecessor, by the
+        // upper half of the CTA (the lower half is still copying the records)
+        const int h = NT >> 1;
+#pragma unroll 1
+        for (int d = tid - h; d >= 0 && d < D; d += h) {
+            float area;
+            pose_box(src_pose + (size_t)d * POSE_F, &s.dcent[d * 4], &area);
+            s.darea[d] = area;
+        }
+#pragma unroll 1
+        for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = 0u; s.lgate[i] = 0u; }
+    }
     // ---- per-stream ordering across launches ----
     // Consecutive tracker launches run on two alternating CUDA streams and may overlap: the CTA of
     // stream b only needs the state ITS predecessor (the previous frame of the same video stream) left
@@ -640,7 +654,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
             }
         }
 #pragma unroll 1
-        for (int ai = tid; ai < na; ai += NT) {   // mean torso speed per active row (:287-298)
+        for (int ai = tid - (NT >> 1); ai >= 0 && ai < na; ai += (NT >> 1)) {   // mean torso speed per active row (:287-298), upper half of the CTA
             const int t = s.act_list[ai];
             const int torso[4] = {5, 6, 11, 12};
             float av = 0.0f;
@@ -651,16 +665,6 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
             }
             s.tav[t] = av * 0.25f;
         }
-    }
-    if (D > 0) {
-#pragma unroll 1
-        for (int d = tid; d < D; d += NT) {
-            float area;
-            pose_box(c.det + (size_t)d * POSE_F, &s.dcent[d * 4], &area);
-            s.darea[d] = area;
-        }
-#pragma unroll 1
-        for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = 0u; s.lgate[i] = 0u; }
     }
     __syncthreads();
     if (assoc12) {
