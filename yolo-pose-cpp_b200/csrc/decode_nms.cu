@@ -898,284 +898,6 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
 }
 
 // =======================================================================================
-// K2r: rank + NMS with a round-based sweep (complete records; the default for heads in HBM)
-// =======================================================================================
-// Same results as pb_nms_kernel's complete sweep, different schedule.  The greedy sweep
-// (gpu_postprocess.cu:209-242) only ever needs the pair test (:88-172) between a KEPT rank and a later
-// rank that is still alive, so instead of deciding 64 consecutive ranks per tile (2016 pair tests, most
-// of them between ranks that are already gone) every round takes the first NR_G ranks that are still
-// alive, k_0 < ... < k_{G-1}, and tests each of them against every later alive rank — one warp per
-// (k_g, 32 later ranks), the G ranks of the round among themselves included.  A pair the IoU rule and the
-// exact bounds of stage A leave undecided is finished by the same warp: lane = keypoint, 17 exponentials
-// at once, summed in keypoint order (the reference's order).  After one barrier every thread replays the
-// G x G outcome in rank order — k_g is kept iff no kept k_h, h < g, struck it — and the strike words of
-// the kept ranks are OR-ed into the dead set.  Work done for a k_g that turns out to be struck is the
-// price of deciding up to NR_G ranks per barrier pair instead of one.  ~20 kept of ~130 candidates:
-// 4-5 rounds; 85 kept of 650: ~15 rounds.
-constexpr int NR_G = 8;
-
-__global__ void __launch_bounds__(NM_THREADS, 1)
-pb_nms_rounds_kernel(CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr, PostBuffers out, SmemOffsets so) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    NmSmem s;
-    nm_from_offsets(smem_raw, so, s);
-    const int CS = Ccap + 1;
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = NM_THREADS / 32;
-    const float* recs = cs.records + (size_t)b * nseg * segcap * HEAD_ROWS;
-    const int* ancs = cs.anchors + (size_t)b * nseg * segcap;
-    float* o_pose = out.det_poses + (size_t)b * Kcap * POSE_F;
-    float* o_box = out.det_bboxes + (size_t)b * Kcap * 4;
-    float* o_score = out.det_scores + (size_t)b * Kcap;
-    int* o_slot = out.keep_slots + (size_t)b * Kcap;
-    int* o_anchor = out.keep_anchors + (size_t)b * Kcap;
-    int* segstart = reinterpret_cast<int*>(s.l1_key);          // [nseg + 1] (idle list storage)
-    unsigned* strike = s.l2_key;                               // [NR_G][W]
-    const int W = (Ccap + 31) / 32 + 2;
-
-    unsigned long long t_stamp = 0;
-    if (tid == 0) t_stamp = globaltimer_ns();
-    if (tid == 0 && out.dbg) out.dbg[((size_t)out.dbg_slot * gridDim.x + b) * 6 + 3] = t_stamp;
-    auto stamp = [&](int slot) {
-        if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
-    };
-
-    // ---------------- 0. candidate list = concatenation of the segment lists (anchor order) -----
-    if (tid < 16) { s.misc[tid] = 0; s.acc[tid] = 0ull; }
-    if (tid < KP) s.sig[tid] = kSigmas[tid];
-    for (int i = tid; i < W; i += NM_THREADS) s.sup[i] = 0u;
-    if (warp == 0) {
-        int run = 0;
-        for (int sg0 = 0; sg0 < nseg; sg0 += 32) {
-            const int sg = sg0 + lane;
-            const int n = (sg < nseg) ? cs.counts[b * nseg + sg] : 0;
-            int incl = n;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-            if (sg < nseg) segstart[sg] = run + incl - n;
-            run += __shfl_sync(FULL, incl, 31);
-        }
-        if (lane == 0) segstart[nseg] = run;
-    }
-    __syncthreads();
-    const int C = segstart[nseg] < Ccap ? segstart[nseg] : Ccap;
-    for (int c = tid; c < C; c += NM_THREADS) {
-        int sg = 0;
-        while (segstart[sg + 1] <= c) ++sg;                    // c < total: terminates inside the table
-        const int ri = sg * segcap + (c - segstart[sg]);
-        s.recidx[c] = ri;
-        s.score[c] = recs[(size_t)ri * HEAD_ROWS + 4];
-    }
-    __syncthreads();
-    stamp(0);
-
-    // ---------------- 1. rank by (score desc, slot asc)  (:178-203, R2) ----------------
-    for (int i = tid; i < C; i += NM_THREADS) {
-        const float si = s.score[i];
-        int rank = 0;
-        for (int j = 0; j < C; ++j) {
-            const float sj = s.score[j];
-            rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
-        }
-        s.order[rank] = i;
-    }
-    __syncthreads();
-    stamp(1);
-
-    // ---------------- 2. records -> shared memory SoA in rank order, one warp per record ----------------
-    // lane l holds record elements l and 32 + l (two coalesced loads, LB records in flight per warp):
-    // box = elements 0-3, keypoint k = elements 5+3k .. 7+3k; visibility bits (conf > 0.2) by ballot.
-    constexpr int LB = 4;
-    for (int r0 = warp; r0 < C; r0 += NWARPS * LB) {
-        float v0a[LB], v1a[LB];
-#pragma unroll
-        for (int u = 0; u < LB; ++u) {
-            const int r = r0 + u * NWARPS;
-            v0a[u] = 0.0f; v1a[u] = 0.0f;
-            if (r < C) {
-                const float* rec = recs + (size_t)s.recidx[s.order[r]] * HEAD_ROWS;
-                v0a[u] = rec[lane];
-                if (lane < HEAD_ROWS - 32) v1a[u] = rec[32 + lane];
-            }
-        }
-        const int e0 = lane - 5, e1 = lane + 27;               // element index - 5
-        const int k0 = e0 / 3, c0 = e0 - 3 * k0;               // valid for lane >= 5
-        const int k1 = e1 / 3, c1 = e1 - 3 * k1;               // valid for lane < 24
-        const bool has0 = lane >= 5, has1 = lane < HEAD_ROWS - 32;
-#pragma unroll 1
-        for (int u = 0; u < LB; ++u) {
-            const int r = r0 + u * NWARPS;
-            if (r >= C) break;                                  // warp-uniform
-            const float v0 = v0a[u], v1 = v1a[u];
-            if (lane < 4) s.box[lane * CS + r] = v0;
-            if (has0) { if (c0 == 0) s.kx[k0 * CS + r] = v0; else if (c0 == 1) s.ky[k0 * CS + r] = v0; }
-            if (has1) { if (c1 == 0) s.kx[k1 * CS + r] = v1; else if (c1 == 1) s.ky[k1 * CS + r] = v1; }
-            const unsigned b0 = __ballot_sync(FULL, has0 && c0 == 2 && v0 > 0.2f);     // bit 7 + 3k, k = 0..8
-            const unsigned b1 = __ballot_sync(FULL, has1 && c1 == 2 && v1 > 0.2f);     // bit 2 + 3(k - 9), k = 9..16
-            if (lane == 0) {
-                unsigned vis = 0u;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) vis |= ((b0 >> (7 + 3 * k)) & 1u) << k;
-#pragma unroll
-                for (int k = 9; k < KP; ++k) vis |= ((b1 >> (2 + 3 * (k - 9))) & 1u) << k;
-                s.vis[r] = vis;
-            }
-        }
-    }
-    __syncthreads();
-    for (int r = tid; r < C; r += NM_THREADS) {   // cx,cy,w,h -> corners (:66-69), area (:128), keypoint extents
-        const float cx = s.box[0 * CS + r], cy = s.box[1 * CS + r], w = s.box[2 * CS + r], h = s.box[3 * CS + r];
-        const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f, x2 = cx + w * 0.5f, y2 = cy + h * 0.5f;
-        s.box[0 * CS + r] = x1; s.box[1 * CS + r] = y1; s.box[2 * CS + r] = x2; s.box[3 * CS + r] = y2;
-        s.area[r] = (x2 - x1) * (y2 - y1);
-        float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
-#pragma unroll
-        for (int k = 1; k < KP; ++k) {
-            const float x = s.kx[k * CS + r], y = s.ky[k * CS + r];
-            lx = fminf(lx, x); hx = fmaxf(hx, x); ly = fminf(ly, y); hy = fmaxf(hy, y);
-        }
-        s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
-    }
-    // ---------------- 3. greedy suppression in rank order (:88-172 + :209-242), NR_G ranks per round ----------------
-    // control block in s.fl: [0, NR_G) the round's ranks k_g, [8] their number G, [9] kept so far
-    const int nwordsC = (C + 31) >> 5;
-    // warp 0: the next round's ranks = the first NR_G alive ranks >= cursor (lanes = words of the dead set)
-    auto next_list = [&](int cursor) {
-        int found = 0;
-        for (int wb = cursor >> 5; wb < nwordsC && found < NR_G; wb += 32) {
-            const int w = wb + lane;
-            unsigned alive = 0u;
-            if (w < nwordsC) {
-                alive = ~s.sup[w];
-                if (w == (cursor >> 5)) alive &= ~0u << (cursor & 31);
-                if (w == nwordsC - 1 && (C & 31)) alive &= (1u << (C & 31)) - 1u;
-            }
-            const int cnt = __popc(alive);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-            int ord = found + incl - cnt;
-            while (alive != 0u && ord < NR_G) { s.fl[ord++] = w * 32 + __ffs(alive) - 1; alive &= alive - 1u; }
-            found += __shfl_sync(FULL, incl, 31);
-        }
-        return found < NR_G ? found : NR_G;
-    };
-    if (warp == 0) {
-        const int G0 = next_list(0);
-        if (lane == 0) { s.fl[8] = G0; s.fl[9] = 0; }
-    }
-    __syncthreads();
-    stamp(2);
-    for (;;) {
-        const int G = s.fl[8];
-        if (G == 0) break;
-        const int k_first = s.fl[0], k_last = s.fl[G - 1];
-        const int w0 = (k_first + 1) >> 5, nW = nwordsC - w0;   // words that hold ranks > k_0
-        for (int it = warp; it < G * nW; it += NWARPS) {
-            const int g = it / nW, wd = w0 + (it - g * nW);
-            const int k = s.fl[g];
-            const int j = wd * 32 + lane;
-            int q = 0;
-            float iou = 0.0f, t8 = 0.0f;
-            unsigned vp = 0u;
-            if (j < C && j > k && !((s.sup[wd] >> lane) & 1u)) q = nms_stage_a2(s, CS, k, j, nms_thr, iou, t8, vp);
-            unsigned hit = __ballot_sync(FULL, q == 1);
-            unsigned und = __ballot_sync(FULL, q == 2);
-            if (und != 0u) {
-                // undecided pairs, one after the other with lane = keypoint: the exact per-keypoint bound
-                // (stage B) by ballot, then the 17 exponentials summed in keypoint order (:151-167)
-                float kxk = 0.0f, kyk = 0.0f, sg2 = 0.0f;
-                if (lane < KP) { kxk = s.kx[lane * CS + k]; kyk = s.ky[lane * CS + k]; sg2 = s.sig[lane]; }
-                do {
-                    const int l = __ffs(und) - 1;
-                    und &= und - 1u;
-                    const int jj = wd * 32 + l;
-                    const float iou_l = __shfl_sync(FULL, iou, l), t8_l = __shfl_sync(FULL, t8, l);
-                    const unsigned vp_l = __shfl_sync(FULL, vp, l);
-                    const int cnt = __popc(vp_l);
-                    const bool visb = lane < KP && ((vp_l >> lane) & 1u);
-                    float d2 = 0.0f, den = 1.0f;
-                    if (visb) {
-                        const float dx = kxk - s.kx[lane * CS + jj], dy = kyk - s.ky[lane * CS + jj];
-                        d2 = dx * dx + dy * dy;
-                        den = t8_l * sg2 * sg2;
-                    }
-                    const int m = __popc(__ballot_sync(FULL, visb && d2 < 3.003f * den));
-                    const float need = (iou_l > 0.2f) ? pb_min(nms_thr, 0.4f) : nms_thr;
-                    if (!((float)m + 0.05f * (float)(cnt - m) < (need - 0.002f) * (float)cnt)) {
-                        const float term = visb ? pb_expf(-d2 / den) : 0.0f;
-                        float sum = 0.0f;
-#pragma unroll
-                        for (int kp = 0; kp < KP; ++kp) sum += __shfl_sync(FULL, term, kp);
-                        const float oks = sum / (float)cnt;
-                        if ((oks > nms_thr) || (oks > 0.4f && iou_l > 0.2f)) hit |= 1u << l;
-                    }
-                } while (und != 0u);
-            }
-            if (lane == 0) strike[g * W + wd] = hit;
-        }
-        __syncthreads();
-        if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[10] += now - t_stamp; s.acc[3] += now - t_stamp; t_stamp = now; s.acc[12] += 1ull; }
-        if (warp == 0) {
-            // replay the round in rank order: k_g is kept iff no kept k_h, h < g, struck it
-            int kmine = 0, sm = 0;
-            if (lane < G) {
-                kmine = s.fl[lane];
-#pragma unroll
-                for (int h = 0; h < NR_G - 1; ++h)
-                    if (h < lane) sm |= (int)((strike[h * W + (kmine >> 5)] >> (kmine & 31)) & 1u) << h;
-            }
-            unsigned keptmask = 0u;
-            int nk = s.fl[9];
-#pragma unroll
-            for (int g = 0; g < NR_G; ++g) {
-                const int mg = __shfl_sync(FULL, sm, g), kg = __shfl_sync(FULL, kmine, g);
-                if (g < G && nk < Kcap && !((unsigned)mg & keptmask)) {     // :224 "num_keep < 256"
-                    keptmask |= 1u << g;
-                    if (lane == 0) s.keep[nk] = kg;
-                    ++nk;
-                }
-            }
-            for (int wd = w0 + lane; wd < nwordsC; wd += 32) {
-                unsigned mm = 0u;
-#pragma unroll
-                for (int g = 0; g < NR_G; ++g) if ((keptmask >> g) & 1u) mm |= strike[g * W + wd];
-                s.sup[wd] |= mm;
-            }
-            __syncwarp();
-            const int Gn = (nk < Kcap) ? next_list(k_last + 1) : 0;         // every alive rank up to k_{G-1} has been decided
-            if (lane == 0) { s.fl[8] = Gn; s.fl[9] = nk; }
-            if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[11] += now - t_stamp; s.acc[3] += now - t_stamp; t_stamp = now; }
-        }
-        __syncthreads();
-    }
-    const int nkeep = s.fl[9];
-    stamp(3);
-
-    // ---------------- 4. kept detections in score order ----------------
-    for (int it = tid; it < nkeep * POSE_F; it += NM_THREADS) {
-        const int k = it / POSE_F, e = it - k * POSE_F;
-        o_pose[it] = recs[(size_t)s.recidx[s.order[s.keep[k]]] * HEAD_ROWS + 5 + e];   // verbatim (:75-80)
-    }
-    for (int it = tid; it < nkeep * 4; it += NM_THREADS) {
-        const int k = it >> 2, e = it & 3;
-        o_box[it] = s.box[e * CS + s.keep[k]];
-    }
-    for (int k = tid; k < nkeep; k += NM_THREADS) {
-        const int slot = s.order[s.keep[k]];
-        o_score[k] = s.score[slot];
-        o_slot[k] = slot;
-        o_anchor[k] = ancs[s.recidx[slot]];
-    }
-    stamp(4);
-    if (tid == 0) { out.num_keep[b] = nkeep; out.num_cand[b] = C; s.acc[7] = 1ull; }
-    if (tid == 0 && out.dbg) out.dbg[((size_t)out.dbg_slot * gridDim.x + b) * 6 + 4] = globaltimer_ns();
-    __syncthreads();
-    if (tid < 16 && s.acc[tid] != 0ull) out.stage_ns[(size_t)b * 16 + tid] += s.acc[tid];
-}
-
-// =======================================================================================
 // launch
 // =======================================================================================
 DecodePlan decode_plan(int B, int N, int max_cand) {
@@ -1215,20 +937,7 @@ cudaError_t launch_nms(const float* d_heads, int N, int sweep, int B, int max_ca
         if (e != cudaSuccess) return e;
         configured = smem2;
     }
-    // complete records (sweep 0): PB_NMS_ROUNDS=1 selects the round-based kernel (experiment: 20.8 us against the
-    // tile sweep's 15.6 us per launch at 64 streams x 131 candidates)
-    static const bool rounds = getenv("PB_NMS_ROUNDS") != nullptr;
-    if (sweep == 0 && rounds) {
-        static size_t configured_r = 0;
-        if (smem2 > configured_r) {
-            cudaError_t e = cudaFuncSetAttribute(pb_nms_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            if (e != cudaSuccess) return e;
-            configured_r = smem2;
-        }
-        pb_nms_rounds_kernel<<<B, NM_THREADS, smem2, stream>>>(cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out, so);
-    } else {
-        pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, sweep, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out, so);
-    }
+    pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, sweep, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out, so);
     count_launch();
     return cudaGetLastError();
 }

@@ -681,9 +681,6 @@ int pb_get_post_stage_us(pb_handle_t h, double* out5) {
     PB_CUDA(cudaMemcpy(ns.data(), h->post.stage_ns, ns.size() * 8, cudaMemcpyDeviceToHost));
     double acc[16] = {0};
     for (int b = 0; b < B; ++b) for (int i = 0; i < 16; ++i) acc[i] += (double)ns[(size_t)b * 16 + i];
-    if (getenv("PB_DEBUG_STAGES") && acc[7] > 0)
-        fprintf(stderr, "[pb] nms per launch: pair phase %.2f us, replay phase %.2f us, rounds %.2f\n",
-                acc[10] / acc[7] / 1e3, acc[11] / acc[7] / 1e3, acc[12] / acc[7]);
     for (int i = 0; i < 5; ++i) out5[i] = acc[7] > 0 ? acc[i] / acc[7] / 1e3 : 0.0;
     return PB_OK;
 }
