@@ -578,14 +578,30 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
     __syncthreads();
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
-    int na_local = 0;
+    // State slabs -> shared memory, and in the same pass the ordered active list (ascending t).  The list position of
+    // a row is its rank among the active rows — the auction breaks ties between equal bids by it (lowest row,
+    // hungarian.cu:100) — so it must not depend on which warp gets here first: every warp derives the number of
+    // active rows in front of its block of 32 from ballots over the preceding blocks (read from the state slab
+    // itself, so no barrier is needed between the copy and the list) instead of from an atomic counter.
 #pragma unroll 1
-    for (int t = tid; t < T; t += NT) {
-        const int a = g_active[t];
-        s.active[t] = a; s.states[t] = g_states[t]; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
-        s.row[t] = -1;
-        s.rowbc[t] = g_dirty[t];            // predicted pose changed since its centre was derived (idle auction scratch)
-        na_local += (a == 1);
+    for (int t0 = c.warp * 32; t0 < T; t0 += NT) {
+        const int t = t0 + c.lane;
+        int a = 0, st = 0;
+        if (t < T) {
+            a = g_active[t]; st = g_states[t];
+            s.active[t] = a; s.states[t] = st; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
+            s.row[t] = -1;
+            s.rowbc[t] = g_dirty[t];        // predicted pose changed since its centre was derived (idle auction scratch)
+        }
+        int start = 0;
+#pragma unroll 1
+        for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, g_active[pb + c.lane] == 1));
+        const bool act = (a == 1);
+        const unsigned bm = __ballot_sync(FULLM, act);
+        const unsigned lm = __ballot_sync(FULLM, act && st == ST_LOST);
+        if (c.lane == 0 && lm) atomicAdd(&s.misc[6], __popc(lm));              // LOST rows at frame start (a sum: order-free)
+        if (act) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
+        if (c.lane == 0 && t0 + 32 >= T) s.misc[0] = start + __popc(bm);
     }
 #pragma unroll 1
     for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
@@ -595,25 +611,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
     c.pred = P.pred_in_smem ? s.pred : g_pred;
     if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
     __syncthreads();
-    {   // active count + ordered active list (ascending t).  The list position of a row is its rank among the
-        // active rows — the auction breaks ties between equal bids by it (lowest row, hungarian.cu:100) — so
-        // it must not depend on which warp gets here first: every warp derives the number of active rows
-        // in front of its block from ballots over the preceding blocks instead of from an atomic counter.
-        for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
-            int start = 0;
-            for (int pb = 0; pb < base; pb += 32) start += __popc(__ballot_sync(FULLM, s.active[pb + c.lane] == 1));
-            const int t = base + c.lane;
-            const bool a = (t < T) && (s.active[t] == 1);
-            const unsigned bm = __ballot_sync(FULLM, a);
-            const unsigned lm = __ballot_sync(FULLM, a && s.states[t] == ST_LOST);
-            if (c.lane == 0 && lm) atomicAdd(&s.misc[6], __popc(lm));          // LOST rows at frame start (a sum: order-free)
-            if (a) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
-            if (c.lane == 0 && base + 32 >= T) s.misc[0] = start + __popc(bm);
-        }
-    }
-    __syncthreads();
     const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
-    (void)na_local;
     stamp(0);
 
     // ---------------- predict (:1160-1175, kernel :102-138) ----------------
