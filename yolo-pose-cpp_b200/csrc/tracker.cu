@@ -281,12 +281,18 @@ __device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
 struct Ctx {
     TkSmem s;
     int T, D, Dw, tid, nthreads, lane, warp, nwarps;
+    unsigned magicD, magicW;   // ceil(2^32 / D), ceil(2^32 / words): i / D == __umulhi(i, magicD) for i * D < 2^32 (0: divisor 1)
     bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
     int term_floats;
     float* cost;        // shared or global, flat [t*D + d]
     const float* det;   // shared or global scratch [d*51]
     float* pred;        // shared or global (persistent) [t*51]
 };
+
+// i / d for the small non-negative indices of the stage loops, d fixed per frame: one multiply instead of the
+// ~25-instruction division sequence (magic = ceil(2^32 / d), exact while i * d < 2^32; d == 1 gives magic 0).
+__device__ __forceinline__ int fast_div(int i, unsigned magic) { return magic ? (int)__umulhi((unsigned)i, magic) : i; }
+__device__ __forceinline__ unsigned div_magic(int d) { return d > 1 ? (0xffffffffu / (unsigned)d + 1u) : 0u; }
 
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
 __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
@@ -297,7 +303,7 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
         float* cc = s.terms;
         const int D = c.D;
 #pragma unroll 1
-        for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = i / D; cc[i] = s.cost[s.act_list[ai] * D + (i - ai * D)]; }
+        for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = fast_div(i, c.magicD); cc[i] = s.cost[s.act_list[ai] * D + (i - ai * D)]; }
         __syncthreads();
         if (c.tid < 32) {
             unsigned* cb = reinterpret_cast<unsigned*>(s.colbid);
@@ -439,7 +445,7 @@ __device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
     const int D = c.D, Dw = c.Dw;
 #pragma unroll 1
     for (int i = c.tid; i < na * D; i += c.nthreads) {
-        const int ai = i / D, d = i - ai * D;
+        const int ai = fast_div(i, c.magicD), d = i - ai * D;
         const int t = s.act_list[ai];
         if ((gate[t * Dw + (d >> 5)] >> (d & 31)) & 1u)
             c.cost[(size_t)t * D + d] = torso_cost(c.pred + (size_t)t * POSE_F, c.det + (size_t)d * POSE_F);
@@ -523,6 +529,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
     int n_in = src.num[b];
     const int D = n_in < Dm ? (n_in < 0 ? 0 : n_in) : Dm;
     c.D = D; c.Dw = (Dm + 31) / 32;
+    c.magicD = div_magic(D); c.magicW = div_magic((D + 31) / 32);   // before the wait: off the chain of dependent frames
     const int Dw = c.Dw;
     const float* src_pose = src.poses + (size_t)b * src.stride * POSE_F;
     const float* src_score = src.scores + (size_t)b * src.stride;
@@ -671,7 +678,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
         const int words = (D + 31) / 32;
 #pragma unroll 1
         for (int i = c.warp; i < na * words; i += c.nwarps) {
-            const int ai = i / words, w = i - ai * words;
+            const int ai = fast_div(i, c.magicW), w = i - ai * words;
             const int t = s.act_list[ai];
             const int d = w * 32 + c.lane;
             const bool lost = (s.states[t] == ST_LOST);
