@@ -236,27 +236,6 @@ __device__ __forceinline__ bool gate_cell(const float* tc, const float* dc, floa
     return ratio < thr;
 }
 
-// kernelOKSWithGating cell (:360-424).
-__device__ __forceinline__ float oks_cost(const float* tp, const float* dp, float ta, float da, float vis) {
-    const float scale_sq = pb_max((da + ta) * 0.5f, 1000.0f);
-    const float t2 = 2.0f * scale_sq;
-    float sum = 0.0f;
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        if (dp[k * 3 + 2] > vis && tp[k * 3 + 2] > vis) {
-            const float dx = dp[k * 3] - tp[k * 3], dy = dp[k * 3 + 1] - tp[k * 3 + 1];
-            const float d2 = dx * dx + dy * dy;
-            const float sg = kSigmas[k] * 2.0f;
-            const float s2 = sg * sg;
-            sum += pb_expf(-d2 / (t2 * s2));
-            ++cnt;
-        }
-    }
-    const float oks = (cnt >= 3) ? (sum / (float)cnt) : 0.0f;
-    return 1.0f - oks;
-}
-
 // kernelTorsoOKS cell (:455-489).
 __device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
     const int torso[4] = {5, 6, 11, 12};
