@@ -456,8 +456,11 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     // ---------------- 0. candidate list = concatenation of the segment lists (anchor order) -----
     if (tid < 16) { s.misc[tid] = 0; s.acc[tid] = 0ull; }
     if (tid < KP) s.sig[tid] = kSigmas[tid];
+#pragma unroll 1
     for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.sup[i] = 0u;
+#pragma unroll 1
     for (int i = tid; i < Ccap; i += NM_THREADS) s.vis[i] = 0u;
+#pragma unroll 1
     for (int p = tid; p < 2016; p += NM_THREADS) {       // triangular pair table: row a holds the 63-a pairs (a, b > a)
         int a = (int)((127.0f - sqrtf(16129.0f - 8.0f * (float)p)) * 0.5f);    // first pair of row a is a*(127-a)/2
         if (a < 0) a = 0;
@@ -481,6 +484,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     }
     __syncthreads();
     const int C = s.misc[0];
+#pragma unroll 1
     for (int c = tid; c < C; c += NM_THREADS) {          // slot c -> record of its segment, and its score
         int sg = 0;
         while (segstart[sg + 1] <= c) ++sg;
@@ -522,12 +526,15 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     // kept earlier rank overlaps it by the complete rule, kept only when all kept earlier ranks were
     // tested against it.
     if (lazy) {
+#pragma unroll 1
     for (int it = tid; it < C * 4; it += NM_THREADS) {
         const int r = it >> 2, e = it & 3;
         s.box[e * CS + r] = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + e];
     }
+#pragma unroll 1
     for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.have[i] = 0u;
     __syncthreads();
+#pragma unroll 1
     for (int r = tid; r < C; r += NM_THREADS) {   // cx,cy,w,h -> corners (:66-69), area (:128)
         const float cx = s.box[0 * CS + r], cy = s.box[1 * CS + r], w = s.box[2 * CS + r], h = s.box[3 * CS + r];
         const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f, x2 = cx + w * 0.5f, y2 = cy + h * 0.5f;
@@ -539,6 +546,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         // "deferred" flavour: the decode kernel gathered complete records (head in HBM), so all keypoints
         // go to shared memory now and nothing is fetched later; what remains of the lazy sweep is its
         // evaluation ORDER — IoU strikes first, OKS tests only for the ranks still alive at their own tile.
+#pragma unroll 1
         for (int it = tid; it < C * POSE_F; it += NM_THREADS) {
             const int r = it / POSE_F, e = it - r * POSE_F;
             const float v = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + 5 + e];
@@ -548,6 +556,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
         }
         __syncthreads();
+#pragma unroll 1
         for (int r = tid; r < C; r += NM_THREADS) {
             float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
 #pragma unroll
@@ -557,6 +566,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             }
             s.ext[0 * CS + r] = lx; s.ext[1 * CS + r] = hx; s.ext[2 * CS + r] = ly; s.ext[3 * CS + r] = hy;
         }
+#pragma unroll 1
         for (int i = tid; i < (Ccap + 31) / 32 + 2; i += NM_THREADS) s.have[i] = 0xffffffffu;
         __syncthreads();
     }
@@ -564,6 +574,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     // fetch the keypoints of the ranks listed in s.fl[0..nf): head -> candidate record (for the output
     // stage) + shared memory (rank-indexed), then their keypoint extents
     auto fetch_list = [&](int nf) {
+#pragma unroll 1
         for (int it = tid; it < nf * POSE_F; it += NM_THREADS) {
             const int p = it / POSE_F, e = it - p * POSE_F;
             const int r = s.fl[p];
@@ -576,6 +587,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
         }
         __syncthreads();
+#pragma unroll 1
         for (int p = tid; p < nf; p += NM_THREADS) {
             const int r = s.fl[p];
             float lx = s.kx[r], hx = lx, ly = s.ky[r], hy = ly;
@@ -596,6 +608,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         const int pairs = nf * nk;
         for (int pbase = 0; pbase < pairs; pbase += NM_LIST) {
             const int pend = (pairs - pbase) < NM_LIST ? (pairs - pbase) : NM_LIST;
+#pragma unroll 1
             for (int p0 = 0; p0 < pend; p0 += NM_THREADS) {
                 int q = 0, i = 0, j = 0;
                 if (p0 + tid < pend) {
@@ -622,6 +635,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         const unsigned long long valid = (tl == 64) ? ~0ull : ((1ull << tl) - 1ull);
         const unsigned long long live = valid & ~((unsigned long long)s.sup[t0 >> 5] | ((unsigned long long)s.sup[(t0 >> 5) + 1] << 32));
         // (1) IoU mask among the live ranks of the tile
+#pragma unroll 1
         for (int p = tid; p < 2016; p += NM_THREADS) {
             const unsigned short ab = s.tri[p];
             const int a = ab >> 8, bb = ab & 0xff;
@@ -662,6 +676,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             fetch_list(na_);
             cross_tests(na_, nk0);                                    // (3) the added ranks against every earlier kept candidate
             // (4) pairs inside the fetched set that involve an added rank: IoU is in the mask already, the OKS rules may fire
+#pragma unroll 1
             for (int p0 = 0; p0 < 2016; p0 += NM_THREADS) {
                 const int p = p0 + tid;
                 int q = 0, a = 0, bb = 0;
@@ -726,6 +741,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             cross_tests(nf2, nk0);                                    // the newly fetched ranks against the earlier kept
             if (tid < 64) s.tmask[tid] = 0ull;
             __syncthreads();
+#pragma unroll 1
             for (int p0 = 0; p0 < 2016; p0 += NM_THREADS) {
                 const int p = p0 + tid;
                 int q = 0, a = 0, bb = 0;
@@ -763,6 +779,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         // (6) the tile's kept ranks strike the later ranks by the IoU rule (their OKS tests wait for the keypoints)
         const int j0 = t0 + 64, rem_n = C - j0;
         if (rem_n > 0 && ntk > 0) {
+#pragma unroll 1
             for (int p = tid; p < ntk * rem_n; p += NM_THREADS) {
                 const int ai = p / rem_n, j = j0 + (p - ai * rem_n);
                 if (!is_sup(s.sup, j) && pair_iou(s, CS, s.tk[ai], j) > nms_thr) atomicOr(&s.sup[j >> 5], 1u << (j & 31));
@@ -775,6 +792,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     } else {
 
     // ---------------- 2. records -> shared memory SoA in rank order ----------------
+#pragma unroll 1
     for (int it = tid; it < C * HEAD_ROWS; it += NM_THREADS) {
         const int r = it / HEAD_ROWS, row = it - r * HEAD_ROWS;
         const float v = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + row];
@@ -788,6 +806,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         }
     }
     __syncthreads();
+#pragma unroll 1
     for (int r = tid; r < C; r += NM_THREADS) {   // cx,cy,w,h -> corners (:66-69), area (:128), keypoint extents
         const float cx = s.box[0 * CS + r], cy = s.box[1 * CS + r], w = s.box[2 * CS + r], h = s.box[3 * CS + r];
         const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f, x2 = cx + w * 0.5f, y2 = cy + h * 0.5f;
@@ -810,6 +829,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
         if (tid == 0) { s.misc[3] = 0; s.misc[4] = 0; }
         __syncthreads();
         // (a) pairs inside the tile
+#pragma unroll 1
         for (int p0 = 0; p0 < 2016; p0 += NM_THREADS) {
             const int p = p0 + tid;
             int q = 0, a = 0, bb = 0;
@@ -851,6 +871,7 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
             const int pairs = ntk * rem_n;
             for (int pbase = 0; pbase < pairs; pbase += NM_LIST) {
                 const int pend = (pairs - pbase) < NM_LIST ? (pairs - pbase) : NM_LIST;
+#pragma unroll 1
                 for (int p0 = 0; p0 < pend; p0 += NM_THREADS) {
                     int q = 0, i = 0, j = 0;
                     if (p0 + tid < pend) {
@@ -876,14 +897,17 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     const int nkeep = s.misc[1];
 
     // ---------------- 4. kept detections in score order ----------------
+#pragma unroll 1
     for (int it = tid; it < nkeep * POSE_F; it += NM_THREADS) {
         const int k = it / POSE_F, e = it - k * POSE_F;
         o_pose[it] = recs[(size_t)s.recidx[s.order[s.keep[k]]] * HEAD_ROWS + 5 + e];   // verbatim (:75-80)
     }
+#pragma unroll 1
     for (int it = tid; it < nkeep * 4; it += NM_THREADS) {
         const int k = it >> 2, e = it & 3;
         o_box[it] = s.box[e * CS + s.keep[k]];
     }
+#pragma unroll 1
     for (int k = tid; k < nkeep; k += NM_THREADS) {
         const int slot = s.order[s.keep[k]];
         o_score[k] = s.score[slot];
