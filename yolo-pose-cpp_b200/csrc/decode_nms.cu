@@ -792,17 +792,38 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     } else {
 
     // ---------------- 2. records -> shared memory SoA in rank order ----------------
+    // eight independent loads per thread in flight (the stores to shared memory would otherwise keep the compiler
+    // from moving the next load above them: one L2 round trip per element)
+    {
+        const int total = C * HEAD_ROWS;
 #pragma unroll 1
-    for (int it = tid; it < C * HEAD_ROWS; it += NM_THREADS) {
-        const int r = it / HEAD_ROWS, row = it - r * HEAD_ROWS;
-        const float v = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + row];
-        if (row < 4) {
-            s.box[row * CS + r] = v;
-        } else if (row > 4) {
-            const int k = (row - 5) / 3, comp = (row - 5) - 3 * k;
-            if (comp == 0) s.kx[k * CS + r] = v;
-            else if (comp == 1) s.ky[k * CS + r] = v;
-            else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
+        for (int it0 = tid; it0 < total; it0 += NM_THREADS * 8) {
+            float v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int it = it0 + u * NM_THREADS;
+                v8[u] = 0.0f;
+                if (it < total) {
+                    const int r = it / HEAD_ROWS, row = it - r * HEAD_ROWS;
+                    v8[u] = recs[(size_t)s.recidx[s.order[r]] * HEAD_ROWS + row];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int it = it0 + u * NM_THREADS;
+                if (it < total) {
+                    const int r = it / HEAD_ROWS, row = it - r * HEAD_ROWS;
+                    const float v = v8[u];
+                    if (row < 4) {
+                        s.box[row * CS + r] = v;
+                    } else if (row > 4) {
+                        const int k = (row - 5) / 3, comp = (row - 5) - 3 * k;
+                        if (comp == 0) s.kx[k * CS + r] = v;
+                        else if (comp == 1) s.ky[k * CS + r] = v;
+                        else if (v > 0.2f) atomicOr(&s.vis[r], 1u << k);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
