@@ -535,14 +535,14 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
         for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = 0u; s.lgate[i] = 0u; }
     }
     // ---- per-stream ordering across launches ----
-    // Consecutive tracker launches run on two alternating CUDA streams and may overlap: the CTA of
-    // stream b only needs the state ITS predecessor (the previous frame of the same video stream) left
-    // behind, not the whole previous grid, so a video stream whose auction ran to the iteration limit
-    // delays nobody but itself.  Everything above reads this frame's detections only; from here on
-    // the CTA touches the stream's persistent state and waits for seq_done[b] == seq - 1 (release by the
-    // predecessor's last instruction, acquire here).  Launches are issued in sequence order and a launch
-    // is submitted only after the one before its predecessor has completed, so at most one grid can be
-    // waiting and the grid it waits for never waits itself; the time-out only guards against misuse.
+    // Consecutive tracker launches run on different CUDA streams (up to three "lanes", pb_api.cu) and may overlap:
+    // the CTA of stream b only needs the state ITS predecessor (the previous frame of the same video stream) left
+    // behind, not the whole previous grid, so a video stream whose auction ran to the iteration limit delays
+    // nobody but itself.  Everything above reads this frame's detections only; from here on the CTA touches the
+    // stream's persistent state and waits for seq_done[b] == seq - 1 (first release of the predecessor, acquire
+    // here).  Launches are issued in sequence order and the host keeps at most `lanes` of them in flight; the
+    // oldest never waits and the younger ones hold fewer SMs than the device has, so the oldest always runs to
+    // completion; the time-out only guards against misuse.
     if (tid == 0) {
         const int want = P.seq - 1;
         const int* flag = tb.seq_done + b;
