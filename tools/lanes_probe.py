@@ -11,7 +11,7 @@ d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()
 NSTEP = int(os.environ.get("PB_STEPS", "400"))
 def measure(lanes, depth, reps=3):
     os.environ["PB_LANES"] = str(lanes)
-    pp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=depth)
+    pp = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=depth, max_candidates=int(os.environ.get("PB_MAXCAND", "1024")))
     def run(n, f0):
         for i in range(f0, f0 + n): pp.step(d[i % F], i)
         pp.join()

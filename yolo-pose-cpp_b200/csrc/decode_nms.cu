@@ -162,7 +162,10 @@ pb_decode_gather_kernel(const float* __restrict__ heads, int N, int nseg, int gr
 // =======================================================================================
 // K2: rank + NMS
 // =======================================================================================
-constexpr int NM_THREADS = 1024;
+#ifndef PB_NM_THREADS
+#define PB_NM_THREADS 1024
+#endif
+constexpr int NM_THREADS = PB_NM_THREADS;
 constexpr int NM_LIST = 2048;                // undecided pairs per round (>= 64*63/2 = 2016)
 constexpr int NM_TERM_PAIRS = 128;           // pairs whose 17 terms are evaluated at once
 
@@ -428,7 +431,7 @@ __device__ __forceinline__ void resolve_lists(const NmSmem& s, int CS, int t0, f
     }
 }
 
-__global__ void __launch_bounds__(NM_THREADS, 1)
+__global__ void __launch_bounds__(NM_THREADS, NM_THREADS <= 512 ? 2 : 1)
 pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr,
               PostBuffers out, SmemOffsets so) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
