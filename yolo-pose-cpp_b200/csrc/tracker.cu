@@ -386,7 +386,7 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
                 const int t = key >> 16, d = key & 0xffff;
                 const float* tp = c.pred + (size_t)t * POSE_F + k * 3;
                 const float* dp = c.det + (size_t)d * POSE_F + k * 3;
-                float term = 0.0f;
+                float term = -0.0f;                  // marker of an invisible keypoint: adds nothing, is not counted (below)
                 if (dp[2] > vis && tp[2] > vis) {
                     const float scale_sq = pb_max((s.darea[d] + s.tarea[t]) * 0.5f, 1000.0f);
                     const float t2 = 2.0f * scale_sq;
@@ -403,13 +403,17 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
             for (int e = c.tid; e < ncur; e += c.nthreads) {
                 const int key = s.cell_list[cb + e];
                 const int t = key >> 16, d = key & 0xffff;
-                const float* tp = c.pred + (size_t)t * POSE_F;
-                const float* dp = c.det + (size_t)d * POSE_F;
+                // keypoint-ordered sum over the visible keypoints (:408-419).  An invisible keypoint left -0.0f: x + -0.0f
+                // is x for every x this sum can hold (it starts at +0 and its terms are >= +0 or NaN), and a visible
+                // term is never -0.0f, so neither the confidences nor a branch are needed here.
                 float sum = 0.0f;
                 int cnt = 0;
 #pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (dp[k * 3 + 2] > vis && tp[k * 3 + 2] > vis) { sum += s.terms[e * KP + k]; ++cnt; }
+                for (int k = 0; k < KP; ++k) {
+                    const float tv = s.terms[e * KP + k];
+                    sum += tv;
+                    cnt += (__float_as_uint(tv) != 0x80000000u) ? 1 : 0;
+                }
                 const float oks = (cnt >= 3) ? (sum / (float)cnt) : 0.0f;
                 c.cost[(size_t)t * D + d] = 1.0f - oks;
             }
