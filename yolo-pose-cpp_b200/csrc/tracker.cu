@@ -277,6 +277,20 @@ __device__ __forceinline__ unsigned div_magic(int d) { return d > 1 ? (0xfffffff
 __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
     TkSmem& s = c.s;
     if (c.warp_auction && na <= 32 && c.D <= 64) {
+        if (after_lock) {
+            // Rows matched in an earlier tier are locked (all their cells are 1e9, lock_pairs) and can never bid.  When
+            // that is every active row — the usual frame: everybody found its detection in tier 1 — the solve would
+            // clear the assignments and stop before its first iteration: do just that, without compacting the rows.
+            const bool may = c.lane < na && s.rowb[s.act_list[c.lane]] < 0;
+            if (__ballot_sync(FULLM, may) == 0u) {                 // the same in every warp
+#pragma unroll 1
+                for (int t = c.tid; t < c.T; t += c.nthreads) s.row[t] = -1;
+#pragma unroll 1
+                for (int d = c.tid; d < c.D; d += c.nthreads) s.col[d] = -1;
+                __syncthreads();
+                return;
+            }
+        }
         // compact the active rows (cc[i*D + d], i = position in act_list) into the term buffer, which is idle
         // between cost passes: the single-warp solve then reads a bidder's row with one conflict-free load
         float* cc = s.terms;
