@@ -788,10 +788,24 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
 
     // ---------------- new tracks (:1489-1526; R3/R4: ascending detection order) ------------
     if (D > 0) {
-        if (tid == 0) {
+        // which detections start a track?  (unmatched and score >= new_track_thresh.)  Usually none: warp 0 finds that out
+        // with ballots and the serial pass below, the pose copies and a barrier are skipped.
+        if (tid < 32) {
+            unsigned any = 0u;
+#pragma unroll 1
+            for (int base = 0; base < D; base += 32) {
+                const int d = base + c.lane;
+                bool q = false;
+                if (d < D) { s.slot_for_det[d] = -1; q = s.col[d] < 0 && !(s.dscore[d] < P.new_track_thresh); }
+                any |= __ballot_sync(FULLM, q);
+            }
+            if (c.lane == 0) s.misc[7] = any != 0u;
+        }
+        __syncthreads();
+        const bool newborn = s.misc[7] != 0;
+        if (newborn && tid == 0) {
             int hint = g_scal[1], next_id = g_scal[0];
             for (int d = 0; d < D; ++d) {
-                s.slot_for_det[d] = -1;
                 if (s.col[d] >= 0) continue;
                 if (s.dscore[d] < P.new_track_thresh) continue;
                 const int start = hint % T;
@@ -811,6 +825,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
             }
             g_scal[1] = hint; g_scal[0] = next_id;
         }
+        if (newborn) {
         __syncthreads();
 #pragma unroll 1
         for (int i = tid; i < D * POSE_F; i += NT) {
@@ -823,6 +838,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
             const int d = i / 34, e = i - d * 34;
             const int sl = s.slot_for_det[d];
             if (sl >= 0) g_vel[sl * 34 + e] = 0.0f;
+        }
         }
     }
     __syncthreads();
