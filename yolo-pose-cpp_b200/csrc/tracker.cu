@@ -846,8 +846,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
 
     // ---------------- de-duplication (:1528-1557; R5: sequential semantics) ----------------
     {
-        if (tid == 0) { s.misc[1] = 0; s.misc[2] = 0; }
-        __syncthreads();
+        // misc[1] (eligible count) and misc[2] (duplicate pairs) are still zero from the prologue: nothing else uses them
         for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {   // eligible list, ascending (ordered like act_list above)
             auto elig = [&](int t) { return (t < T) && s.active[t] == 1 && s.states[t] != ST_LOST && s.hits[t] >= P.min_hits; };
             int start = 0;
