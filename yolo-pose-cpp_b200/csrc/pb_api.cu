@@ -222,6 +222,11 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
         c.max_tracks < 1 || c.max_detections < 1) { pb_set_error("pb_create: sizes must be positive"); return PB_ERR_INVALID; }
     if (c.num_anchors > 65536) { pb_set_error("pb_create: num_anchors > 65536 unsupported"); return PB_ERR_UNSUPPORTED; }
     if (c.max_tracks >= 65536 || c.max_detections >= 65536) { pb_set_error("pb_create: max_tracks/max_detections too large"); return PB_ERR_UNSUPPORTED; }
+    if ((unsigned long long)c.max_tracks * (unsigned long long)c.max_detections * (unsigned long long)c.max_detections >= (1ull << 32)) {
+        // the tracker's stage loops divide cell indices by the frame's detection count with a 32-bit magic multiplier
+        pb_set_error("pb_create: max_tracks * max_detections^2 must stay below 2^32");
+        return PB_ERR_UNSUPPORTED;
+    }
     if (c.max_keep > c.max_candidates) { pb_set_error("pb_create: max_keep > max_candidates"); return PB_ERR_INVALID; }
     if (c.keypoint_fetch < 0 || c.keypoint_fetch > 3) { pb_set_error("pb_create: keypoint_fetch must be 0..3"); return PB_ERR_INVALID; }
     if (c.pipeline_depth < 1 || c.pipeline_depth > 8) { pb_set_error("pb_create: pipeline_depth must be 1..8"); return PB_ERR_INVALID; }
@@ -239,6 +244,14 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
         pb_set_error("pb_create: max_candidates=%d needs %zu B of shared memory (> %zu)", c.max_candidates,
                      decode_nms_smem_bytes(c.max_candidates, c.max_keep), (size_t)prop.sharedMemPerBlockOptin);
         return PB_ERR_UNSUPPORTED;
+    }
+    {
+        const TrackerPlan tp = tracker_plan(c.max_tracks, c.max_detections);
+        if (tp.smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+            pb_set_error("pb_create: max_tracks=%d / max_detections=%d need %zu B of shared memory (> %zu)", c.max_tracks,
+                         c.max_detections, tp.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
+            return PB_ERR_UNSUPPORTED;
+        }
     }
     if (const char* g = getenv("PB_L2_FETCH")) {       // experiment: 32 / 64 / 128 byte L2 fetch granularity
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
