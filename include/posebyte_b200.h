@@ -74,7 +74,10 @@ const char* pb_version(void);
 void pb_default_config(pb_config* cfg);
 
 /* GPUPostprocess::GPUPostprocess + GPUTracker::GPUTracker (gpu_postprocess.cu:319-347,
- * gpu_tracker.cu:925-1010).  Fails with PB_ERR_NO_DEVICE when no GPU is present. */
+ * gpu_tracker.cu:925-1010).  Fails with PB_ERR_NO_DEVICE when no GPU is present and with
+ * PB_ERR_UNSUPPORTED for sizes the kernels do not hold: num_anchors > 65536, max_tracks or
+ * max_detections >= 65536, max_tracks * max_detections^2 >= 2^32, candidate or track tables
+ * beyond the shared memory of an SM (pb_last_error() names the limit). */
 int pb_create(const pb_config* cfg, pb_handle_t* out);
 int pb_destroy(pb_handle_t h);
 /* Back to the freshly constructed state (all tracks dropped, ids restart at 1). */
