@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libposebyte_oracle.so")
+LIB_PATH = os.environ.get("PB_ORACLE_LIB") or os.path.join(_HERE, "_build", "libposebyte_oracle.so")
+BUILD_FLAGS = "portable build (-O2 -march=x86-64-v3)"
 
 TRACK_OUTPUT = np.dtype([("track_id", "<i4"), ("score", "<f4"), ("bbox", "<f4", (4,)),
                          ("keypoints", "<f4", (17, 3))])

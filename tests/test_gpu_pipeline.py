@@ -229,3 +229,42 @@ def test_long_run_equals_checker_and_pipelined_lanes(pb, orc, cuda):
         s1, s2 = trk.get_state(), a.get_state(b)
         for k in ("ids", "hits", "ages", "states", "active", "row_assign", "col_assign", "poses", "vel"):
             assert s1[k].tobytes() == s2[k].tobytes(), (b, k)
+
+
+@pytest.mark.gpu
+def test_config4_full_shape_128_streams_per_gpu(pb, orc, cuda):
+    """BASELINE config 4 per-GPU shape: 128 streams (1024 over 8 GPUs), max-age 30, occlusion gaps.  128 one-CTA-per-SM
+    tracker grids do not overlap (two would not fit 148 SMs), which is a different launch plan from the 64-stream
+    case: pipelined steps without synchronisation against a serial handle (all streams) and the checker (every 8th)."""
+    torch = cuda
+    B, F, STEPS = 128, 10, 60
+    scfg = pb.synth_config(canvas=640, persons=20, period=F, occlusion=1)
+    host = pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)
+    heads = torch.from_numpy(host).cuda()
+    serial = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=30)
+    piped = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=30, pipeline_depth=5)
+    for f in range(STEPS):
+        serial.step(heads[f % F], f); piped.step(heads[f % F], f)
+    piped.join(); torch.cuda.synchronize()
+    o1, c1 = serial.get_tracks_all(); o2, c2 = piped.get_tracks_all()
+    assert np.array_equal(c1, c2) and c1.sum() > 500 and o1.tobytes() == o2.tobytes()
+    assert serial.state_save()[24:] == piped.state_save()[24:]
+    for b in range(0, B, 8):
+        dets = [orc.postprocess(host[f, b]) for f in range(F)]
+        trk = orc.Tracker(max_age=30)
+        for f in range(STEPS):
+            trk.update(dets[f % F]["poses"], dets[f % F]["scores"], f)
+        assert trk.get_tracks().tobytes() == o2[b, :c2[b]].tobytes(), b
+        s1, s2 = trk.get_state(), piped.get_state(b)
+        for k in ("ids", "hits", "ages", "states", "active", "row_assign", "poses", "vel"):
+            assert s1[k].tobytes() == s2[k].tobytes(), (b, k)
+
+
+@pytest.mark.gpu
+def test_config3_crowd_16_streams(pb, orc, cuda):
+    """BASELINE config 3 at B = 16: 1280x1280 heads [16,56,33600], 100 persons in clumps, max_tracks 256 / max_detections 128."""
+    cfg = pb.synth_config(canvas=1280, persons=100, period=6, clumps=10, kp_drop_prob=0.15)
+    heads = pb.synth_heads(cfg, 0, 16, 0, 6, frame_major=True)
+    got, total = gpu_hashes(pb, cuda, heads, max_tracks=256, max_detections=128)
+    ref = orc.run_streams(heads, True, threads=8, max_tracks=256, max_detections=128)
+    assert np.array_equal(got, ref["hashes"]) and total == ref["tracks_total"] > 2000

@@ -126,3 +126,85 @@ def test_reset_and_determinism(pb, orc, cuda):
             acc.append(c.tobytes() + b"".join(o[b, : c[b]].tobytes() for b in range(2)))
         outs.append(b"".join(acc))
     assert outs[0] == outs[1]
+
+
+def feed_direct(pb, orc, torch, pipe, trks, frames_of_dets, check_every=1, T=None):
+    """frames_of_dets[f][b] = (poses [n,51], scores [n]); pb_tracker_update against the checker, state dumps and records."""
+    B = len(trks)
+    stride = max(max(len(s) for _, s in fr) for fr in frames_of_dets) or 1
+    lost_seen = recovered = 0
+    prev_states = [None] * B
+    for f, fr in enumerate(frames_of_dets):
+        poses = np.zeros((B, stride, 51), np.float32); scores = np.zeros((B, stride), np.float32); num = np.zeros(B, np.int32)
+        for b, (p, s) in enumerate(fr):
+            poses[b, : len(s)] = p; scores[b, : len(s)] = s; num[b] = len(s)
+        pipe.tracker_update(f, torch.from_numpy(poses).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(num).cuda(), stride)
+        torch.cuda.synchronize()
+        na = pipe.get_num_active()
+        for b, (p, s) in enumerate(fr):
+            assert trks[b].update(p, s, f) == na[b], (f, b)
+            rs = trks[b].get_state()
+            st = np.where(rs["active"] == 1, rs["states"], -1)
+            lost_seen += int((st == 2).sum())
+            if prev_states[b] is not None:
+                recovered += int(((prev_states[b] == 2) & (st == 1)).sum())
+            prev_states[b] = st
+            assert pipe.get_tracks(b).tobytes() == trks[b].get_tracks().tobytes(), (f, b)
+            if f % check_every == 0 or f == len(frames_of_dets) - 1:
+                bad = compare_state(pipe.get_state(b), rs, int(rs["scalars"][2]), T, f"f{f} b{b}")
+                assert not bad, bad
+    return lost_seen, recovered
+
+
+@pytest.mark.parametrize("gating", [1, 0])
+def test_config5_full_shape_lost_and_recovery(pb, orc, cuda, gating):
+    """BASELINE config 5 at its full shape: 512 tracks x 512 detections per stream, 8 streams, spatial gating on and
+    off, 36 frames with occlusion gaps and a short max-age so that CONFIRMED -> LOST, tier-3 recovery and removal
+    all happen at this size (multi-chunk cost passes, CTA-wide auction, cost matrix spilled to global memory)."""
+    T = Dm = 512
+    B, F = 8, 36
+    cfgs = [pb.synth_config(canvas=4096, persons=512, period=64, occlusion=(b & 1), max_speed=2.0, seed=0x5EEDB200 + b) for b in range(B)]
+    pipe = pb.Pipeline(num_streams=B, num_anchors=64, max_candidates=64, max_keep=64, max_tracks=T, max_detections=Dm, max_age=3,
+                       gating_enabled=gating)
+    trks = [orc.Tracker(max_tracks=T, max_detections=Dm, max_age=3, gating_enabled=gating) for _ in range(B)]
+    frames = []
+    for f in range(F):
+        fr = []
+        for b in range(B):
+            p, s = pb.synth_dets(cfgs[b], b, f)
+            o = np.argsort(-s, kind="stable")
+            fr.append((p[o], s[o]))
+        frames.append(fr)
+    lost, rec = feed_direct(pb, orc, cuda, pipe, trks, frames, check_every=6, T=T)
+    assert lost > 20 and rec > 5, (lost, rec)
+    assert max(len(pipe.get_tracks(b)) for b in range(B)) > 300
+
+
+def test_dedup_overflow_takes_the_ordered_recompute(pb, orc, cuda):
+    """More than 256 duplicate pairs in one frame (tracker.cu DUP_CAP): 40 near-identical detections start 40
+    tracks (min_hits 1) whose predicted boxes all overlap in the next frame: 780 pairs, resolved with the
+    sequential semantics of rule R5 by the overflow branch."""
+    rng = np.random.default_rng(3)
+    cfg = pb.synth_config(canvas=640, persons=1, period=8)
+    base, _ = pb.synth_dets(cfg, 0, 0)
+    n = 40
+    frames = []
+    for f in range(5):
+        p = np.repeat(base[:1], n, 0).copy()
+        p[:, 0::3] += rng.normal(0, 0.4, (n, 17)).astype(np.float32) + f
+        p[:, 1::3] += rng.normal(0, 0.4, (n, 17)).astype(np.float32)
+        s = np.sort(rng.uniform(0.5, 0.9, n).astype(np.float32))[::-1].copy()
+        frames.append([(p, s), (p[:3], s[:3])])
+    pipe = pb.Pipeline(num_streams=2, max_tracks=64, max_detections=48, min_hits=1)
+    trks = [orc.Tracker(max_tracks=64, max_detections=48, min_hits=1) for _ in range(2)]
+    feed_direct(pb, orc, cuda, pipe, trks, frames, T=64)
+    st = trks[0].get_state()
+    assert 1 <= int(st["active"].sum()) < n              # the duplicates were removed
+
+
+def test_cell_list_clamp_is_unreachable(pb, cuda):
+    """CELL_LIST_CAP (4096 gated cells per chunk of active rows) can only be exceeded by a single row with more than
+    4096 detections; such a table does not fit the tracker's shared memory and pb_create refuses it."""
+    with pytest.raises(pb.PbError) as e:
+        pb.Pipeline(num_streams=1, max_tracks=4, max_detections=4097)
+    assert e.value.status == pb.PB_ERR_UNSUPPORTED

@@ -164,6 +164,40 @@ def _ptr(x):
     return x.data_ptr()          # torch.Tensor
 
 
+def _dev_f32(x, numel: int, device: int, what: str):
+    """Address of a device buffer of at least `numel` contiguous float32 elements on `device`.  Torch tensors are
+    checked (dtype, device, contiguity, size); a raw int address is taken on trust, as in C."""
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray) or not hasattr(x, "data_ptr"):
+        raise ValueError(f"{what}: expected a CUDA tensor (or a raw device address), got {type(x).__name__}")
+    import torch
+    if x.dtype != torch.float32:
+        raise ValueError(f"{what}: dtype {x.dtype}, expected float32")
+    if not x.is_cuda or x.device.index != device:
+        raise ValueError(f"{what}: tensor on {x.device}, the handle lives on cuda:{device}")
+    if not x.is_contiguous():
+        raise ValueError(f"{what}: tensor is not contiguous")
+    if x.numel() < numel:
+        raise ValueError(f"{what}: {x.numel()} elements, at least {numel} needed")
+    return x.data_ptr()
+
+
+def _host_array(x, dtype, nbytes: int, what: str, writable=False):
+    if not isinstance(x, np.ndarray):
+        raise ValueError(f"{what}: expected a numpy array")
+    dtypes = dtype if isinstance(dtype, tuple) else (dtype,)
+    if not any(x.dtype == np.dtype(d) for d in dtypes):
+        raise ValueError(f"{what}: dtype {x.dtype}, expected {' or '.join(str(np.dtype(d)) for d in dtypes)}")
+    if not x.flags.c_contiguous:
+        raise ValueError(f"{what}: array is not C-contiguous")
+    if x.nbytes < nbytes:
+        raise ValueError(f"{what}: {x.nbytes} bytes, at least {nbytes} needed")
+    if writable and not x.flags.writeable:
+        raise ValueError(f"{what}: array is read-only")
+    return x.ctypes.data
+
+
 def _stream_ptr(stream):
     if stream is None:
         import torch
@@ -183,6 +217,7 @@ class Pipeline:
         self.B = self.cfg.num_streams
         self.T = self.cfg.max_tracks
         self.Dm = self.cfg.max_detections
+        self._head_numel = self.B * 56 * self.cfg.num_anchors
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -196,14 +231,22 @@ class Pipeline:
 
     # -- the path ---------------------------------------------------------------------
     def postprocess(self, heads, conf=0.30, nms=0.65, stream=None):
-        check(lib().pb_postprocess(self._h, _ptr(heads), conf, nms, _stream_ptr(stream)))
+        check(lib().pb_postprocess(self._h, _dev_f32(heads, self._head_numel, self.cfg.device, "heads"), conf, nms, _stream_ptr(stream)))
 
     def tracker_update(self, frame_id, det_poses=None, det_scores=None, num_dets=None, det_stride=0, stream=None):
+        if det_poses is not None and not isinstance(det_poses, int):
+            dev = self.cfg.device
+            _dev_f32(det_poses, self.B * det_stride * 51, dev, "det_poses")
+            _dev_f32(det_scores, self.B * det_stride, dev, "det_scores")
+            import torch
+            if not (hasattr(num_dets, "dtype") and num_dets.dtype == torch.int32 and num_dets.is_cuda and num_dets.device.index == dev
+                    and num_dets.is_contiguous() and num_dets.numel() >= self.B):
+                raise ValueError("num_dets: expected a contiguous int32 CUDA tensor with one count per stream")
         check(lib().pb_tracker_update(self._h, _ptr(det_poses), _ptr(det_scores), _ptr(num_dets), det_stride,
                                       frame_id, _stream_ptr(stream)))
 
     def step(self, heads, frame_id, conf=0.30, nms=0.65, stream=None):
-        check(lib().pb_step(self._h, _ptr(heads), conf, nms, frame_id, _stream_ptr(stream)))
+        check(lib().pb_step(self._h, _dev_f32(heads, self._head_numel, self.cfg.device, "heads"), conf, nms, frame_id, _stream_ptr(stream)))
 
     def join(self, stream=None):
         """Make `stream` wait for work a pipelined step left on the internal streams."""
@@ -217,13 +260,19 @@ class Pipeline:
             out = np.zeros((self.B, self.Dm), dtype=TRACK_OUTPUT)
         if counts is None:
             counts = np.zeros(self.B, dtype=np.int32)
-        check(lib().pb_step_host(self._h, heads_np.ctypes.data, conf, nms, frame_id, out.ctypes.data, counts.ctypes.data))
+        hp = _host_array(heads_np, np.float32, self._head_numel * 4, "heads")
+        op = _host_array(out, (TRACK_OUTPUT, np.uint8), self.B * self.Dm * 228, "out", writable=True)
+        cp = _host_array(counts, np.int32, self.B * 4, "counts", writable=True)
+        check(lib().pb_step_host(self._h, hp, conf, nms, frame_id, op, cp))
         return out, counts
 
     def submit_host(self, heads_np: np.ndarray, frame_id, out: np.ndarray, counts: np.ndarray, conf=0.30, nms=0.65):
         """Asynchronous step_host: all three arrays must be views of page-locked memory and stay
         untouched until wait() returns."""
-        check(lib().pb_submit_host(self._h, heads_np.ctypes.data, conf, nms, frame_id, out.ctypes.data, counts.ctypes.data))
+        hp = _host_array(heads_np, np.float32, self._head_numel * 4, "heads")
+        op = _host_array(out, (TRACK_OUTPUT, np.uint8), self.B * self.Dm * 228, "out", writable=True)
+        cp = _host_array(counts, np.int32, self.B * 4, "counts", writable=True)
+        check(lib().pb_submit_host(self._h, hp, conf, nms, frame_id, op, cp))
 
     def wait(self):
         check(lib().pb_wait(self._h))
@@ -245,6 +294,10 @@ class Pipeline:
         return buf.tobytes()
 
     def state_load(self, blob: bytes):
+        n = C.c_size_t(0)
+        check(lib().pb_state_size(self._h, C.byref(n)))
+        if len(blob) < n.value:
+            raise PbError(PB_ERR_INVALID, f"state_load: blob of {len(blob)} bytes, the handle's snapshots have {n.value}")
         buf = np.frombuffer(blob, np.uint8)
         check(lib().pb_state_load(self._h, buf.ctypes.data, buf.size))
 

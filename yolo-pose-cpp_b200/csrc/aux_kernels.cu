@@ -348,8 +348,7 @@ void launchPoseNMS(const float* poses, const float* scores, const float* sigmas,
                    float score_threshold, pb_stream_t stream) {
     if (num_detections <= 0) return;
     const size_t smem = (size_t)num_detections * 4 + (size_t)((num_detections + 31) / 32) * 4 + 16;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(pose_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem((const void*)pose_nms_kernel, smem);
     pose_nms_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(poses, scores, sigmas, keep, num_detections,
                                                            num_keypoints, oks_threshold, score_threshold);
     count_launch();
@@ -361,8 +360,8 @@ int pb_nms_legacy(const void* d_dets, const int* d_offsets, int num_images, int 
     if (num_images <= 0) return PB_OK;
     if (max_per_image <= 0 || max_per_image > 16384) { pb_set_error("pb_nms_legacy: max_per_image out of range"); return PB_ERR_INVALID; }
     const size_t smem = (size_t)max_per_image * 4 + (size_t)((max_per_image + 31) / 32) * 4 + 16;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nms_legacy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)nms_legacy_kernel, smem);
         if (e != cudaSuccess) { pb_set_error("pb_nms_legacy: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     }
     nms_legacy_kernel<<<num_images, 512, smem, (cudaStream_t)stream>>>(
@@ -383,8 +382,8 @@ int pb_auction_solve(const float* d_cost, int batch, int num_rows, int num_cols,
     const int stage_cost = (staged <= 96 * 1024 && num_cols <= 65535) ? 1 : 0;
     if (stage_cost) smem = staged;
     if (smem > 200 * 1024) { pb_set_error("pb_auction_solve: problem too large"); return PB_ERR_UNSUPPORTED; }
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(auction_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)auction_batch_kernel, smem);
         if (e != cudaSuccess) { pb_set_error("pb_auction_solve: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
     }
     auction_batch_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(d_cost, num_rows, num_cols, d_row_assign,

@@ -499,14 +499,42 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     stamp(0);
 
     // ---------------- 1. rank by (score desc, slot asc)  (:178-203, R2) ----------------
-    for (int i = tid; i < C; i += NM_THREADS) {
-        const float si = s.score[i];
-        int rank = 0;
-        for (int j = 0; j < C; ++j) {
-            const float sj = s.score[j];
-            rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    // NaN confidences pass the filter (:51) and the reference's insertion sort never moves anything across one
+    // (`score < key` is false on either side): a NaN stays at its slot index and the runs between NaNs are sorted
+    // on their own.  The all-pairs count below is that order only without NaNs, so their presence selects the
+    // segmented count (still a permutation: rank = slots of earlier segments + rank inside the own segment).
+    {
+        bool nan_here = false;
+        for (int i = tid; i < C; i += NM_THREADS) nan_here |= (s.score[i] != s.score[i]);
+        if (nan_here) s.misc[8] = 1;                 // misc[] was cleared above, before two barriers
+    }
+    __syncthreads();
+    if (s.misc[8] == 0) {
+        for (int i = tid; i < C; i += NM_THREADS) {
+            const float si = s.score[i];
+            int rank = 0;
+            for (int j = 0; j < C; ++j) {
+                const float sj = s.score[j];
+                rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+            }
+            s.order[rank] = i;
         }
-        s.order[rank] = i;
+    } else {
+        for (int i = tid; i < C; i += NM_THREADS) {
+            const float si = s.score[i];
+            int rank = i;
+            if (si == si) {
+                int lo = i, hi = i;                  // the NaN-free run [lo, hi] around slot i
+                while (lo > 0 && s.score[lo - 1] == s.score[lo - 1]) --lo;
+                while (hi + 1 < C && s.score[hi + 1] == s.score[hi + 1]) ++hi;
+                rank = lo;
+                for (int j = lo; j <= hi; ++j) {
+                    const float sj = s.score[j];
+                    rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+                }
+            }
+            s.order[rank] = i;
+        }
     }
     __syncthreads();
     stamp(1);
@@ -979,11 +1007,9 @@ cudaError_t launch_nms(const float* d_heads, int N, int sweep, int B, int max_ca
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream) {
     const size_t smem2 = decode_nms_smem_bytes(max_cand, max_keep);
     const SmemOffsets so = nm_offsets(max_cand, max_keep);
-    static size_t configured = 0;
-    if (smem2 > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pb_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    {
+        const cudaError_t e = ensure_dyn_smem((const void*)pb_nms_kernel, smem2);
         if (e != cudaSuccess) return e;
-        configured = smem2;
     }
     pb_nms_kernel<<<B, NM_THREADS, smem2, stream>>>(d_heads, N, sweep, cs, plan.nseg, plan.segcap, max_cand, max_keep, nms_thr, out, so);
     count_launch();

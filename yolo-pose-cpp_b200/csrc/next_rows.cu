@@ -337,11 +337,9 @@ int pb_greedy_match(const float* d_cost, int batch, int num_rows, int num_cols, 
     if ((long long)num_rows * num_cols > 0x7fffffffLL) { pb_set_error("pb_greedy_match: matrix too large"); return PB_ERR_UNSUPPORTED; }
     const size_t smem = (size_t)(num_rows + num_cols + 2) * 4 + 8 * 8 + 16;
     if (smem > 200 * 1024) { pb_set_error("pb_greedy_match: rows + cols too large for shared memory"); return PB_ERR_UNSUPPORTED; }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pb::greedy_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = pb::ensure_dyn_smem((const void*)pb::greedy_match_kernel, smem);
         if (e != cudaSuccess) { pb_set_error("pb_greedy_match: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
-        configured = smem;
     }
     pb::greedy_match_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(d_cost, num_rows, num_cols, threshold, d_row_matched);
     pb::count_launch(1);
@@ -356,11 +354,9 @@ int pb_assign_legacy(const float* d_cost, int batch, int num_rows, int num_cols,
     if (!d_cost || !d_row_assign || !d_col_assign) { pb_set_error("pb_assign_legacy: bad argument"); return PB_ERR_INVALID; }
     const size_t smem = (size_t)num_cols * 16 + (size_t)num_rows * 4 + 16;
     if (smem > 200 * 1024) { pb_set_error("pb_assign_legacy: problem too large"); return PB_ERR_UNSUPPORTED; }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pb::assign_legacy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = pb::ensure_dyn_smem((const void*)pb::assign_legacy_kernel, smem);
         if (e != cudaSuccess) { pb_set_error("pb_assign_legacy: %s", cudaGetErrorString(e)); return PB_ERR_CUDA; }
-        configured = smem;
     }
     pb::assign_legacy_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(d_cost, num_rows, num_cols, threshold, d_row_assign, d_col_assign, d_count);
     pb::count_launch(1);

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <vector>
@@ -18,6 +20,21 @@
 namespace pb {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[{func, dev}];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
 }  // namespace pb
 
 static thread_local char g_err[512] = "";
@@ -82,6 +99,18 @@ static int prof_event(pb_handle_st* h) {
     return (int)h->ev_used++;
 }
 
+// Every entry point that takes a handle runs on the handle's device and gives the caller's current device back.
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DevGuard() { if (switched) cudaSetDevice(prev); }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
+
 #define PB_CUDA(call)                                                                         \
     do { cudaError_t e_ = (call);                                                             \
          if (e_ != cudaSuccess) { pb_set_error("%s failed: %s", #call, cudaGetErrorString(e_)); return PB_ERR_CUDA; } } while (0)
@@ -117,6 +146,8 @@ static int for_each_state_slab(pb_handle_st* h, F&& f) {
 }
 
 extern "C" {
+
+static int check_order_flag(pb_handle_st* h);
 
 const char* pb_last_error(void) { return g_err; }
 const char* pb_version(void) { return "posebyte-b200 0.1 (sm_100a)"; }
@@ -236,7 +267,8 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
         pb_set_error("pb_create: CUDA device %d not available (this library has no CPU path)", c.device);
         return PB_ERR_NO_DEVICE;
     }
-    PB_CUDA(cudaSetDevice(c.device));
+    DevGuard dev_guard(c.device);           // the caller's current device is restored on return
+    { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != c.device) { pb_set_error("pb_create: cannot select device %d", c.device); return PB_ERR_CUDA; } }
     cudaDeviceProp prop{};
     PB_CUDA(cudaGetDeviceProperties(&prop, c.device));
     if (prop.major < 10) { pb_set_error("pb_create: device sm_%d%d, built for sm_100a only", prop.major, prop.minor); return PB_ERR_NO_DEVICE; }
@@ -279,7 +311,7 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
 
 int pb_destroy(pb_handle_t h) {
     if (!h) return PB_OK;
-    cudaSetDevice(h->cfg.device);
+    DevGuard dev_guard(h->cfg.device);
     cudaDeviceSynchronize();          // pipelined steps may still be running on the internal streams
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_stage) cudaFree(h->d_stage);
@@ -311,6 +343,7 @@ static int join_on(pb_handle_st* h, cudaStream_t stream) {
 
 int pb_reset(pb_handle_t h, pb_stream_t stream) {
     if (!h) { pb_set_error("pb_reset: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_TRY(join_on(h, (cudaStream_t)stream));
     PB_CUDA(launch_tracker_reset(h->trk, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, h->trk_seq, (cudaStream_t)stream));
     h->frames = 0;
@@ -319,11 +352,13 @@ int pb_reset(pb_handle_t h, pb_stream_t stream) {
 
 int pb_join(pb_handle_t h, pb_stream_t stream) {
     if (!h) { pb_set_error("pb_join: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     return join_on(h, (cudaStream_t)stream);
 }
 
 int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, pb_stream_t stream) {
     if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
     PB_TRY(join_on(h, (cudaStream_t)stream));
     int e0 = -1, e1 = -1, em = -1;
@@ -344,7 +379,7 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
 static TrackParams track_params(pb_handle_st* h, int frame_id) {
     const pb_config& c = h->cfg;
     TrackParams p{};
-    p.seq = ++h->trk_seq;
+    p.seq = h->trk_seq + 1;                 // committed (h->trk_seq = p.seq) once the launch has succeeded: no gap on failure
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
@@ -354,6 +389,7 @@ static TrackParams track_params(pb_handle_st* h, int frame_id) {
 int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_det_scores,
                       const int* d_num_dets, int det_stride, int frame_id, pb_stream_t stream) {
     if (!h) { pb_set_error("pb_tracker_update: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
     PB_TRY(join_on(h, (cudaStream_t)stream));
     DetSource src;
@@ -370,6 +406,7 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
     int e0 = -1, e1 = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
     PB_CUDA(launch_tracker(h->trk, p, src, h->plan, (cudaStream_t)stream));
+    h->trk_seq = p.seq;
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
         h->ev_track.push_back({e0, e1});
@@ -434,6 +471,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     if (ns != ts) PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_nms, 0));
     DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
     PB_CUDA(launch_tracker(h->trk, tp, src, h->plan, ts));
+    h->trk_seq = tp.seq;
     PB_TRY(enqueue_readback(h, ts));
     PB_CUDA(cudaEventRecord(sl.ev_trk, ts));
     h->last_trk_stream = ts;
@@ -447,6 +485,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
 
 int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int frame_id, pb_stream_t stream) {
     if (!h || !d_heads) { pb_set_error("pb_step: null argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     if (h->cfg.pipeline_depth > 1 && !h->profiling) return step_pipelined(h, d_heads, conf, nms, frame_id, (cudaStream_t)stream);
     PB_TRY(pb_postprocess(h, d_heads, conf, nms, stream));
     PB_TRY(pb_tracker_update(h, nullptr, nullptr, nullptr, 0, frame_id, stream));
@@ -456,6 +495,7 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int fram
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                  void* h_tracks, int* h_counts) {
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_step_host: null argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
     const size_t B = c.num_streams, Dm = c.max_detections;
     const size_t head_bytes = B * HEAD_ROWS * (size_t)c.num_anchors * sizeof(float);
@@ -499,13 +539,14 @@ int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int
         memcpy(h_counts, h->h_cnt_pinned, B * sizeof(int));
         memcpy(h_tracks, h->h_out_pinned, B * Dm * 228);
     }
-    return PB_OK;
+    return check_order_flag(h);
 }
 
 // ---- SURVEY.md §8f rows f2 / f4 ---------------------------------------------------------------
 
 int pb_set_output_transform(pb_handle_t h, const float* h_xform) {
     if (!h) { pb_set_error("pb_set_output_transform: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     if (!h_xform) { h->trk.out_xform = nullptr; return PB_OK; }
     const size_t n = (size_t)h->cfg.num_streams * 4;
@@ -517,6 +558,7 @@ int pb_set_output_transform(pb_handle_t h, const float* h_xform) {
 
 int pb_state_size(pb_handle_t h, size_t* bytes) {
     if (!h || !bytes) { pb_set_error("pb_state_size: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     size_t total = sizeof(SnapHeader);
     PB_TRY(for_each_state_slab(h, [&](void*, size_t n) -> int { total += n; return PB_OK; }));
     *bytes = total;
@@ -526,8 +568,10 @@ int pb_state_size(pb_handle_t h, size_t* bytes) {
 int pb_state_save(pb_handle_t h, void* h_blob, size_t capacity) {
     size_t need = 0;
     PB_TRY(pb_state_size(h, &need));
+    DevGuard dev_guard(h->cfg.device);
     if (!h_blob || capacity < need) { pb_set_error("pb_state_save: blob too small (%zu < %zu)", capacity, need); return PB_ERR_INVALID; }
     PB_CUDA(cudaDeviceSynchronize());
+    PB_TRY(check_order_flag(h));
     SnapHeader hd{kSnapMagic, 1u, h->cfg.num_streams, h->cfg.max_tracks, h->cfg.max_detections, h->frames};
     unsigned char* p = static_cast<unsigned char*>(h_blob);
     memcpy(p, &hd, sizeof(hd)); p += sizeof(hd);
@@ -541,6 +585,7 @@ int pb_state_save(pb_handle_t h, void* h_blob, size_t capacity) {
 int pb_state_load(pb_handle_t h, const void* h_blob, size_t bytes) {
     size_t need = 0;
     PB_TRY(pb_state_size(h, &need));
+    DevGuard dev_guard(h->cfg.device);
     if (!h_blob || bytes < need) { pb_set_error("pb_state_load: blob too small"); return PB_ERR_INVALID; }
     SnapHeader hd{};
     memcpy(&hd, h_blob, sizeof(hd));
@@ -562,6 +607,7 @@ int pb_state_load(pb_handle_t h, const void* h_blob, size_t bytes) {
 int pb_submit_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                    void* h_tracks, int* h_counts) {
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_submit_host: null argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
     cudaPointerAttributes at{}, ot{}, oc{};
     const bool ok = cudaPointerGetAttributes(&at, h_heads) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
@@ -588,6 +634,7 @@ static int check_order_flag(pb_handle_st* h) {
 
 int pb_wait(pb_handle_t h) {
     if (!h) { pb_set_error("pb_wait: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_TRY(join_on(h, h->own_stream));
     PB_CUDA(cudaStreamSynchronize(h->own_stream));
     return check_order_flag(h);
@@ -595,6 +642,7 @@ int pb_wait(pb_handle_t h) {
 
 int pb_get_tracks(pb_handle_t h, int b, void* out, int cap, int* n_out) {
     if (!h || b < 0 || b >= h->cfg.num_streams || !n_out) { pb_set_error("pb_get_tracks: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     PB_TRY(check_order_flag(h));
     int n = 0;
@@ -609,6 +657,7 @@ int pb_get_tracks(pb_handle_t h, int b, void* out, int cap, int* n_out) {
 
 int pb_get_tracks_all(pb_handle_t h, void* out, int* counts) {
     if (!h || !out || !counts) { pb_set_error("pb_get_tracks_all: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     PB_TRY(check_order_flag(h));
     const size_t B = h->cfg.num_streams;
@@ -619,7 +668,9 @@ int pb_get_tracks_all(pb_handle_t h, void* out, int* counts) {
 
 int pb_get_num_active(pb_handle_t h, int* out) {
     if (!h || !out) { pb_set_error("pb_get_num_active: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
+    PB_TRY(check_order_flag(h));
     std::vector<int> sc((size_t)h->cfg.num_streams * 4);
     PB_CUDA(cudaMemcpy(sc.data(), h->trk.scalars, sc.size() * sizeof(int), cudaMemcpyDeviceToHost));
     for (int b = 0; b < h->cfg.num_streams; ++b) out[b] = sc[(size_t)b * 4 + 3];
@@ -632,6 +683,7 @@ int pb_get_num_active(pb_handle_t h, int* out) {
 int pb_get_kept(pb_handle_t h, int b, float* poses, float* bboxes, float* scores, int* keep_slots,
                 int* keep_anchors, int cap, int* num_keep, int* num_cand) {
     if (!h || b < 0 || b >= h->cfg.num_streams) { pb_set_error("pb_get_kept: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     const size_t K = h->cfg.max_keep;
     int nk = 0, nc = 0;
@@ -654,7 +706,9 @@ int pb_get_state(pb_handle_t h, int b, float* poses, float* vel, float* scores, 
                  int* hits, int* ages, int* last_frame, int* active, int* row_assign, int* col_assign,
                  float* cost, float* predicted, float* centers, int* scalars) {
     if (!h || b < 0 || b >= h->cfg.num_streams) { pb_set_error("pb_get_state: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
+    PB_TRY(check_order_flag(h));
     const size_t T = h->cfg.max_tracks, Dm = h->cfg.max_detections;
     const TrackBuffers& t = h->trk;
     PB_D2H(poses, t.poses + b * T * POSE_F, T * POSE_F);
@@ -688,6 +742,7 @@ int pb_get_device_views(pb_handle_t h, pb_device_views* v) {
 
 int pb_get_post_stage_us(pb_handle_t h, double* out5) {
     if (!h || !out5) { pb_set_error("pb_get_post_stage_us: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     const int B = h->cfg.num_streams;
     std::vector<unsigned long long> ns((size_t)B * 16);
@@ -700,6 +755,7 @@ int pb_get_post_stage_us(pb_handle_t h, double* out5) {
 
 int pb_get_nms_path_counts(pb_handle_t h, long long* fast_path, long long* complete_path, long long* keypoint_fetches) {
     if (!h) { pb_set_error("pb_get_nms_path_counts: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     const int B = h->cfg.num_streams;
     std::vector<unsigned long long> ns((size_t)B * 16);
@@ -720,6 +776,7 @@ int pb_set_profiling(pb_handle_t h, int enabled) {
 
 int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_n, double* track_ms, int* track_n) {
     if (!h) { pb_set_error("pb_get_kernel_ms: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     auto sum = [&](std::vector<std::pair<int, int>>& v, double* ms, int* n) {
         double acc = 0;
@@ -737,6 +794,7 @@ int pb_get_kernel_ms(pb_handle_t h, double* post_ms, int* post_n, double* track_
 
 int pb_get_kernel_us(pb_handle_t h, double* gather_us, double* nms_us, double* track_us, int* launches) {
     if (!h) { pb_set_error("pb_get_kernel_us: null handle"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     auto total = [&](std::vector<std::pair<int, int>>& v) {
         double acc = 0;
@@ -756,6 +814,7 @@ int pb_get_kernel_us(pb_handle_t h, double* gather_us, double* nms_us, double* t
 
 int pb_get_stream_stage_ns(pb_handle_t h, unsigned long long* out) {
     if (!h || !out) { pb_set_error("pb_get_stream_stage_ns: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     PB_CUDA(cudaMemcpy(out, h->trk.stage_ns, (size_t)h->cfg.num_streams * 20 * 8, cudaMemcpyDeviceToHost));
     return PB_OK;
@@ -763,6 +822,7 @@ int pb_get_stream_stage_ns(pb_handle_t h, unsigned long long* out) {
 
 int pb_debug_timeline(pb_handle_t h, unsigned long long* out) {
     if (!h || !out) { pb_set_error("pb_debug_timeline: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     if (!h->trk.dbg) { pb_set_error("pb_debug_timeline: create the handle with PB_TIMELINE=1 in the environment"); return PB_ERR_UNSUPPORTED; }
     PB_CUDA(cudaDeviceSynchronize());
     PB_CUDA(cudaMemcpy(out, h->trk.dbg, (size_t)64 * h->cfg.num_streams * 6 * 8, cudaMemcpyDeviceToHost));
@@ -771,6 +831,7 @@ int pb_debug_timeline(pb_handle_t h, unsigned long long* out) {
 
 int pb_get_timing(pb_handle_t h, pb_timing* out) {
     if (!h || !out) { pb_set_error("pb_get_timing: bad argument"); return PB_ERR_INVALID; }
+    DevGuard dev_guard(h->cfg.device);
     PB_CUDA(cudaDeviceSynchronize());
     const int B = h->cfg.num_streams;
     std::vector<unsigned long long> ns((size_t)B * 20);

@@ -128,5 +128,8 @@ cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSourc
 cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, int seq, cudaStream_t stream);
 
 void count_launch(int n = 1);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it for `func` on the
+// current device when `bytes` exceeds what was set there before (thread-safe; pb_api.cu).
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
 
 }  // namespace pb

@@ -531,8 +531,13 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
     const float* src_pose = src.poses + (size_t)b * src.stride * POSE_F;
     const float* src_score = src.scores + (size_t)b * src.stride;
     float* det_w = P.det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
+    // Detections in shared memory: copied now.  In the global scratch (large max_detections) they are copied after the
+    // wait below: the predecessor of this video stream — possibly still running on another lane — reads the same
+    // scratch until its first release.
+    if (P.det_in_smem) {
 #pragma unroll 1
-    for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
+        for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
+    }
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) { s.dscore[d] = src_score[d]; s.col[d] = -1; }
     if (tid < 32) s.misc[tid] = 0;
@@ -569,7 +574,7 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
             int v;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v - want >= 0) break;
-            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); break; }
+            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; break; }
         }
         const unsigned long long w1 = globaltimer_ns();
         if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(P.seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
@@ -580,6 +585,21 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
         if (prev_end != 0ull && t_begin > prev_end) s.acc[19] += t_begin - prev_end;    // ... of which: this CTA had not started yet
     }
     __syncthreads();
+    if (s.misc[10]) {
+        // Time-out (misuse, or a foreign kernel starving the predecessor for 0.5 s): the stream's state is not this
+        // frame's predecessor state.  Leave it untouched, pass the sequence number on so that later frames do not
+        // wait again, and let the sticky error flag invalidate the results (every synchronising entry point reports it).
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
+        }
+        return;
+    }
+    if (!P.det_in_smem) {
+#pragma unroll 1
+        for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
+    }
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
     // State slabs -> shared memory, and in the same pass the ordered active list (ascending t).  The list position of
@@ -727,10 +747,18 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
             int v;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(tb.out_done + b) : "memory");
             if (v - want >= 0) break;
-            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); break; }
+            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; break; }
         }
     }
     __syncthreads();
+    if (s.misc[10]) {       // see the first wait: no update, no records; only the prediction scratch has been touched
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
+        }
+        return;
+    }
     // ---------------- update matched (:1438-1472, kernels :141-189, :612-648) -------------
     if (D > 0) {
         const float process_noise = 0.1f, measurement_noise = 0.3f;
@@ -1033,18 +1061,13 @@ cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, i
 
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream) {
-    static size_t configured[4] = {0, 0, 0, 0};
     const bool allsmem = plan.cost_in_smem && plan.det_in_smem && plan.pred_in_smem;
     const int v = plan.threads == 256 ? 0 : (plan.threads == 512 ? 1 : (allsmem ? 3 : 2));
-    if (plan.smem_bytes > configured[v]) {
-        cudaError_t e;
-        const int bytes = (int)plan.smem_bytes;
-        if (v == 0) e = cudaFuncSetAttribute(pb_tracker_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        else if (v == 1) e = cudaFuncSetAttribute(pb_tracker_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        else if (v == 2) e = cudaFuncSetAttribute(pb_tracker_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        else e = cudaFuncSetAttribute(pb_tracker_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    const void* fn = v == 0 ? (const void*)pb_tracker_kernel<256, false> : v == 1 ? (const void*)pb_tracker_kernel<512, false>
+                   : v == 2 ? (const void*)pb_tracker_kernel<1024, false> : (const void*)pb_tracker_kernel<1024, true>;
+    {
+        const cudaError_t e = ensure_dyn_smem(fn, plan.smem_bytes);
         if (e != cudaSuccess) return e;
-        configured[v] = plan.smem_bytes;
     }
     p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
     p.term_floats = plan.term_floats;
