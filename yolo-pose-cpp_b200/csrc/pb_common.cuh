@@ -81,7 +81,7 @@ struct TrackParams {
     int frame_id;
     int seq;             // sequence number of this launch; the CTA of stream b starts once seq_done[b] == seq - 1
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
-    int cost_in_smem, det_in_smem, pred_in_smem, term_floats;
+    int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap;
     SmemOffsets so;      // shared-memory layout (tracker_plan)
 };
 
@@ -121,8 +121,8 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
 cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 lazy, 2 deferred*/, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
-struct TrackerPlan { size_t smem_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats; SmemOffsets so; };
-TrackerPlan tracker_plan(int T, int Dm);
+struct TrackerPlan { size_t smem_bytes, prefix_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap; SmemOffsets so; };
+TrackerPlan tracker_plan(int T, int Dm, bool compact = false);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);
 cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, int seq, cudaStream_t stream);

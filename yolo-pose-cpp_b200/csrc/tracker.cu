@@ -1,140 +1,13 @@
-// tracker.cu — PoseBYTE tracker update for B independent streams, one CTA per stream.
-//
-// Replaces GPUTracker::update + getActiveTracks (reference src/cuda/gpu_tracker.cu:
-// 1057-1158, 1559-1639) — ~490 stream operations and 2 host synchronisations per frame
-// and stream upstream — with ONE launch for all streams.  The stage order, every
-// formula and every persistent buffer follow the reference literally (SURVEY.md §8a rows
-// A5-A16, quirks Q1-Q8); the stages run back to back inside the CTA with the working set
-// (cost matrix, detections, predicted poses, gate bitmasks, assignments, prices) in
-// shared memory:
-//   predict (:102-138) -> keypoint-box centres (:196-237) -> velocity-adaptive spatial
-//   gate (:241-317), bit-packed -> tier 1: visibility-masked OKS (:333-425) + auction +
-//   lock (:540-567) -> tier 2: torso OKS (:429-490) + auction + merge (:575-588) + lock
-//   -> tier 3: lost-track gate x1.3, OKS, auction, merge -> constant-gain update
-//   (:141-189, :612-648) -> ageing (:651-688) -> new tracks (:695-780, rules R3/R4) ->
-//   IoU de-duplication (:788-895, rule R5) -> TrackOutput assembly (:1594-1636).
-// The auction (hungarian.cu:27-123, 358-405) keeps the reference's bid arithmetic and
-// tie-breaks (R6); one warp runs the whole solve with lane = column, prices and owners in
-// registers (auction.cuh), and the loop stops at the first iteration without a bid — a
-// fixed point of the reference's 50 fixed iterations.
+// tracker.cu — stand-alone tracker launch (pb_tracker_update, the serial and the three-kernel pipelined step): one CTA per
+// stream running tracker_body (tracker_body.cuh); shared-memory plan; state reset.
 #include <cstdlib>
-#include "pb_common.cuh"
-#include "auction.cuh"
+#include "tracker_body.cuh"
 
 namespace pb {
 
-constexpr unsigned FULLM = 0xffffffffu;
-constexpr int DUP_CAP = 256;
-constexpr int CELL_LIST_CAP = 4096;       // gated cells compacted per chunk of active rows
-
-struct TkSmem {
-    int *active, *states, *hits, *ids, *ages, *row, *rowb, *act_list, *elig_list, *rowbc, *rowbid;   // [T]
-    int *col, *colb, *slot_for_det, *out_list;                                        // [Dm]
-    float *price, *dscore, *darea;                                                    // [Dm]
-    unsigned long long* colbid;                                                       // [Dm]
-    float *tcent, *tarea, *tav;                                                       // [T*4],[T],[T]
-    float* dcent;                                                                     // [Dm*4]
-    unsigned *gate, *lgate;                                                           // [T*Dw]
-    unsigned* colmask;                                                                // [Dw]
-    int* dup;                                                                         // [DUP_CAP]
-    int* misc;                                                                        // [32]
-    unsigned long long* acc;                                                          // [20] telemetry
-    float* terms;                                                                     // [term_floats]
-    float* sig;                                                                       // [17]
-    int* cell_list;                                                                   // [CELL_LIST_CAP]
-    int* aowner;                                                                      // [Dm] auction scratch
-    float *cost, *det, *pred;                                                         // optional
-};
-
-__host__ __device__ inline size_t tk_align(size_t x) { return (x + 15) & ~(size_t)15; }
-
-__host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, int cost_s, int det_s,
-                                           int pred_s, int term_floats, TkSmem* s) {
-    const int Dw = (Dm + 31) / 32;
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = tk_align(off + bytes); return o; };
-    size_t o_colbid = take((size_t)Dm * 8), o_acc = take(20 * 8);
-    size_t o_i[11]; for (int i = 0; i < 11; ++i) o_i[i] = take((size_t)T * 4);
-    size_t o_d[4]; for (int i = 0; i < 4; ++i) o_d[i] = take((size_t)Dm * 4);
-    size_t o_f[3]; for (int i = 0; i < 3; ++i) o_f[i] = take((size_t)Dm * 4);
-    size_t o_tcent = take((size_t)T * 16), o_tarea = take((size_t)T * 4), o_tav = take((size_t)T * 4);
-    size_t o_dcent = take((size_t)Dm * 16);
-    size_t o_gate = take((size_t)T * Dw * 4), o_lgate = take((size_t)T * Dw * 4), o_colmask = take((size_t)Dw * 4);
-    size_t o_dup = take(DUP_CAP * 4), o_misc = take(32 * 4);
-    size_t o_terms = take((size_t)term_floats * 4), o_sig = take(KP * 4), o_cl = take(CELL_LIST_CAP * 4);
-    size_t o_aown = take((size_t)Dm * 4);
-    size_t o_cost = cost_s ? take((size_t)T * Dm * 4) : 0;
-    size_t o_det = det_s ? take((size_t)Dm * POSE_F * 4) : 0;
-    size_t o_pred = pred_s ? take((size_t)T * POSE_F * 4) : 0;
-    if (s) {
-        s->colbid = (unsigned long long*)(base + o_colbid);
-        s->acc = (unsigned long long*)(base + o_acc);
-        int** ip[11] = {&s->active, &s->states, &s->hits, &s->ids, &s->ages, &s->row, &s->rowb, &s->act_list, &s->elig_list,
-                        &s->rowbc, &s->rowbid};
-        for (int i = 0; i < 11; ++i) *ip[i] = (int*)(base + o_i[i]);
-        int** dp[4] = {&s->col, &s->colb, &s->slot_for_det, &s->out_list};
-        for (int i = 0; i < 4; ++i) *dp[i] = (int*)(base + o_d[i]);
-        float** fp[3] = {&s->price, &s->dscore, &s->darea};
-        for (int i = 0; i < 3; ++i) *fp[i] = (float*)(base + o_f[i]);
-        s->tcent = (float*)(base + o_tcent); s->tarea = (float*)(base + o_tarea); s->tav = (float*)(base + o_tav);
-        s->dcent = (float*)(base + o_dcent);
-        s->gate = (unsigned*)(base + o_gate); s->lgate = (unsigned*)(base + o_lgate);
-        s->colmask = (unsigned*)(base + o_colmask);
-        s->dup = (int*)(base + o_dup); s->misc = (int*)(base + o_misc);
-        s->terms = (float*)(base + o_terms); s->sig = (float*)(base + o_sig); s->cell_list = (int*)(base + o_cl);
-        s->aowner = (int*)(base + o_aown);
-        s->cost = cost_s ? (float*)(base + o_cost) : nullptr;
-        s->det = det_s ? (float*)(base + o_det) : nullptr;
-        s->pred = pred_s ? (float*)(base + o_pred) : nullptr;
-    }
-    return off;
-}
-
-
-// Shared-memory layout as byte offsets, computed once on the host (tracker_plan) and handed to the kernel as a
-// launch parameter: the 36 pointers of TkSmem are then one constant-bank add each wherever the compiler
-// rematerialises them, instead of the offset arithmetic of tk_carve (measured: ~1000 SASS instructions).
-__device__ __forceinline__ void tk_from_offsets(unsigned char* base, const SmemOffsets& o, TkSmem& s) {
-    s.active = reinterpret_cast<int*>(base + o.off[0]);
-    s.states = reinterpret_cast<int*>(base + o.off[1]);
-    s.hits = reinterpret_cast<int*>(base + o.off[2]);
-    s.ids = reinterpret_cast<int*>(base + o.off[3]);
-    s.ages = reinterpret_cast<int*>(base + o.off[4]);
-    s.row = reinterpret_cast<int*>(base + o.off[5]);
-    s.rowb = reinterpret_cast<int*>(base + o.off[6]);
-    s.act_list = reinterpret_cast<int*>(base + o.off[7]);
-    s.elig_list = reinterpret_cast<int*>(base + o.off[8]);
-    s.rowbc = reinterpret_cast<int*>(base + o.off[9]);
-    s.rowbid = reinterpret_cast<int*>(base + o.off[10]);
-    s.col = reinterpret_cast<int*>(base + o.off[11]);
-    s.colb = reinterpret_cast<int*>(base + o.off[12]);
-    s.slot_for_det = reinterpret_cast<int*>(base + o.off[13]);
-    s.out_list = reinterpret_cast<int*>(base + o.off[14]);
-    s.price = reinterpret_cast<float*>(base + o.off[15]);
-    s.dscore = reinterpret_cast<float*>(base + o.off[16]);
-    s.darea = reinterpret_cast<float*>(base + o.off[17]);
-    s.colbid = reinterpret_cast<unsigned long long*>(base + o.off[18]);
-    s.tcent = reinterpret_cast<float*>(base + o.off[19]);
-    s.tarea = reinterpret_cast<float*>(base + o.off[20]);
-    s.tav = reinterpret_cast<float*>(base + o.off[21]);
-    s.dcent = reinterpret_cast<float*>(base + o.off[22]);
-    s.gate = reinterpret_cast<unsigned*>(base + o.off[23]);
-    s.lgate = reinterpret_cast<unsigned*>(base + o.off[24]);
-    s.colmask = reinterpret_cast<unsigned*>(base + o.off[25]);
-    s.dup = reinterpret_cast<int*>(base + o.off[26]);
-    s.misc = reinterpret_cast<int*>(base + o.off[27]);
-    s.acc = reinterpret_cast<unsigned long long*>(base + o.off[28]);
-    s.terms = reinterpret_cast<float*>(base + o.off[29]);
-    s.sig = reinterpret_cast<float*>(base + o.off[30]);
-    s.cell_list = reinterpret_cast<int*>(base + o.off[31]);
-    s.aowner = reinterpret_cast<int*>(base + o.off[32]);
-    s.cost = reinterpret_cast<float*>(base + o.off[33]);
-    s.det = reinterpret_cast<float*>(base + o.off[34]);
-    s.pred = reinterpret_cast<float*>(base + o.off[35]);
-}
-static void tk_offsets(int T, int Dm, int cost_s, int det_s, int pred_s, int term_floats, SmemOffsets& o) {
+static void tk_offsets(int T, int Dm, int cost_s, int det_s, int pred_s, int term_floats, int cell_cap, SmemOffsets& o) {
     TkSmem t;
-    tk_carve(nullptr, T, Dm, cost_s, det_s, pred_s, term_floats, &t);
+    tk_carve(nullptr, T, Dm, cost_s, det_s, pred_s, term_floats, cell_cap, &t);
     o.off[0] = (unsigned)(uintptr_t)t.active;
     o.off[1] = (unsigned)(uintptr_t)t.states;
     o.off[2] = (unsigned)(uintptr_t)t.hits;
@@ -173,22 +46,29 @@ static void tk_offsets(int T, int Dm, int cost_s, int det_s, int pred_s, int ter
     o.off[35] = (unsigned)(uintptr_t)t.pred;
 }
 
-TrackerPlan tracker_plan(int T, int Dm) {
+// compact: the plan of the fused per-stream kernel, which wants two CTAs per SM — a term buffer of 256 cells per
+// round instead of 481+ and a cell list of 2048 instead of 4096 entries (more rounds for large frames, same results:
+// cells are independent).  The term buffer also holds the compacted cost rows of the single-warp auction
+// (at most 32 rows x 64 columns).
+TrackerPlan tracker_plan(int T, int Dm, bool compact) {
     TrackerPlan p{};
     const size_t budget = 200 * 1024;
     p.cost_in_smem = p.det_in_smem = p.pred_in_smem = 0;
     // term buffer: at least one active row (Dm * 17 floats), 32 KB when it fits
     int term_floats = Dm * KP;
-    if (term_floats < 8192) term_floats = 8192;
+    const int floor_floats = compact ? 4352 : 8192;
+    if (term_floats < floor_floats) term_floats = floor_floats;
     p.term_floats = term_floats;
-    size_t base = tk_carve(nullptr, T, Dm, 0, 0, 0, term_floats, nullptr);
+    p.cell_cap = compact ? 2048 : 4096;
+    if (p.cell_cap < Dm) p.cell_cap = Dm;
+    size_t base = tk_carve(nullptr, T, Dm, 0, 0, 0, term_floats, p.cell_cap, nullptr);
     size_t cost_b = tk_align((size_t)T * Dm * 4), det_b = tk_align((size_t)Dm * POSE_F * 4), pred_b = tk_align((size_t)T * POSE_F * 4);
     size_t used = base;
     if (used + cost_b <= budget) { p.cost_in_smem = 1; used += cost_b; }
     if (used + det_b <= budget) { p.det_in_smem = 1; used += det_b; }
     if (used + pred_b <= budget) { p.pred_in_smem = 1; used += pred_b; }
-    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, nullptr);
-    tk_offsets(T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.so);
+    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.cell_cap, nullptr, &p.prefix_bytes);
+    tk_offsets(T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.cell_cap, p.so);
     const long cells = (long)T * Dm;
     // small tables (the tracker's 128 x 64 case): 1024 threads — the auction runs in one warp whatever the
     // block size, every other stage (copies, gate, cost passes, outputs) is data-parallel and measured
@@ -198,832 +78,11 @@ TrackerPlan tracker_plan(int T, int Dm) {
     return p;
 }
 
-// ---------------------------------------------------------------------------------------
-// keypoint-box statistics of one pose (17 lanes of a warp would be overkill: T+D poses)
-// centres as kernelComputeBboxCenters (:196-237); area as the scale term of
-// kernelOKSWithGating (:364-392).  Both use keypoints with conf > 0.1.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void pose_box(const float* p, float* cent4, float* area) {
-    float lx = 1e9f, ly = 1e9f, hx = -1e9f, hy = -1e9f;
-    int valid = 0;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        if (p[k * 3 + 2] > 0.1f) {
-            const float x = p[k * 3], y = p[k * 3 + 1];
-            lx = pb_min(lx, x); ly = pb_min(ly, y); hx = pb_max(hx, x); hy = pb_max(hy, y);
-            ++valid;
-        }
-    }
-    *area = (hx - lx) * (hy - ly);
-    if (valid < 2) { cent4[0] = 0.f; cent4[1] = 0.f; cent4[2] = 0.f; cent4[3] = 0.f; return; }
-    const float w = hx - lx, h = hy - ly;
-    cent4[0] = (lx + hx) * 0.5f; cent4[1] = (ly + hy) * 0.5f; cent4[2] = w; cent4[3] = h;
-}
-
-// kernelSpatialGate (:241-317) for one active row / one detection.
-__device__ __forceinline__ bool gate_cell(const float* tc, const float* dc, float av, bool lost,
-                                          float base, bool gating) {
-    const float tw = tc[2], th = tc[3], dw = dc[2], dh = dc[3];
-    if (tw < 1.0f || th < 1.0f || dw < 1.0f || dh < 1.0f) return true;
-    if (!gating) return true;
-    const float dx = tc[0] - dc[0], dy = tc[1] - dc[1];
-    const float dist = sqrtf(dx * dx + dy * dy);
-    const float size = (tw + th + dw + dh) * 0.25f;
-    const float ratio = dist / (size + 1e-6f);
-    const float vf = 1.0f + pb_min(av / (size + 1e-6f), 2.0f);
-    float thr = base * vf;
-    if (lost) thr *= 2.0f;
-    return ratio < thr;
-}
-
-// kernelTorsoOKS cell (:455-489).
-__device__ __forceinline__ float torso_cost(const float* tp, const float* dp) {
-    const int torso[4] = {5, 6, 11, 12};
-    const float scale_sq = 10000.0f;
-    float sum = 0.0f;
-    int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = torso[i];
-        if (dp[k * 3 + 2] > 0.1f && tp[k * 3 + 2] > 0.1f) {
-            const float dx = dp[k * 3] - tp[k * 3], dy = dp[k * 3 + 1] - tp[k * 3 + 1];
-            const float d2 = dx * dx + dy * dy;
-            const float sg = kSigmas[k] * 3.0f;
-            sum += pb_expf(-d2 / (2.0f * scale_sq * sg * sg));
-            ++cnt;
-        }
-    }
-    const float oks = (cnt >= 2) ? (sum / (float)cnt) : 0.0f;
-    return 1.0f - oks;
-}
-
-struct Ctx {
-    TkSmem s;
-    int T, D, Dw, tid, nthreads, lane, warp, nwarps;
-    unsigned magicD, magicW;   // ceil(2^32 / D), ceil(2^32 / words): i / D == __umulhi(i, magicD) for i * D < 2^32 (0: divisor 1)
-    bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
-    int term_floats;
-    float* cost;        // shared or global, flat [t*D + d]
-    const float* det;   // shared or global scratch [d*51]
-    float* pred;        // shared or global (persistent) [t*51]
-};
-
-// i / d for the small non-negative indices of the stage loops, d fixed per frame: one multiply instead of the
-// ~25-instruction division sequence (magic = ceil(2^32 / d), exact while i * d < 2^32; d == 1 gives magic 0).
-__device__ __forceinline__ int fast_div(int i, unsigned magic) { return magic ? (int)__umulhi((unsigned)i, magic) : i; }
-__device__ __forceinline__ unsigned div_magic(int d) { return d > 1 ? (0xffffffffu / (unsigned)d + 1u) : 0u; }
-
-// Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
-__device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
-    TkSmem& s = c.s;
-    if (c.warp_auction && na <= 32 && c.D <= 64) {
-        if (after_lock) {
-            // Rows matched in an earlier tier are locked (all their cells are 1e9, lock_pairs) and can never bid.  When
-            // that is every active row — the usual frame: everybody found its detection in tier 1 — the solve would
-            // clear the assignments and stop before its first iteration: do just that, without compacting the rows.
-            const bool may = c.lane < na && s.rowb[s.act_list[c.lane]] < 0;
-            if (__ballot_sync(FULLM, may) == 0u) {                 // the same in every warp
-#pragma unroll 1
-                for (int t = c.tid; t < c.T; t += c.nthreads) s.row[t] = -1;
-#pragma unroll 1
-                for (int d = c.tid; d < c.D; d += c.nthreads) s.col[d] = -1;
-                __syncthreads();
-                return;
-            }
-        }
-        // compact the active rows (cc[i*D + d], i = position in act_list) into the term buffer, which is idle
-        // between cost passes: the single-warp solve then reads a bidder's row with one conflict-free load
-        float* cc = s.terms;
-        const int D = c.D;
-#pragma unroll 1
-        for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = fast_div(i, c.magicD); cc[i] = s.cost[s.act_list[ai] * D + (i - ai * D)]; }
-        __syncthreads();
-        if (c.tid < 32) {
-            unsigned* cb = reinterpret_cast<unsigned*>(s.colbid);
-            int* cr = reinterpret_cast<int*>(s.colbid) + c.D;
-            // rows matched in an earlier tier are locked: all their cells are 1e9 (lock_pairs), they can never bid
-            const bool may_bid = c.tid < na && !(after_lock && s.rowb[s.act_list[c.tid]] >= 0);
-            const unsigned ub0 = __ballot_sync(FULLM, may_bid);
-            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc);
-            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc);
-        }
-        __syncthreads();
-    } else if (c.warp_auction && na <= 32) {
-        if (c.tid < 32)
-            auction_solve_hybrid32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
-                                   reinterpret_cast<unsigned*>(s.colbid), reinterpret_cast<int*>(s.colbid) + c.D);
-        __syncthreads();
-    } else if (c.warp_auction) {
-        // colbid (8 B per column) doubles as the 32-bit bid array + the lowest-row array
-        unsigned* colbid32 = reinterpret_cast<unsigned*>(s.colbid);
-        int* colrow = reinterpret_cast<int*>(s.colbid) + c.D;
-        auction_solve_warp(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, colbid32, colrow, s.rowbc,
-                           reinterpret_cast<unsigned*>(s.rowbid), c.tid);
-    } else {
-        auction_solve_cta(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, s.colbid, &s.misc[8],
-                          c.tid, c.nthreads);
-    }
-}
-
-// kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.  Only rows that were active at
-// frame start are touched: the cells of inactive rows are never read by the auction (inactive
-// rows do not bid) and are overwritten with 1.0 by the last cost pass of the frame anyway.
-__device__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
-    TkSmem& s = c.s;
-    const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
-#pragma unroll 1
-    for (int ai = c.warp; ai < na; ai += c.nwarps) {
-        const int t = s.act_list[ai];
-        const bool rowm = s.row[t] >= 0;
-        for (int w = 0; w < words; ++w) {
-            const int d = w * 32 + c.lane;
-            const bool colm = (d < D) && (s.col[d] >= 0);
-            const unsigned bm = __ballot_sync(FULLM, colm);
-            if (d < D && (rowm || colm)) c.cost[(size_t)t * D + d] = 1e9f;
-            if (c.lane == 0) gate[t * Dw + w] = rowm ? 0u : (gate[t * Dw + w] & ~bm);
-        }
-    }
-    __syncthreads();
-}
-
-// cost <- 1.0 on inactive rows (:351-354): warp per row.  Only the last writer of a frame matters
-// for these rows (see lock_pairs), so this runs once per frame, in the lost-track tier.
-__device__ void cost_inactive_rows(Ctx& c) {
-    TkSmem& s = c.s;
-#pragma unroll 1
-    for (int t = c.warp; t < c.T; t += c.nwarps)
-        if (s.active[t] == 0)
-#pragma unroll 1
-            for (int d = c.lane; d < c.D; d += 32) c.cost[(size_t)t * c.D + d] = 1.0f;
-}
-
-// Visibility-masked OKS cost on the gated cells of the active rows (kernelOKSWithGating :360-424).
-// The gated cells are first compacted into a list (warp per row, ballot append); then the
-// exponentials are spread over threads: one thread per (cell, keypoint) evaluates a term into
-// shared memory and one thread per cell adds the terms of its visible keypoints in keypoint
-// order (the reference's summation order) and finishes the cell.
-__device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
-    TkSmem& s = c.s;
-    const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
-    int rows_per_chunk = CELL_LIST_CAP / D;            // worst case: every cell of the chunk is gated
-    if (rows_per_chunk < 1) rows_per_chunk = 1;
-    const int cells_per_round = c.term_floats / KP;
-    for (int a0 = 0; a0 < na; a0 += rows_per_chunk) {
-        const int a1 = (a0 + rows_per_chunk < na) ? a0 + rows_per_chunk : na;
-        if (c.tid == 0) s.misc[5] = 0;
-        __syncthreads();
-#pragma unroll 1
-        for (int ai = a0 + c.warp; ai < a1; ai += c.nwarps) {
-            const int t = s.act_list[ai];
-            for (int w = 0; w < words; ++w) {
-                const int d = w * 32 + c.lane;
-                const unsigned gw = gate[t * Dw + w];
-                if (gw == 0u) continue;
-                const int n = __popc(gw);
-                int base = 0;
-                if (c.lane == 0) base = atomicAdd(&s.misc[5], n);
-                base = __shfl_sync(FULLM, base, 0);
-                if ((gw >> c.lane) & 1u) {
-                    const int pos = base + __popc(gw & ((1u << c.lane) - 1u));
-                    if (pos < CELL_LIST_CAP) s.cell_list[pos] = (t << 16) | d;
-                }
-            }
-        }
-        __syncthreads();
-        const int ncell = s.misc[5] < CELL_LIST_CAP ? s.misc[5] : CELL_LIST_CAP;
-        for (int cb = 0; cb < ncell; cb += cells_per_round) {
-            const int ncur = (ncell - cb) < cells_per_round ? (ncell - cb) : cells_per_round;
-#pragma unroll 1
-            for (int idx = c.tid; idx < ncur * KP; idx += c.nthreads) {
-                const int e = idx / KP, k = idx - e * KP;
-                const int key = s.cell_list[cb + e];
-                const int t = key >> 16, d = key & 0xffff;
-                const float* tp = c.pred + (size_t)t * POSE_F + k * 3;
-                const float* dp = c.det + (size_t)d * POSE_F + k * 3;
-                float term = -0.0f;                  // marker of an invisible keypoint: adds nothing, is not counted (below)
-                if (dp[2] > vis && tp[2] > vis) {
-                    const float scale_sq = pb_max((s.darea[d] + s.tarea[t]) * 0.5f, 1000.0f);
-                    const float t2 = 2.0f * scale_sq;
-                    const float dx = dp[0] - tp[0], dy = dp[1] - tp[1];
-                    const float d2 = dx * dx + dy * dy;
-                    const float sg = s.sig[k] * 2.0f;
-                    const float s2 = sg * sg;
-                    term = pb_expf(-d2 / (t2 * s2));
-                }
-                s.terms[idx] = term;
-            }
-            __syncthreads();
-#pragma unroll 1
-            for (int e = c.tid; e < ncur; e += c.nthreads) {
-                const int key = s.cell_list[cb + e];
-                const int t = key >> 16, d = key & 0xffff;
-                // keypoint-ordered sum over the visible keypoints (:408-419).  An invisible keypoint left -0.0f: x + -0.0f
-                // is x for every x this sum can hold (it starts at +0 and its terms are >= +0 or NaN), and a visible
-                // term is never -0.0f, so neither the confidences nor a branch are needed here.
-                float sum = 0.0f;
-                int cnt = 0;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    const float tv = s.terms[e * KP + k];
-                    sum += tv;
-                    cnt += (__float_as_uint(tv) != 0x80000000u) ? 1 : 0;
-                }
-                const float oks = (cnt >= 3) ? (sum / (float)cnt) : 0.0f;
-                c.cost[(size_t)t * D + d] = 1.0f - oks;
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// Torso-only OKS (kernelTorsoOKS :455-489): four exponentials per cell, one thread per cell.
-__device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
-    TkSmem& s = c.s;
-    const int D = c.D, Dw = c.Dw;
-#pragma unroll 1
-    for (int i = c.tid; i < na * D; i += c.nthreads) {
-        const int ai = fast_div(i, c.magicD), d = i - ai * D;
-        const int t = s.act_list[ai];
-        if ((gate[t * Dw + (d >> 5)] >> (d & 31)) & 1u)
-            c.cost[(size_t)t * D + d] = torso_cost(c.pred + (size_t)t * POSE_F, c.det + (size_t)d * POSE_F);
-    }
-    __syncthreads();
-}
-
-__device__ void backup_assign(Ctx& c) {      // no barrier: callers synchronise before the next solve
-    TkSmem& s = c.s;
-#pragma unroll 1
-    for (int t = c.tid; t < c.T; t += c.nthreads) s.rowb[t] = s.row[t];
-#pragma unroll 1
-    for (int d = c.tid; d < c.D; d += c.nthreads) s.colb[d] = s.col[d];
-}
-__device__ void merge_assign(Ctx& c) {   // kernelMergeAssignments :575-588
-    TkSmem& s = c.s;
-#pragma unroll 1
-    for (int t = c.tid; t < c.T; t += c.nthreads) if (s.rowb[t] >= 0) s.row[t] = s.rowb[t];
-#pragma unroll 1
-    for (int d = c.tid; d < c.D; d += c.nthreads) if (s.colb[d] >= 0) s.col[d] = s.colb[d];
-    __syncthreads();
-}
-
-__device__ __forceinline__ float center_iou(const float* a, const float* b) {   // kernelTrackIoU :825-854
-    const float cx1 = a[0], cy1 = a[1], w1 = a[2], h1 = a[3];
-    const float cx2 = b[0], cy2 = b[1], w2 = b[2], h2 = b[3];
-    const float x1a = cx1 - w1 * 0.5f, x1b = cx1 + w1 * 0.5f, y1a = cy1 - h1 * 0.5f, y1b = cy1 + h1 * 0.5f;
-    const float x2a = cx2 - w2 * 0.5f, x2b = cx2 + w2 * 0.5f, y2a = cy2 - h2 * 0.5f, y2b = cy2 + h2 * 0.5f;
-    const float ix1 = pb_max(x1a, x2a), iy1 = pb_max(y1a, y2a);
-    const float ix2 = pb_min(x1b, x2b), iy2 = pb_min(y1b, y2b);
-    const float iw = pb_max(0.0f, ix2 - ix1), ih = pb_max(0.0f, iy2 - iy1);
-    const float inter = iw * ih;
-    const float a1 = w1 * h1, a2 = w2 * h2;
-    const float uni = a1 + a2 - inter;
-    return (uni > 0) ? (inter / uni) : 0.0f;
-}
-
-// ALLSMEM: cost matrix, detections and predicted poses all live in shared memory (the plan's usual case); the
-// flags are then compile-time constants and every access to them is an LDS instead of a generic load.
 template <int NTHREADS, bool ALLSMEM>
 __global__ void __launch_bounds__(NTHREADS)
-pb_tracker_kernel(TrackBuffers tb, TrackParams P_, DetSource src) {
-    TrackParams P = P_;
-    if (ALLSMEM) { P.cost_in_smem = 1; P.det_in_smem = 1; P.pred_in_smem = 1; }
+pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Ctx c;
-    tk_from_offsets(smem_raw, P.so, c.s);
-    c.term_floats = P.term_floats;
-    TkSmem& s = c.s;
-    const int b = blockIdx.x;
-    const int T = P.T, Dm = P.Dm;
-    c.T = T; c.tid = threadIdx.x; c.nthreads = NTHREADS; c.lane = threadIdx.x & 31;
-    c.warp = threadIdx.x >> 5; c.nwarps = NTHREADS >> 5;
-    const int tid = c.tid, NT = c.nthreads;
-
-    // per-stream slabs
-    float* g_poses = tb.poses + (size_t)b * T * POSE_F;
-    float* g_vel = tb.vel + (size_t)b * T * 34;
-    float* g_scores = tb.scores + (size_t)b * T;
-    float* g_pred = tb.predicted + (size_t)b * T * POSE_F;
-    float* g_tcent = tb.tcent + (size_t)b * T * 4;
-    float* g_cost = tb.cost + (size_t)b * T * Dm;
-    float* g_dscore = tb.det_scores + (size_t)b * Dm;
-    int* g_states = tb.states + (size_t)b * T; int* g_ids = tb.ids + (size_t)b * T;
-    int* g_hits = tb.hits + (size_t)b * T; int* g_ages = tb.ages + (size_t)b * T;
-    int* g_last = tb.last_frame + (size_t)b * T; int* g_active = tb.active + (size_t)b * T;
-    int* g_dirty = tb.pred_dirty + (size_t)b * T;
-    int* g_scal = tb.scalars + (size_t)b * 4;
-    unsigned long long* g_ns = tb.stage_ns + (size_t)b * 20;
-
-    unsigned long long t_stamp = 0;
-    if (tid == 0) t_stamp = globaltimer_ns();
-    const unsigned long long t_begin = t_stamp;
-    // stage telemetry (TrackerTiming): thread 0 accumulates globaltimer deltas in shared memory
-    // and flushes them once at the end of the kernel
-    auto stamp = [&](int slot) {
-        if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
-    };
-
-    // ---------------- prologue (:1065-1088) ----------------
-    int n_in = src.num[b];
-    const int D = n_in < Dm ? (n_in < 0 ? 0 : n_in) : Dm;
-    c.D = D; c.Dw = (Dm + 31) / 32;
-    c.magicD = div_magic(D); c.magicW = div_magic((D + 31) / 32);   // before the wait: off the chain of dependent frames
-    const int Dw = c.Dw;
-    const float* src_pose = src.poses + (size_t)b * src.stride * POSE_F;
-    const float* src_score = src.scores + (size_t)b * src.stride;
-    float* det_w = P.det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
-    // Detections in shared memory: copied now.  In the global scratch (large max_detections) they are copied after the
-    // wait below: the predecessor of this video stream — possibly still running on another lane — reads the same
-    // scratch until its first release.
-    if (P.det_in_smem) {
-#pragma unroll 1
-        for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
-    }
-#pragma unroll 1
-    for (int d = tid; d < D; d += NT) { s.dscore[d] = src_score[d]; s.col[d] = -1; }
-    if (tid < 32) s.misc[tid] = 0;
-    if (tid < 20) s.acc[tid] = 0ull;
-    if (tid < KP) s.sig[tid] = kSigmas[tid];
-    if (D > 0) {
-        // detection centres / areas (kernelComputeBboxCenters on the detections, :1180-1186) and the cleared gate
-        // words depend on this frame's detections only: done here, before the wait for the predecessor, by the
-        // upper half of the CTA (the lower half is still copying the records)
-        const int h = NT >> 1;
-#pragma unroll 1
-        for (int d = tid - h; d >= 0 && d < D; d += h) {
-            float area;
-            pose_box(src_pose + (size_t)d * POSE_F, &s.dcent[d * 4], &area);
-            s.darea[d] = area;
-        }
-#pragma unroll 1
-        for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = 0u; s.lgate[i] = 0u; }
-    }
-    // ---- per-stream ordering across launches ----
-    // Consecutive tracker launches run on different CUDA streams (up to three "lanes", pb_api.cu) and may overlap:
-    // the CTA of stream b only needs the state ITS predecessor (the previous frame of the same video stream) left
-    // behind, not the whole previous grid, so a video stream whose auction ran to the iteration limit delays
-    // nobody but itself.  Everything above reads this frame's detections only; from here on the CTA touches the
-    // stream's persistent state and waits for seq_done[b] == seq - 1 (first release of the predecessor, acquire
-    // here).  Launches are issued in sequence order and the host keeps at most `lanes` of them in flight; the
-    // oldest never waits and the younger ones hold fewer SMs than the device has, so the oldest always runs to
-    // completion; the time-out only guards against misuse.
-    if (tid == 0) {
-        const int want = P.seq - 1;
-        const int* flag = tb.seq_done + b;
-        const unsigned long long w0 = globaltimer_ns();
-        for (;;) {
-            int v;
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v - want >= 0) break;
-            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; break; }
-        }
-        const unsigned long long w1 = globaltimer_ns();
-        if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(P.seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
-        s.acc[15] += w1 - w0;                        // telemetry: time spent waiting for the predecessor
-        s.acc[16] += w0 - t_begin;                   // telemetry: detection-only prologue
-        const unsigned long long prev_end = g_ns[18];   // absolute time at which the predecessor released the stream
-        if (prev_end != 0ull && w1 > prev_end) s.acc[17] += w1 - prev_end;              // predecessor's release -> this CTA goes on
-        if (prev_end != 0ull && t_begin > prev_end) s.acc[19] += t_begin - prev_end;    // ... of which: this CTA had not started yet
-    }
-    __syncthreads();
-    if (s.misc[10]) {
-        // Time-out (misuse, or a foreign kernel starving the predecessor for 0.5 s): the stream's state is not this
-        // frame's predecessor state.  Leave it untouched, pass the sequence number on so that later frames do not
-        // wait again, and let the sticky error flag invalidate the results (every synchronising entry point reports it).
-        if (tid == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
-        }
-        return;
-    }
-    if (!P.det_in_smem) {
-#pragma unroll 1
-        for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
-    }
-#pragma unroll 1
-    for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
-    // State slabs -> shared memory, and in the same pass the ordered active list (ascending t).  The list position of
-    // a row is its rank among the active rows — the auction breaks ties between equal bids by it (lowest row,
-    // hungarian.cu:100) — so it must not depend on which warp gets here first: every warp derives the number of
-    // active rows in front of its block of 32 from ballots over the preceding blocks (read from the state slab
-    // itself, so no barrier is needed between the copy and the list) instead of from an atomic counter.
-#pragma unroll 1
-    for (int t0 = c.warp * 32; t0 < T; t0 += NT) {
-        const int t = t0 + c.lane;
-        int a = 0, st = 0;
-        if (t < T) {
-            a = g_active[t]; st = g_states[t];
-            s.active[t] = a; s.states[t] = st; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
-            s.row[t] = -1;
-            s.rowbc[t] = g_dirty[t];        // predicted pose changed since its centre was derived (idle auction scratch)
-        }
-        int start = 0;
-#pragma unroll 1
-        for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, g_active[pb + c.lane] == 1));
-        const bool act = (a == 1);
-        const unsigned bm = __ballot_sync(FULLM, act);
-        const unsigned lm = __ballot_sync(FULLM, act && st == ST_LOST);
-        if (c.lane == 0 && lm) atomicAdd(&s.misc[6], __popc(lm));              // LOST rows at frame start (a sum: order-free)
-        if (act) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
-        if (c.lane == 0 && t0 + 32 >= T) s.misc[0] = start + __popc(bm);
-    }
-#pragma unroll 1
-    for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
-    c.det = det_w;
-    c.cost = P.cost_in_smem ? s.cost : g_cost;
-    c.warp_auction = P.cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
-    c.pred = P.pred_in_smem ? s.pred : g_pred;
-    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
-    __syncthreads();
-    const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
-    stamp(0);
-
-    // ---------------- predict (:1160-1175, kernel :102-138) ----------------
-    if (na > 0) {
-#pragma unroll 1
-        for (int i = tid; i < na * KP; i += NT) {
-            const int ai = i / KP, k = i - ai * KP;
-            const int t = s.act_list[ai];
-            const int po = t * POSE_F + k * 3, vo = t * 34 + k * 2;
-            const float x = g_poses[po], y = g_poses[po + 1], cf = g_poses[po + 2];
-            const float vx = g_vel[vo], vy = g_vel[vo + 1];
-            const float dt = 1.0f;
-            const float px = x + vx * dt, py = y + vy * dt;
-            g_pred[po] = px; g_pred[po + 1] = py; g_pred[po + 2] = cf;
-            if (P.pred_in_smem) { s.pred[po] = px; s.pred[po + 1] = py; s.pred[po + 2] = cf; }
-            if (s.states[t] == ST_LOST) { g_vel[vo] = vx * 0.95f; g_vel[vo + 1] = vy * 0.95f; }
-            if (k == 0) g_dirty[t] = 1;
-        }
-    }
-    __syncthreads();
-    stamp(1);
-
-    const bool assoc12 = (na > 0) && (D > 0);
-    // ---------------- centres + gates (:1177-1208, kernels :196-317) ----------------
-    if (assoc12) {
-        // track centres: every slot whose predicted pose changed since its centre was derived
-        // (== the reference recomputing all T slots: unchanged slots give unchanged centres)
-#pragma unroll 1
-        for (int t = tid; t < T; t += NT) {
-            if (s.rowbc[t] || (s.active[t] == 1)) {     // predict marks every active slot dirty (below)
-                const float* pp = (P.pred_in_smem && s.active[t] == 1) ? (s.pred + (size_t)t * POSE_F) : (g_pred + (size_t)t * POSE_F);
-                float area;
-                pose_box(pp, &s.tcent[t * 4], &area);
-                s.tarea[t] = area;
-                g_tcent[t * 4] = s.tcent[t * 4]; g_tcent[t * 4 + 1] = s.tcent[t * 4 + 1];
-                g_tcent[t * 4 + 2] = s.tcent[t * 4 + 2]; g_tcent[t * 4 + 3] = s.tcent[t * 4 + 3];
-                g_dirty[t] = 0;
-            }
-        }
-#pragma unroll 1
-        for (int ai = tid - (NT >> 1); ai >= 0 && ai < na; ai += (NT >> 1)) {   // mean torso speed per active row (:287-298), upper half of the CTA
-            const int t = s.act_list[ai];
-            const int torso[4] = {5, 6, 11, 12};
-            float av = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float vx = g_vel[t * 34 + torso[i] * 2], vy = g_vel[t * 34 + torso[i] * 2 + 1];
-                av += sqrtf(vx * vx + vy * vy);
-            }
-            s.tav[t] = av * 0.25f;
-        }
-    }
-    __syncthreads();
-    if (assoc12) {
-        // gate (base 3.0) minus LOST rows (tier 1 mask, :1231) and lost-tier gate (base 3.0*1.3,
-        // only LOST rows survive the two state masks, :1359-1387).  One warp per (row, 32 dets).
-        const int words = (D + 31) / 32;
-#pragma unroll 1
-        for (int i = c.warp; i < na * words; i += c.nwarps) {
-            const int ai = fast_div(i, c.magicW), w = i - ai * words;
-            const int t = s.act_list[ai];
-            const int d = w * 32 + c.lane;
-            const bool lost = (s.states[t] == ST_LOST);
-            const float base = lost ? (3.0f * 1.3f) : 3.0f;
-            bool g = false;
-            if (d < D) g = gate_cell(&s.tcent[t * 4], &s.dcent[d * 4], s.tav[t], lost, base, P.gating_enabled != 0);
-            const unsigned bm = __ballot_sync(FULLM, g);
-            if (c.lane == 0) { if (lost) s.lgate[t * Dw + w] = bm; else s.gate[t * Dw + w] = bm; }
-        }
-    }
-    __syncthreads();
-    stamp(2);
-
-    // ---------------- tiers 1-3 (:1210-1274, :1276-1335, :1337-1436) ----------------
-    // One rolled loop: a single copy of the cost passes, the auction and the lock in the instruction
-    // stream (the kernel runs each of them once or a few times per launch, from a cold instruction cache).
-#pragma unroll 1
-    for (int tier = 0; tier < 3; ++tier) {
-        const bool run = (tier < 2) ? assoc12 : (D > 0);
-        if (run) {
-            if (tier > 0) backup_assign(c);
-            if (tier == 0) {
-                cost_pass_oks(c, s.gate, na, 0.2f);
-                stamp(12);
-            } else if (tier == 1) {
-                cost_pass_torso(c, s.gate, na);
-            } else {
-                cost_inactive_rows(c);
-                lock_pairs(c, s.lgate, na);
-                // the lost-tier gate holds bits of LOST rows only (gate stage): without such a row it is empty
-                if (s.misc[6] > 0) cost_pass_oks(c, s.lgate, na, 0.2f);
-            }
-            auction_solve(c, na, tier > 0);
-            if (tier == 0) stamp(13);
-            if (tier > 0) merge_assign(c);
-            if (tier < 2) lock_pairs(c, s.gate, na);
-            if (tier == 0) stamp(14);
-        }
-        stamp(3 + tier);
-    }
-
-    // The predecessor's record assembly reads g_poses after it released the state (second release at its end):
-    // nothing before this point writes g_poses, tb.outputs or the telemetry slots; wait for it here (it finished
-    // long ago unless the launches ran far apart from the usual order).
-    if (tid == 0) {
-        const int want = P.seq - 1;
-        const unsigned long long w0 = globaltimer_ns();
-        for (;;) {
-            int v;
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(tb.out_done + b) : "memory");
-            if (v - want >= 0) break;
-            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; break; }
-        }
-    }
-    __syncthreads();
-    if (s.misc[10]) {       // see the first wait: no update, no records; only the prediction scratch has been touched
-        if (tid == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
-        }
-        return;
-    }
-    // ---------------- update matched (:1438-1472, kernels :141-189, :612-648) -------------
-    if (D > 0) {
-        const float process_noise = 0.1f, measurement_noise = 0.3f;
-        const float K = measurement_noise / (measurement_noise + process_noise);
-        const float alpha = 0.3f;
-#pragma unroll 1
-        for (int i = tid; i < na * KP; i += NT) {
-            const int ai = i / KP, k = i - ai * KP;
-            const int t = s.act_list[ai];
-            const int d = s.row[t];
-            if (d < 0) continue;
-            const int to = t * POSE_F + k * 3, vo = t * 34 + k * 2;
-            const float* dp = c.det + (size_t)d * POSE_F + k * 3;
-            const float ox = g_poses[to], oy = g_poses[to + 1];
-            const float zx = dp[0], zy = dp[1], zc = dp[2];
-            const float nx = ox + K * (zx - ox);
-            const float ny = oy + K * (zy - oy);
-            const float dx = zx - ox, dy = zy - oy;
-            g_vel[vo] = alpha * dx + (1 - alpha) * g_vel[vo];
-            g_vel[vo + 1] = alpha * dy + (1 - alpha) * g_vel[vo + 1];
-            g_poses[to] = nx; g_poses[to + 1] = ny; g_poses[to + 2] = zc;
-        }
-#pragma unroll 1
-        for (int ai = tid; ai < na; ai += NT) {
-            const int t = s.act_list[ai];
-            const int d = s.row[t];
-            if (d < 0) continue;
-            g_scores[t] = s.dscore[d];
-            const int h = s.hits[t] + 1;
-            s.hits[t] = h;
-            s.ages[t] = 0;
-            g_last[t] = P.frame_id;
-            const int st = s.states[t];
-            if (st == ST_TENTATIVE && h >= P.min_hits) s.states[t] = ST_CONFIRMED;
-            else if (st == ST_LOST) s.states[t] = ST_CONFIRMED;
-        }
-    }
-    __syncthreads();
-    stamp(6);
-
-    // ---------------- age unmatched (:1474-1487, kernel :651-688) ----------------
-#pragma unroll 1
-    for (int ai = tid; ai < na; ai += NT) {
-        const int t = s.act_list[ai];
-        if (s.row[t] >= 0) continue;
-        const int age = s.ages[t] + 1;
-        s.ages[t] = age;
-        const int st = s.states[t];
-        if (st == ST_TENTATIVE) { if (age > 2) s.active[t] = 0; }
-        else if (st == ST_CONFIRMED) { if (age > P.max_age) s.states[t] = ST_LOST; }
-        else if (st == ST_LOST) { if (age > P.max_age + 10) s.active[t] = 0; }
-    }
-    __syncthreads();
-    stamp(7);
-
-    // ---------------- new tracks (:1489-1526; R3/R4: ascending detection order) ------------
-    if (D > 0) {
-        // which detections start a track?  (unmatched and score >= new_track_thresh.)  Usually none: warp 0 finds that out
-        // with ballots and the serial pass below, the pose copies and a barrier are skipped.
-        if (tid < 32) {
-            unsigned any = 0u;
-#pragma unroll 1
-            for (int base = 0; base < D; base += 32) {
-                const int d = base + c.lane;
-                bool q = false;
-                if (d < D) { s.slot_for_det[d] = -1; q = s.col[d] < 0 && !(s.dscore[d] < P.new_track_thresh); }
-                any |= __ballot_sync(FULLM, q);
-            }
-            if (c.lane == 0) s.misc[7] = any != 0u;
-        }
-        __syncthreads();
-        const bool newborn = s.misc[7] != 0;
-        if (newborn && tid == 0) {
-            int hint = g_scal[1], next_id = g_scal[0];
-            for (int d = 0; d < D; ++d) {
-                if (s.col[d] >= 0) continue;
-                if (s.dscore[d] < P.new_track_thresh) continue;
-                const int start = hint % T;
-                ++hint;
-                for (int i = 0; i < T; ++i) {
-                    int sl = start + i; if (sl >= T) sl -= T;
-                    if (s.active[sl] == 0) { s.active[sl] = 1; s.slot_for_det[d] = sl; break; }
-                }
-                const int sl = s.slot_for_det[d];
-                if (sl >= 0) {
-                    s.ids[sl] = next_id++;
-                    s.hits[sl] = 1; s.ages[sl] = 0; s.states[sl] = ST_TENTATIVE;
-                    g_scores[sl] = s.dscore[d];
-                    g_last[sl] = P.frame_id;
-                    s.col[d] = sl;
-                }
-            }
-            g_scal[1] = hint; g_scal[0] = next_id;
-        }
-        if (newborn) {
-        __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i < D * POSE_F; i += NT) {
-            const int d = i / POSE_F, e = i - d * POSE_F;
-            const int sl = s.slot_for_det[d];
-            if (sl >= 0) g_poses[sl * POSE_F + e] = c.det[(size_t)d * POSE_F + e];
-        }
-#pragma unroll 1
-        for (int i = tid; i < D * 34; i += NT) {
-            const int d = i / 34, e = i - d * 34;
-            const int sl = s.slot_for_det[d];
-            if (sl >= 0) g_vel[sl * 34 + e] = 0.0f;
-        }
-        }
-    }
-    __syncthreads();
-    stamp(8);
-
-    // ---------------- de-duplication (:1528-1557; R5: sequential semantics) ----------------
-    {
-        // misc[1] (eligible count) and misc[2] (duplicate pairs) are still zero from the prologue: nothing else uses them
-        for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {   // eligible list, ascending (ordered like act_list above)
-            auto elig = [&](int t) { return (t < T) && s.active[t] == 1 && s.states[t] != ST_LOST && s.hits[t] >= P.min_hits; };
-            int start = 0;
-            for (int pb = 0; pb < base; pb += 32) start += __popc(__ballot_sync(FULLM, elig(pb + c.lane)));
-            const int t = base + c.lane;
-            const bool e = elig(t);
-            const unsigned bm = __ballot_sync(FULLM, e);
-            if (e) s.elig_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
-            if (c.lane == 0 && base + 32 >= T) s.misc[1] = start + __popc(bm);
-        }
-        __syncthreads();
-        const int ne = s.misc[1];
-#pragma unroll 1
-        for (int i = tid; i < ne * ne; i += NT) {
-            const int ia = i / ne, ib = i - ia * ne;
-            const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
-            if (t1 < t2 && center_iou(&s.tcent[t1 * 4], &s.tcent[t2 * 4]) > 0.7f) {
-                const int pos = atomicAdd(&s.misc[2], 1);
-                if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
-            }
-        }
-        __syncthreads();
-        const int ndup = s.misc[2];
-        if (tid == 0 && ndup > 0) {
-            auto resolve = [&](int t1, int t2) {
-                if (s.active[t1] == 0 || s.active[t2] == 0) return;      // LOST excluded by eligibility
-                if (s.hits[t1] < s.hits[t2] || (s.hits[t1] == s.hits[t2] && s.ids[t1] > s.ids[t2])) s.active[t1] = 0;
-                else s.active[t2] = 0;
-            };
-            if (ndup <= DUP_CAP) {
-                for (int i = 1; i < ndup; ++i) {                         // lexicographic (t1, t2)
-                    const int key = s.dup[i];
-                    int j = i - 1;
-                    while (j >= 0 && s.dup[j] > key) { s.dup[j + 1] = s.dup[j]; --j; }
-                    s.dup[j + 1] = key;
-                }
-                for (int i = 0; i < ndup; ++i) resolve(s.dup[i] >> 16, s.dup[i] & 0xffff);
-            } else {                                                     // overflow: recompute in order
-                for (int ia = 0; ia < ne; ++ia)
-                    for (int ib = 0; ib < ne; ++ib) {
-                        const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
-                        if (t1 < t2 && center_iou(&s.tcent[t1 * 4], &s.tcent[t2 * 4]) > 0.7f) resolve(t1, t2);
-                    }
-            }
-        }
-        __syncthreads();
-    }
-    stamp(9);
-
-    // ---------------- write back state ----------------
-    int cnt_local = 0;
-#pragma unroll 1
-    for (int t = tid; t < T; t += NT) {
-        g_active[t] = s.active[t]; g_states[t] = s.states[t]; g_hits[t] = s.hits[t]; g_ids[t] = s.ids[t];
-        g_ages[t] = s.ages[t];
-        tb.row_assign[(size_t)b * T + t] = s.row[t];
-        cnt_local += (s.active[t] == 1);
-    }
-#pragma unroll 1
-    for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
-    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
-    // block-wide sum of cnt_local (update()'s return value, :1130-1136)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt_local += __shfl_xor_sync(FULLM, cnt_local, off);
-    if (c.lane == 0 && cnt_local) atomicAdd(&s.misc[4], cnt_local);
-    __syncthreads();
-    if (tid == 0) {
-        // ---- first release: the stream's STATE is final; its next frame may go on (see the wait in the prologue).
-        // The TrackOutput records below read g_poses and write tb.outputs; the successor touches neither before its
-        // update stage, where it waits for the second flag (out_done).  The ~2 us of record assembly thus leave
-        // the chain of dependent frames.
-        g_scal[2] = D; g_scal[3] = s.misc[4];
-        g_ns[18] = globaltimer_ns();
-        if (tb.dbg) tb.dbg[((size_t)(P.seq & 63) * P.B + b) * 6 + 2] = g_ns[18];
-        __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
-    }
-
-    // ---------------- outputs: getActiveTracks (:1594-1636) on the device ------------------
-    if (tid < 32) {
-        int count = 0;
-        for (int base = 0; base < D; base += 32) {
-            const int d = base + c.lane;
-            bool emit = false;
-            if (d < D) {
-                const int sl = s.col[d];
-                if (sl >= 0) {
-                    const int st = s.states[sl];
-                    emit = !(st == ST_TENTATIVE && s.hits[sl] < P.min_hits) && (st != ST_LOST);
-                }
-            }
-            const unsigned bm = __ballot_sync(FULLM, emit);
-            if (emit) s.out_list[count + __popc(bm & ((1u << c.lane) - 1u))] = d;
-            count += __popc(bm);
-        }
-        if (c.lane == 0) s.misc[3] = count;
-    }
-    __syncthreads();
-    const int n_out = s.misc[3];
-    {
-        // optional un-letterboxing of the records, scaleTrackOutputs (reference src/main.cpp:48-68):
-        // value = (value - pad) * scale, applied to the box and the keypoints after the box was built
-        const bool xf = tb.out_xform != nullptr;
-        const float sx = xf ? tb.out_xform[b * 4 + 0] : 1.0f, sy = xf ? tb.out_xform[b * 4 + 1] : 1.0f;
-        const float px_ = xf ? tb.out_xform[b * 4 + 2] : 0.0f, py_ = xf ? tb.out_xform[b * 4 + 3] : 0.0f;
-        float* outw = reinterpret_cast<float*>(tb.outputs) + (size_t)b * Dm * 57;
-#pragma unroll 1
-        for (int o = c.warp; o < n_out; o += c.nwarps) {
-            const int d = s.out_list[o];
-            const int sl = s.col[d];
-            float* rec = outw + (size_t)o * 57;
-            float x = 0.f, y = 0.f, cf = 0.f;
-            float lx = 1e9f, ly = 1e9f, hx = -1e9f, hy = -1e9f;
-            if (c.lane < KP) {
-                x = g_poses[sl * POSE_F + c.lane * 3]; y = g_poses[sl * POSE_F + c.lane * 3 + 1]; cf = g_poses[sl * POSE_F + c.lane * 3 + 2];
-                rec[6 + c.lane * 3] = xf ? (x - px_) * sx : x; rec[7 + c.lane * 3] = xf ? (y - py_) * sy : y; rec[8 + c.lane * 3] = cf;
-                if (cf > 0.2f) { lx = x; ly = y; hx = x; hy = y; }
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                lx = pb_min(lx, __shfl_xor_sync(FULLM, lx, off)); ly = pb_min(ly, __shfl_xor_sync(FULLM, ly, off));
-                hx = pb_max(hx, __shfl_xor_sync(FULLM, hx, off)); hy = pb_max(hy, __shfl_xor_sync(FULLM, hy, off));
-            }
-            if (c.lane == 0) {
-                const float px = (hx - lx) * 0.1f, py = (hy - ly) * 0.1f;
-                reinterpret_cast<int*>(rec)[0] = s.ids[sl];
-                rec[1] = s.dscore[d];
-                const float b0 = lx - px, b1 = ly - py, b2 = hx + px, b3 = hy + py;
-                rec[2] = xf ? (b0 - px_) * sx : b0; rec[3] = xf ? (b1 - py_) * sy : b1;
-                rec[4] = xf ? (b2 - px_) * sx : b2; rec[5] = xf ? (b3 - py_) * sy : b3;
-            }
-        }
-    }
-
-    if (tid == 0) {
-        tb.num_outputs[b] = n_out;
-        const unsigned long long now = globaltimer_ns();
-        s.acc[10] = now - t_begin;
-        s.acc[11] = 1ull;
-    }
-    __syncthreads();
-    if (tid < 18 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
-    if (tid == 19 && s.acc[19] != 0ull) g_ns[19] += s.acc[19];
-    // second release: records and telemetry written, g_poses no longer read
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
-    }
+    tracker_body<NTHREADS, ALLSMEM, false>(tb, P, src, blockIdx.x, smem_raw, 0);
 }
 
 __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm, int seq) {
@@ -1070,7 +129,7 @@ cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSourc
         if (e != cudaSuccess) return e;
     }
     p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
-    p.term_floats = plan.term_floats;
+    p.term_floats = plan.term_floats; p.cell_cap = plan.cell_cap;
     p.so = plan.so;
     if (v == 0) pb_tracker_kernel<256, false><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, src);
     else if (v == 1) pb_tracker_kernel<512, false><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, src);
