@@ -53,13 +53,19 @@ typedef struct pb_config {
     int use_cuda_graph;      /* kept for API parity, unused upstream (gpu_tracker.cu:1660) */
     int gating_enabled;      /* extension: 0 replaces the spatial gate by all-ones (config 5) */
     int device;              /* CUDA device ordinal */
-    int pipeline_depth;      /* 1: pb_step runs entirely on the caller's stream.  2..8: pb_step
+    int pipeline_depth;      /* 1: pb_step runs entirely on the caller's stream.  2..12: pb_step
                               * overlaps consecutive steps on internal streams (see pb_join) */
     int keypoint_fetch;      /* 0 (default): the NMS kernel fetches keypoints lazily (IoU rule first, keypoints
                               * only for the ranks whose OKS tests are unavoidable) iff the head is read in
                               * place from host memory (pb_step_host); 1: always lazy; 2: never (complete
                               * sweep); 3: complete records, but the lazy sweep's evaluation order (OKS tests
                               * deferred until a rank's own tile; ~12 % faster on dense 1280x1280 crowds) */
+    int fuse_stages;         /* NMS and tracker update of a stream-frame in ONE CTA (fused.cu: kept detections handed over in
+                              * shared memory, shared memory sized by the candidates present so that two stream-CTAs share an
+                              * SM, frames of a video stream handed from CTA to CTA through a chain word): 1 wherever the tables
+                              * allow it, 0 never (separate NMS and tracker kernels), 2 (default) where it is the faster plan —
+                              * measured on B200: more than 74 streams per handle, where two one-CTA-per-SM tracker grids no
+                              * longer fit the device side by side.  Same results either way. */
 } pb_config;
 
 /* TrackerTiming (gpu_tracker.h:29-41), filled from device timestamps. */

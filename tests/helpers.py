@@ -27,3 +27,9 @@ def compare_state(got: dict, ref: dict, D: int, T: int, where="") -> list:
     if not np.array_equal(got["scalars"], ref["scalars"]):
         bad.append(f"{where} scalars differ: got {got['scalars']} ref {ref['scalars']}")
     return bad
+
+
+def valid_records(out, counts) -> bytes:
+    """The TrackOutput records a handle reports ([B, Dm] buffer + counts): only the first counts[b] of every stream are defined
+    (pipelined handles keep one record buffer per ring slot, so what lies behind them differs from a serial handle's)."""
+    return b"".join(out[b, : counts[b]].tobytes() for b in range(len(counts)))

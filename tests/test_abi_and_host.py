@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(pb):
 
 
 def test_struct_layouts_match_header(pb):
-    assert C.sizeof(pb.PbConfig) == 17 * 4
+    assert C.sizeof(pb.PbConfig) == 18 * 4
     assert pb.default_config().pipeline_depth == 1
     assert C.sizeof(pb.PbTiming) == 10 * 8 + 8
     assert pb.TRACK_OUTPUT.itemsize == 228 and pb.POSE_DETECTION.itemsize == 224

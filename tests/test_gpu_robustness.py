@@ -4,6 +4,8 @@ two devices in one process, argument validation of the Python binding."""
 import numpy as np
 import pytest
 
+from helpers import valid_records
+
 pytestmark = pytest.mark.gpu
 
 
@@ -50,7 +52,7 @@ def test_pipelined_steps_with_detections_in_global_scratch(pb, orc, cuda):
     piped.join(); torch.cuda.synchronize()
     o1, c1 = serial.get_tracks_all(); o2, c2 = piped.get_tracks_all()
     assert np.array_equal(c1, c2) and c1.sum() > 0
-    assert o1.tobytes() == o2.tobytes()
+    assert valid_records(o1, c1) == valid_records(o2, c2)
     assert serial.state_save()[24:] == piped.state_save()[24:]
     trk = orc.Tracker(max_tracks=128, max_detections=1024, max_age=4)
     dets = [orc.postprocess(host[f, 5]) for f in range(F)]
@@ -59,7 +61,8 @@ def test_pipelined_steps_with_detections_in_global_scratch(pb, orc, cuda):
     assert trk.get_tracks().tobytes() == o2[5, :c2[5]].tobytes()
 
 
-def test_foreign_kernel_filling_the_sms_beside_pipelined_steps(pb, cuda):
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_foreign_kernel_filling_the_sms_beside_pipelined_steps(pb, cuda, fuse):
     """The drop-in site has a TensorRT engine on the same GPU: long foreign kernels that fill every SM run on
     another stream while pipelined steps (tracker CTAs spinning on their predecessors' flags) are in flight.
     Results must equal the serial path's and no time-out may be reported."""
@@ -67,11 +70,11 @@ def test_foreign_kernel_filling_the_sms_beside_pipelined_steps(pb, cuda):
     B, F, STEPS = 64, 16, 96
     scfg = pb.synth_config(canvas=640, persons=16, period=F, occlusion=1)
     heads = torch.from_numpy(pb.synth_heads(scfg, 50, B, 0, F, frame_major=True)).cuda()
-    serial = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+    serial = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, fuse_stages=0)
     for f in range(STEPS):
         serial.step(heads[f % F], f)
     o1, c1 = serial.get_tracks_all()
-    piped = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=5)
+    piped = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=5, fuse_stages=fuse)
     side = torch.cuda.Stream()
     a = torch.randn(8192, 8192, device="cuda")
     big = torch.empty(1 << 28, device="cuda")
@@ -84,7 +87,7 @@ def test_foreign_kernel_filling_the_sms_beside_pipelined_steps(pb, cuda):
     piped.join(); torch.cuda.synchronize()
     piped.wait()                                   # raises if a tracker CTA gave up waiting for its predecessor
     o2, c2 = piped.get_tracks_all()
-    assert np.array_equal(c1, c2) and o1.tobytes() == o2.tobytes()
+    assert np.array_equal(c1, c2) and valid_records(o1, c1) == valid_records(o2, c2)
     assert serial.state_save()[24:] == piped.state_save()[24:]
 
 
@@ -109,7 +112,7 @@ def test_two_handles_on_two_devices_in_one_process(pb, cuda):
         p1.step(h1[f], f, stream=s1)
     p1.join(stream=s1)
     o0, c0 = p0.get_tracks_all(); o1, c1 = p1.get_tracks_all()
-    assert np.array_equal(c0, c1) and c0.sum() > 0 and o0.tobytes() == o1.tobytes()
+    assert np.array_equal(c0, c1) and c0.sum() > 0 and valid_records(o0, c0) == valid_records(o1, c1)
     assert p0.state_save()[24:] == p1.state_save()[24:]
     # the stand-alone entry points with large shared-memory requests on the second device
     torch.cuda.set_device(0)

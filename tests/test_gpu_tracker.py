@@ -11,12 +11,12 @@ pytestmark = pytest.mark.gpu
 
 
 def run_sequence(pb, orc, torch, B, F, canvas=640, persons=20, period=64, occlusion=0, clumps=0, T=128, Dm=64,
-                 max_age=10, min_hits=3, gating=1, stream0=0, check_state_every=1):
+                 max_age=10, min_hits=3, gating=1, stream0=0, check_state_every=1, fuse=2):
     cfg = pb.synth_config(canvas=canvas, persons=persons, period=period, occlusion=occlusion, clumps=clumps,
                           kp_drop_prob=0.15 if clumps else 0.05)
     heads = pb.synth_heads(cfg, stream0, B, 0, F, frame_major=True)
     pipe = pb.Pipeline(num_streams=B, num_anchors=cfg.num_anchors, max_tracks=T, max_detections=Dm, max_age=max_age,
-                       min_hits=min_hits, gating_enabled=gating)
+                       min_hits=min_hits, gating_enabled=gating, fuse_stages=fuse)
     trk = [orc.Tracker(max_tracks=T, max_detections=Dm, max_age=max_age, min_hits=min_hits, gating_enabled=gating)
            for _ in range(B)]
     d = torch.from_numpy(heads).cuda()
@@ -39,12 +39,14 @@ def run_sequence(pb, orc, torch, B, F, canvas=640, persons=20, period=64, occlus
     return n_out
 
 
-def test_config1_like_sequence(pb, orc, cuda):
-    assert run_sequence(pb, orc, cuda, B=3, F=48) > 1000
+@pytest.mark.parametrize("fuse", [0, 1])        # separate NMS / tracker kernels, fused per-stream kernel
+def test_config1_like_sequence(pb, orc, cuda, fuse):
+    assert run_sequence(pb, orc, cuda, B=3, F=48, fuse=fuse) > 1000
 
 
-def test_occlusion_lost_and_recovery(pb, orc, cuda):
-    assert run_sequence(pb, orc, cuda, B=4, F=90, period=90, occlusion=1, max_age=5) > 1000
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_occlusion_lost_and_recovery(pb, orc, cuda, fuse):
+    assert run_sequence(pb, orc, cuda, B=4, F=90, period=90, occlusion=1, max_age=5, fuse=fuse) > 1000
 
 
 def test_dense_crowd_1280(pb, orc, cuda):
@@ -55,8 +57,17 @@ def test_small_tables_force_truncation_and_slot_reuse(pb, orc, cuda):
     assert run_sequence(pb, orc, cuda, B=2, F=40, persons=20, T=16, Dm=12, max_age=2, occlusion=1, period=40) > 50
 
 
-def test_min_hits_one_and_gating_off(pb, orc, cuda):
-    assert run_sequence(pb, orc, cuda, B=2, F=24, persons=10, min_hits=1, gating=0) > 100
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_min_hits_one_and_gating_off(pb, orc, cuda, fuse):
+    assert run_sequence(pb, orc, cuda, B=2, F=24, persons=10, min_hits=1, gating=0, fuse=fuse) > 100
+
+
+def test_fused_kernel_spill_path(pb, orc, cuda, monkeypatch):
+    """Fused per-stream kernel with a shared-memory tier of 64 candidates: streams with more candidates keep the NMS stage's
+    per-candidate arrays in their global scratch (the spill path), the others in shared memory, in the same launch."""
+    monkeypatch.setenv("PB_FUSED_TIER", "64")
+    assert run_sequence(pb, orc, cuda, B=4, F=16, persons=14, fuse=1) > 300
+    assert run_sequence(pb, orc, cuda, B=2, F=6, persons=4, fuse=1) > 10          # below the tier: the shared-memory path
 
 
 def test_direct_detections_with_empty_and_varying_frames(pb, orc, cuda):

@@ -8,6 +8,7 @@ B, F = 64, 16
 scfg = pb.synth_config(canvas=640, persons=20, period=32)
 d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, F, frame_major=True)).cuda()
 pipe = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors)
+print("env", {k: v for k, v in os.environ.items() if k.startswith("PB_")})
 for f in range(32): pipe.step(d[f % F], f)
 prev = pipe.stream_stage_ns().astype(np.int64)
 rows = []
@@ -23,6 +24,7 @@ for i, n in names.items():
 tot = a[:, :, 10]
 worst = np.unravel_index(tot.argmax(), tot.shape)
 print("worst stream-frame:", worst, {n: round(float(a[worst[0], worst[1], i]), 2) for i, n in names.items()})
+print("post stages us:", pipe.post_stage_us())
 na = pipe.get_num_active()
 print("num_active per stream: min", na.min(), "max", na.max())
 tot = a[:, :, 10]                       # [frames, B] us

@@ -44,7 +44,7 @@ class PbConfig(C.Structure):
                 ("match_threshold", C.c_float), ("high_thresh", C.c_float), ("low_thresh", C.c_float),
                 ("new_track_thresh", C.c_float), ("max_age", C.c_int), ("min_hits", C.c_int),
                 ("use_cuda_graph", C.c_int), ("gating_enabled", C.c_int), ("device", C.c_int),
-                ("pipeline_depth", C.c_int), ("keypoint_fetch", C.c_int)]
+                ("pipeline_depth", C.c_int), ("keypoint_fetch", C.c_int), ("fuse_stages", C.c_int)]
 
 
 class PbTiming(C.Structure):

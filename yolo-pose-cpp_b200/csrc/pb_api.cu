@@ -52,6 +52,8 @@ using namespace pb;
 struct PipeSlot {
     PostBuffers post{};
     CandScratch cand{};
+    void* outputs = nullptr;       // [B,Dm] TrackOutput of the step that used this slot (a read-back may still be copying them
+    int* num_outputs = nullptr;    //  while the next step's tracker already assembles its own)
     cudaEvent_t ev_gather = nullptr, ev_nms = nullptr, ev_trk = nullptr;
     bool used = false;
 };
@@ -64,6 +66,11 @@ struct pb_handle_st {
     int cur = 0;
     bool inflight = false;         // work of a pipelined pb_step may still run on the internal streams
     cudaStream_t s_nms = nullptr, s_trk = nullptr, s_trk2 = nullptr, s_trk3 = nullptr;   // lanes: step i's NMS and tracker run on lane i % lanes
+    cudaStream_t f_lane[2 * PB_MAX_RING] = {};   // fused path: step i's kernel runs on f_lane[i % f_lanes]
+    int f_lanes = 1;
+    cudaStream_t s_rb = nullptr;   // fused path: read-back copies (pb_submit_host), ordered behind every kernel that can write the step's records
+    RingTable rtab{};
+    bool borrow_until_wait = false;   // pb_submit_host: the head buffer belongs to the library until pb_wait, no ordering on the caller's stream needed
     int lanes = 0;                 // number of lanes (0: NMS on s_nms, trackers alternate between s_trk and s_trk2)
     int trk_seq = 0;               // sequence number of the last tracker launch (TrackParams::seq)
     cudaStream_t last_trk_stream = nullptr;
@@ -72,6 +79,8 @@ struct pb_handle_st {
     DecodePlan dplan{};
     TrackBuffers trk{};
     TrackerPlan plan{};
+    FusedPlan fplan{};             // fused per-stream kernel (fused.cu); fplan.ok == false: separate NMS and tracker kernels
+    unsigned char* d_spill = nullptr;
     std::vector<void*> allocs;
     // host-buffer path
     float* d_stage = nullptr;      // [B,56,N] device staging
@@ -172,6 +181,7 @@ void pb_default_config(pb_config* c) {
     c->device = 0;
     c->pipeline_depth = 1;
     c->keypoint_fetch = 0;
+    c->fuse_stages = 2;
 }
 
 static int build_handle(pb_handle_st* h) {
@@ -194,6 +204,10 @@ static int build_handle(pb_handle_st* h) {
         PB_TRY(dev_alloc(h, &sl.cand.records, nsc * HEAD_ROWS));
         PB_TRY(dev_alloc(h, &sl.cand.anchors, nsc));
         PB_TRY(dev_alloc(h, &sl.cand.counts, B * (size_t)h->dplan.nseg));
+        unsigned char* outp = nullptr;
+        PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
+        sl.outputs = outp;
+        PB_TRY(dev_alloc(h, &sl.num_outputs, B));
         PB_CUDA(cudaEventCreateWithFlags(&sl.ev_gather, cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&sl.ev_nms, cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&sl.ev_trk, cudaEventDisableTiming));
@@ -204,6 +218,8 @@ static int build_handle(pb_handle_st* h) {
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk2, cudaStreamNonBlocking));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_trk3, cudaStreamNonBlocking));
+        for (int i = 0; i < h->f_lanes; ++i) PB_CUDA(cudaStreamCreateWithFlags(&h->f_lane[i], cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_rb, cudaStreamNonBlocking));
     }
     TrackBuffers& t = h->trk;
     PB_TRY(dev_alloc(h, &t.poses, B * T * POSE_F));
@@ -224,21 +240,37 @@ static int build_handle(pb_handle_st* h) {
     PB_TRY(dev_alloc(h, &t.row_assign, B * T));
     PB_TRY(dev_alloc(h, &t.col_assign, B * Dm));
     PB_TRY(dev_alloc(h, &t.scalars, B * 4));
-    PB_TRY(dev_alloc(h, &t.num_outputs, B));
+    t.outputs = h->ring[0].outputs; t.num_outputs = h->ring[0].num_outputs;
     PB_TRY(dev_alloc(h, &t.det_poses_scratch, B * Dm * POSE_F));
     PB_TRY(dev_alloc(h, &t.stage_ns, B * 20));
     PB_TRY(dev_alloc(h, &t.seq_done, B));
     PB_TRY(dev_alloc(h, &t.out_done, B));
     PB_TRY(dev_alloc(h, &t.error_flag, 1));
+    PB_TRY(dev_alloc(h, &t.chain, B));
+    h->rtab.depth = (int)h->ring.size();
+    {   // CTAs that wait for their turn hold an SM slot each: wait_window * num_streams stays below the SM count
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int w = 2;
+        while (w > 0 && (long)w * c.num_streams >= sms) --w;
+        if (h->rtab.depth < 2) w = 0;
+        if (const char* e = getenv("PB_FUSED_WAIT")) { const int a = atoi(e); if (a >= 0 && a <= 14) w = a; }
+        h->rtab.wait_window = w;
+    }
+    for (size_t i = 0; i < h->ring.size(); ++i) {
+        PipeSlot& sl = h->ring[i];
+        h->rtab.det_poses[i] = sl.post.det_poses; h->rtab.det_scores[i] = sl.post.det_scores; h->rtab.num_keep[i] = sl.post.num_keep;
+        h->rtab.outputs[i] = sl.outputs; h->rtab.num_outputs[i] = sl.num_outputs;
+        PB_TRY(dev_alloc(h, &h->rtab.frame_id[i], B));
+    }
     if (getenv("PB_TIMELINE")) {                       // development aid: absolute begin/end times of the last 64 launches
         PB_TRY(dev_alloc(h, &t.dbg, (size_t)64 * B * 6));
         for (PipeSlot& sl : h->ring) sl.post.dbg = t.dbg;
         h->post.dbg = t.dbg;
     }
-    unsigned char* outp = nullptr;
-    PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
-    t.outputs = outp;
     h->plan = tracker_plan(c.max_tracks, c.max_detections);
+    if (h->fplan.ok && h->fplan.spill_stride) PB_TRY(dev_alloc(h, &h->d_spill, B * h->fplan.spill_stride));
     PB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     PB_CUDA(launch_tracker_reset(h->trk, c.num_streams, c.max_tracks, c.max_detections, h->trk_seq, h->own_stream));
     PB_CUDA(cudaStreamSynchronize(h->own_stream));
@@ -259,8 +291,9 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
         return PB_ERR_UNSUPPORTED;
     }
     if (c.max_keep > c.max_candidates) { pb_set_error("pb_create: max_keep > max_candidates"); return PB_ERR_INVALID; }
+    if (c.fuse_stages < 0 || c.fuse_stages > 2) { pb_set_error("pb_create: fuse_stages must be 0, 1 or 2"); return PB_ERR_INVALID; }
     if (c.keypoint_fetch < 0 || c.keypoint_fetch > 3) { pb_set_error("pb_create: keypoint_fetch must be 0..3"); return PB_ERR_INVALID; }
-    if (c.pipeline_depth < 1 || c.pipeline_depth > 8) { pb_set_error("pb_create: pipeline_depth must be 1..8"); return PB_ERR_INVALID; }
+    if (c.pipeline_depth < 1 || c.pipeline_depth > PB_MAX_RING) { pb_set_error("pb_create: pipeline_depth must be 1..%d", PB_MAX_RING); return PB_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c.device) {
         (void)cudaGetLastError();
@@ -292,6 +325,16 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     if (!h) { pb_set_error("pb_create: out of host memory"); return PB_ERR_INVALID; }
     h->cfg = c;
     h->lazy_keypoints = (c.keypoint_fetch == 1);
+    // fused per-stream kernel: always when asked for (1); by default (2) where it measured faster than the three-kernel step —
+    // handles whose tracker grids cannot overlap (2 * num_streams > SM count): 128 streams 1.95 M against 1.55 M stream-frames/s,
+    // 148 streams 2.30 M against 2.02 M; 64 streams 1.88 M against 2.04 M, one stream 25 us against 22 us per frame
+    const bool want_fused = c.fuse_stages == 1 || (c.fuse_stages == 2 && 2 * c.num_streams > prop.multiProcessorCount) || getenv("PB_FORCE_FUSED");
+    if (want_fused && !getenv("PB_NO_FUSED"))
+        h->fplan = plan_fused(c.max_tracks, c.max_detections, c.max_candidates, c.max_keep, (size_t)prop.sharedMemPerBlockOptin);
+    if (getenv("PB_DEBUG_PLAN"))
+        fprintf(stderr, "[pb] fused plan: ok %d threads %d tier %d smem %zu (tracker %zu, prefix %zu) spill/stream %zu | separate: nms %zu tracker %zu\n",
+                (int)h->fplan.ok, h->fplan.threads, h->fplan.CT, h->fplan.smem_bytes, h->fplan.tk.smem_bytes, h->fplan.tk.prefix_bytes,
+                h->fplan.spill_stride, decode_nms_smem_bytes(c.max_candidates, c.max_keep), tracker_plan(c.max_tracks, c.max_detections).smem_bytes);
     h->overlap_trackers = 2 * c.num_streams <= prop.multiProcessorCount && !getenv("PB_NO_TRACKER_OVERLAP");
     // Lanes: the oldest tracker grid in flight never waits, the younger ones may spin on their predecessors and
     // hold one SM per CTA while they do: (lanes - 1) * num_streams must stay below the SM count.
@@ -299,6 +342,12 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     // Measured at 64 streams: three lanes 37.0 us per batch, two lanes 44.8 (a step's NMS then waits for the tracker two
     // steps back), the separate NMS stream 38-40.
     if (h->overlap_trackers && 2 * c.num_streams < prop.multiProcessorCount && c.pipeline_depth >= 4) h->lanes = 3;
+    if (h->fplan.ok && c.pipeline_depth >= 2) {
+        // fused path: nobody waits on the device (chain hand-off, fused.cu), so the number of steps in flight is not bounded
+        // by the SM count; one ring slot stays free so that a step's decode does not wait for the oldest step in flight
+        h->f_lanes = 2 * c.pipeline_depth;         // streams are cheap: a lane is never what a step waits for (the ring slot is)
+        if (const char* e = getenv("PB_FUSED_LANES")) { const int l = atoi(e); if (l >= 1 && l <= 2 * PB_MAX_RING) h->f_lanes = l; }
+    }
     if (const char* e = getenv("PB_LANES")) {
         const int l = atoi(e);
         if (l >= 0 && l <= 3 && (l <= 1 || (l - 1) * c.num_streams < prop.multiProcessorCount)) h->lanes = l;
@@ -322,6 +371,8 @@ int pb_destroy(pb_handle_t h) {
     if (h->s_trk) cudaStreamDestroy(h->s_trk);
     if (h->s_trk2) cudaStreamDestroy(h->s_trk2);
     if (h->s_trk3) cudaStreamDestroy(h->s_trk3);
+    for (cudaStream_t q : h->f_lane) if (q) cudaStreamDestroy(q);
+    if (h->s_rb) cudaStreamDestroy(h->s_rb);
     for (PipeSlot& sl : h->ring) {
         if (sl.ev_gather) cudaEventDestroy(sl.ev_gather);
         if (sl.ev_nms) cudaEventDestroy(sl.ev_nms);
@@ -356,6 +407,8 @@ int pb_join(pb_handle_t h, pb_stream_t stream) {
     return join_on(h, (cudaStream_t)stream);
 }
 
+static int nms_sweep_mode(const pb_handle_st* h) { return h->lazy_keypoints ? 1 : (h->cfg.keypoint_fetch == 3 ? 2 : 0); }
+
 int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, pb_stream_t stream) {
     if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
@@ -368,7 +421,7 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
         cudaEventRecord(h->ev_pool[em], (cudaStream_t)stream);
         h->ev_gather.push_back({e0, em});
     }
-    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
         h->ev_post.push_back({e0, e1});
@@ -424,6 +477,65 @@ static int enqueue_readback(pb_handle_st* h, cudaStream_t stream) {
     return PB_OK;
 }
 
+
+// Fused step: decode+gather on the caller's stream (the only reader of the borrowed head tensor unless the sweep is lazy),
+// then ONE launch per step — NMS and tracker of every stream-frame in one CTA (fused.cu) — on lane (step mod lanes).  The
+// kernels of up to `lanes` steps are in flight; each video stream's frames stay in order through its chain word: a CTA
+// whose stream is still busy with an earlier frame leaves its kept detections in the step's ring slot and exits, the CTA
+// that holds the chain goes on with them.  Hence: every tracker stage of steps <= i has run when the kernels of ALL steps
+// <= i have completed, which is what the events below express (ev_trk: the step's kernel; ev_nms: the step is complete
+// for the host, including a read-back).  Ring slot = sequence number mod depth; the caller's stream waits for the slot's
+// previous step — and, one step after the other, for every older one — before the decode kernel reuses its scratch.
+static int step_fused(pb_handle_st* h, const float* d_heads, float conf, float nms, int frame_id, cudaStream_t stream) {
+    const pb_config& c = h->cfg;
+    const bool piped = c.pipeline_depth > 1;
+    TrackParams tp = track_params(h, frame_id);
+    const int depth = (int)h->ring.size();
+    const int pos = tp.seq % depth;
+    PipeSlot& sl = h->ring[pos];
+    if (piped && sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));      // the slot's scratch, kept detections and records are free again
+    cudaStream_t ts = stream;
+    static const bool decode_on_lane = getenv("PB_DECODE_ON_LANE") != nullptr;      // experiment: relaxed borrow of the head tensor
+    if (!(piped && decode_on_lane))
+        PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, sl.cand, stream));
+    if (piped) {
+        ts = h->f_lane[tp.seq % h->f_lanes];
+        PB_CUDA(cudaEventRecord(sl.ev_gather, stream));
+        PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_gather, 0));
+        if (decode_on_lane)
+            PB_CUDA(launch_decode_gather(d_heads, c.num_streams, c.num_anchors, conf, h->lazy_keypoints, h->dplan, sl.cand, ts));
+    }
+    sl.post.dbg_slot = tp.seq & 63;
+    PB_CUDA(launch_fused(h->fplan, d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan,
+                         sl.cand, sl.post, h->d_spill, h->trk, tp, h->rtab, ts));
+    h->trk_seq = tp.seq;
+    h->trk.outputs = sl.outputs; h->trk.num_outputs = sl.num_outputs;
+    if (piped) {
+        PB_CUDA(cudaEventRecord(sl.ev_trk, ts));
+        cudaStream_t done_on = ts;
+        if (h->rb_tracks) {
+            // the step's records may have been written by the CTA of an older step's kernel on another lane
+            for (int j = 0; j < h->f_lanes && j < depth; ++j) {
+                PipeSlot& o = h->ring[((tp.seq - j) % depth + depth) % depth];
+                if (o.used || j == 0) PB_CUDA(cudaStreamWaitEvent(h->s_rb, o.ev_trk, 0));
+            }
+            PB_TRY(enqueue_readback(h, h->s_rb));
+            done_on = h->s_rb;
+        }
+        PB_CUDA(cudaEventRecord(sl.ev_nms, done_on));
+        // a lazy sweep fetches keypoints from the borrowed head tensor inside the fused kernel: later work on the caller's
+        // stream is ordered behind it (not needed when the buffer is the library's until pb_wait: pb_submit_host)
+        if (h->lazy_keypoints && !h->borrow_until_wait) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_trk, 0));
+        h->inflight = true;
+    } else {
+        PB_TRY(enqueue_readback(h, ts));
+    }
+    sl.used = true;
+    h->cur = pos; h->post = sl.post; h->cand = sl.cand;
+    h->frames++;
+    return PB_OK;
+}
+
 // Pipelined step (pipeline_depth > 1): the three kernels of one step run on three streams —
 // decode+gather on the caller's (it is the only reader of the borrowed head tensor), NMS and
 // tracker on internal ones — chained by events, with `depth` slots of candidate scratch and
@@ -460,7 +572,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
     sl.post.dbg_slot = tp.seq & 63;
-    PB_CUDA(launch_nms(d_heads, c.num_anchors, h->lazy_keypoints ? 1 : (c.keypoint_fetch == 3 ? 2 : 0), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
+    PB_CUDA(launch_nms(d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
     PB_CUDA(cudaEventRecord(sl.ev_nms, ns));
     // the lazy NMS sweep fetches keypoints from the borrowed head tensor: later work on the caller's
     // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it then.
@@ -486,6 +598,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
 int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int frame_id, pb_stream_t stream) {
     if (!h || !d_heads) { pb_set_error("pb_step: null argument"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
+    if (h->fplan.ok && !h->profiling) return step_fused(h, d_heads, conf, nms, frame_id, (cudaStream_t)stream);
     if (h->cfg.pipeline_depth > 1 && !h->profiling) return step_pipelined(h, d_heads, conf, nms, frame_id, (cudaStream_t)stream);
     PB_TRY(pb_postprocess(h, d_heads, conf, nms, stream));
     PB_TRY(pb_tracker_update(h, nullptr, nullptr, nullptr, 0, frame_id, stream));
@@ -618,7 +731,9 @@ int pb_submit_host(pb_handle_t h, const float* h_heads, float conf, float nms, i
     const bool lazy_before = h->lazy_keypoints;
     if (c.keypoint_fetch == 0) h->lazy_keypoints = true;
     h->rb_tracks = h_tracks; h->rb_counts = h_counts;
+    h->borrow_until_wait = true;
     const int rc = pb_step(h, static_cast<const float*>(at.devicePointer), conf, nms, frame_id, (pb_stream_t)h->own_stream);
+    h->borrow_until_wait = false;
     h->rb_tracks = nullptr; h->rb_counts = nullptr;
     h->lazy_keypoints = lazy_before;
     return rc;

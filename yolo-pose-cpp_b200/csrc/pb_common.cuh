@@ -68,6 +68,7 @@ struct TrackBuffers {
     int* seq_done;       // [B] sequence number of the last tracker launch whose STATE update this stream has completed (see pb_tracker_kernel)
     int* out_done;       // [B] ... whose TrackOutput records are written as well (second release)
     int* error_flag;     // [1] set when a stream's predecessor did not finish within the time-out
+    unsigned long long* chain;   // [B] fused path: who runs the stream's next tracker stage — (published-NMS mask << 32) | next seq << 1 | busy
     unsigned long long* dbg;   // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [0] begin, [1] state acquired, [2] end
 };
 
@@ -126,6 +127,34 @@ TrackerPlan tracker_plan(int T, int Dm, bool compact = false);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);
 cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, int seq, cudaStream_t stream);
+
+// Ring of per-step buffers as the fused kernel sees it: a CTA that owns its stream's chain goes on with the following
+// frames, whose kept detections were published by other CTAs in their steps' slots (slot = seq % depth).
+constexpr int PB_MAX_RING = 12;            // <= 15: the chain word holds a 15-bit mask of published frames
+struct RingTable {
+    const float* det_poses[PB_MAX_RING];   // [B, Kcap, 51]
+    const float* det_scores[PB_MAX_RING];  // [B, Kcap]
+    const int* num_keep[PB_MAX_RING];      // [B]
+    void* outputs[PB_MAX_RING];            // [B, Dm] TrackOutput
+    int* num_outputs[PB_MAX_RING];         // [B]
+    int* frame_id[PB_MAX_RING];            // [B] frame id of the step whose NMS stage published into this slot
+    int depth;
+    int wait_window;                       // a CTA whose frame is fewer than this many frames from the head of its chain waits for its turn (tracker_body.cuh)
+};
+
+// fused per-stream kernel (fused.cu): NMS + tracker of one stream-frame in one CTA
+struct FusedPlan {
+    bool ok;
+    int threads, CT;                    // CTA size; candidates whose NMS working set fits in shared memory (more: spill path)
+    size_t smem_bytes, spill_stride;    // dynamic shared memory per CTA; bytes of spill scratch per stream (0: never spills)
+    unsigned nms_base;
+    SmemOffsets so_small, so_big;
+    TrackerPlan tk;                     // compact tracker layout (detections first)
+};
+FusedPlan plan_fused(int T, int Dm, int max_cand, int max_keep, size_t smem_optin);
+cudaError_t launch_fused(const FusedPlan& fp, const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
+                         const DecodePlan& dp, const CandScratch& cs, const PostBuffers& out, unsigned char* spill,
+                         const TrackBuffers& tb, TrackParams p, const RingTable& ring, cudaStream_t stream);
 
 void count_launch(int n = 1);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it for `func` on the

@@ -82,7 +82,7 @@ template <int NTHREADS, bool ALLSMEM>
 __global__ void __launch_bounds__(NTHREADS)
 pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tracker_body<NTHREADS, ALLSMEM, false>(tb, P, src, blockIdx.x, smem_raw, 0);
+    tracker_body<NTHREADS, ALLSMEM, false>(tb, P, src, blockIdx.x, smem_raw, 0, P.seq, P.frame_id, tb.outputs, tb.num_outputs);
 }
 
 __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm, int seq) {
@@ -102,6 +102,7 @@ __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm, i
         tb.scalars[i * 4 + 0] = 1; tb.scalars[i * 4 + 1] = 0; tb.scalars[i * 4 + 2] = 0; tb.scalars[i * 4 + 3] = 0;
         tb.num_outputs[i] = 0;
         tb.seq_done[i] = seq; tb.out_done[i] = seq;
+        tb.chain[i] = chain_pack(0u, seq + 1, 0);
     }
     if (i == 0) *tb.error_flag = 0;
     if (i < (size_t)B * 20) tb.stage_ns[i] = 0ull;

@@ -269,7 +269,7 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
 // kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.  Only rows that were active at
 // frame start are touched: the cells of inactive rows are never read by the auction (inactive
 // rows do not bid) and are overwritten with 1.0 by the last cost pass of the frame anyway.
-__device__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
+static __device__ __forceinline__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
 #pragma unroll 1
@@ -289,7 +289,7 @@ __device__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
 
 // cost <- 1.0 on inactive rows (:351-354): warp per row.  Only the last writer of a frame matters
 // for these rows (see lock_pairs), so this runs once per frame, in the lost-track tier.
-__device__ void cost_inactive_rows(Ctx& c) {
+static __device__ __forceinline__ void cost_inactive_rows(Ctx& c) {
     TkSmem& s = c.s;
 #pragma unroll 1
     for (int t = c.warp; t < c.T; t += c.nwarps)
@@ -303,7 +303,7 @@ __device__ void cost_inactive_rows(Ctx& c) {
 // exponentials are spread over threads: one thread per (cell, keypoint) evaluates a term into
 // shared memory and one thread per cell adds the terms of its visible keypoints in keypoint
 // order (the reference's summation order) and finishes the cell.
-__device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
+static __device__ __forceinline__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
     int rows_per_chunk = c.cell_cap / D;            // worst case: every cell of the chunk is gated
@@ -378,7 +378,7 @@ __device__ void cost_pass_oks(Ctx& c, const unsigned* gate, int na, float vis) {
 }
 
 // Torso-only OKS (kernelTorsoOKS :455-489): four exponentials per cell, one thread per cell.
-__device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
+static __device__ __forceinline__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw;
 #pragma unroll 1
@@ -391,14 +391,14 @@ __device__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
     __syncthreads();
 }
 
-__device__ void backup_assign(Ctx& c) {      // no barrier: callers synchronise before the next solve
+static __device__ __forceinline__ void backup_assign(Ctx& c) {      // no barrier: callers synchronise before the next solve
     TkSmem& s = c.s;
 #pragma unroll 1
     for (int t = c.tid; t < c.T; t += c.nthreads) s.rowb[t] = s.row[t];
 #pragma unroll 1
     for (int d = c.tid; d < c.D; d += c.nthreads) s.colb[d] = s.col[d];
 }
-__device__ void merge_assign(Ctx& c) {   // kernelMergeAssignments :575-588
+static __device__ __forceinline__ void merge_assign(Ctx& c) {   // kernelMergeAssignments :575-588
     TkSmem& s = c.s;
 #pragma unroll 1
     for (int t = c.tid; t < c.T; t += c.nthreads) if (s.rowb[t] >= 0) s.row[t] = s.rowb[t];
@@ -425,11 +425,102 @@ __device__ __forceinline__ float center_iou(const float* a, const float* b) {   
 // flags are then compile-time constants and every access to them is an LDS instead of a generic load.
 // FUSED: called from the per-stream kernel of fused.cu right after the NMS sweep; this frame's detections (poses,
 // scores) already sit in the tracker's shared-memory arrays and D_fused is their number (<= max_detections).
+// In that kernel the CTA also OWNS the stream's chain of frames (chain word, fused.cu): the previous frame of this video
+// stream is complete, so the two waits below are compiled out.  seq / frame_id / outputs / num_outputs: this frame's
+// sequence number, frame id and record buffers (a fused CTA may go on with later frames of its stream).
+// Chain word (below): bit 0 busy, bits 1..31 next sequence number, bits 32..46 mask of published frames, bits 47..61 mask of
+// waiting frames (bit k of either: frame next + k).
+__host__ __device__ __forceinline__ unsigned long long chain_make(unsigned waiting, unsigned mask, int next, int busy) {
+    return ((unsigned long long)(waiting & 0x7fffu) << 47) | ((unsigned long long)(mask & 0x7fffu) << 32) |
+           ((unsigned long long)((unsigned)next & 0x7fffffffu) << 1) | (unsigned long long)(busy & 1);
+}
+// nothing published, nobody owns the chain, frame `next` is next
+__host__ __device__ __forceinline__ unsigned long long chain_pack(unsigned mask, int next, int busy) { return chain_make(0u, mask, next, busy); }
+
+// ---- the chain word: who runs a video stream's next tracker stage -------------------------------------------------
+// One 64-bit word per stream (chain_make), changed only by compare-and-swap:
+//   next      sequence number of the stream's next tracker stage that has not been started;
+//   busy      a CTA is running the stage next - 1 (it "owns the chain");
+//   mask      bit k: the NMS stage of frame next + k has PUBLISHED its kept detections (ring slot (next + k) % depth) and its CTA is gone;
+//   waiting   bit k: the CTA of frame next + k is alive and WAITS for its turn, its detections in shared memory.
+// A CTA that finishes the NMS stage of frame s
+//   * takes the chain (nobody owns it and s == next) and runs the tracker stage, or
+//   * WAITS for its turn if it is close to the head of the chain (s - next < wait_window): it runs the detection-only part
+//     of the tracker stage, then spins until the frames before its own have been run and the owner yields, or
+//   * publishes its frame in the mask and EXITS: the owner will run the frame from the ring slot.
+// At most wait_window CTAs per video stream wait at any time, each for at most wait_window tracker stages, and the host layer
+// keeps wait_window * num_streams below the SM count, so the CTAs they wait for always find an SM.
+// The owner, when it has written the stream's state back, yields if the next frame's CTA waits (that CTA then runs the
+// state-dependent stages while this one still assembles its TrackOutput records), else goes on with the next frame itself
+// if it has been published, else gives the chain up.  Frames of one video stream are thus processed strictly in order by
+// whichever CTA holds the chain, streams never wait for each other, and a slow frame (an auction that runs to its iteration
+// limit) delays only its own stream.
+// A frame's tracker stage runs in the CTA of its own step's kernel or of an EARLIER step's: every tracker stage of steps <= i
+// has run once the kernels of all steps <= i have completed — that is what the host layer's events rely on.
+struct ChainW { unsigned mask, waiting; int next, busy; };
+__device__ __forceinline__ ChainW chain_decode(unsigned long long v) {
+    ChainW d;
+    d.busy = (int)(v & 1ull); d.next = (int)((v >> 1) & 0x7fffffffull);
+    d.mask = (unsigned)((v >> 32) & 0x7fffull); d.waiting = (unsigned)((v >> 47) & 0x7fffull);
+    return d;
+}
+__device__ __forceinline__ unsigned long long chain_load(const unsigned long long* w) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+    return v;
+}
+// NMS stage of frame `seq` done, detections published.  0: exit; 1: this CTA owns the chain (frame seq is next); 2: wait for the turn
+__device__ __forceinline__ int chain_arrive(unsigned long long* w, int seq, int wait_window) {
+    __threadfence();                                     // release: detections, counts, frame id
+    for (;;) {
+        const unsigned long long cur = chain_load(w);
+        const ChainW d = chain_decode(cur);
+        const int k = seq - d.next;                      // >= 0: a tracker stage never starts before its NMS stage arrived
+        unsigned long long want;
+        int r;
+        if (!d.busy && k == 0) { want = chain_make(d.waiting >> 1, d.mask >> 1, d.next + 1, 1); r = 1; }
+        else if (k < wait_window) { want = chain_make(d.waiting | (1u << k), d.mask, d.next, d.busy); r = 2; }
+        else { want = chain_make(d.waiting, d.mask | (1u << k), d.next, d.busy); r = 0; }
+        if (atomicCAS(w, cur, want) == cur) { __threadfence(); return r; }    // acquire: the previous owner's state
+    }
+}
+// waiting CTA: spin until the frames before `seq` have been run and the chain is free, then take it.  false: time-out.
+__device__ __forceinline__ bool chain_take_over(unsigned long long* w, int seq) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        const unsigned long long cur = chain_load(w);
+        const ChainW d = chain_decode(cur);
+        if (d.busy || d.next != seq) {                   // an owner is running, or an earlier frame has not arrived yet (its CTA will take the chain)
+            if (globaltimer_ns() - t0 > 500000000ull) return false;
+            __nanosleep(32);
+            continue;
+        }
+        const unsigned long long want = chain_make(d.waiting >> 1, d.mask >> 1, d.next + 1, 1);
+        if (atomicCAS(w, cur, want) == cur) { __threadfence(); return true; }
+    }
+}
+// state written back: true = keep the chain and go on with the next frame (published, its CTA gone); false: the chain was
+// handed to the waiting CTA of the next frame, or given up
+__device__ __forceinline__ bool chain_advance(unsigned long long* w) {
+    __threadfence();                                     // release: the stream's state
+    for (;;) {
+        const unsigned long long cur = chain_load(w);
+        const ChainW d = chain_decode(cur);
+        const bool go = !(d.waiting & 1u) && (d.mask & 1u);
+        const unsigned long long want = go ? chain_make(d.waiting >> 1, d.mask >> 1, d.next + 1, 1) : chain_make(d.waiting, d.mask, d.next, 0);
+        if (atomicCAS(w, cur, want) == cur) { __threadfence(); return go; }   // acquire: the published detections
+    }
+}
+
+// wait_mode (fused): 1 = this CTA waits for its turn and takes the chain at the wait point; first_of_owner: the first
+// frame this CTA runs (the previous owner may still be assembling its records: second wait).  Returns (fused) 1 when the
+// CTA keeps the chain and the stream's next frame has arrived, 0 when the chain was handed on or given up, -1 on a time-out.
 template <int NTHREADS, bool ALLSMEM, bool FUSED>
-__device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const TrackParams& P_, const DetSource& src, const int b,
-                                             unsigned char* smem_raw, const int D_fused) {
-    TrackParams P = P_;
-    if (ALLSMEM) { P.cost_in_smem = 1; P.det_in_smem = 1; P.pred_in_smem = 1; }
+__device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackParams& P, const DetSource& src, const int b,
+                                             unsigned char* smem_raw, const int D_fused, const int seq, const int frame_id,
+                                             void* outputs, int* num_outputs, const int wait_mode = 0, const bool first_of_owner = true) {
+    // (no local copy of the parameter block: it stays in constant memory)
+    const bool cost_in_smem = ALLSMEM || P.cost_in_smem, det_in_smem = ALLSMEM || P.det_in_smem, pred_in_smem = ALLSMEM || P.pred_in_smem;
     Ctx c;
     tk_from_offsets(smem_raw, P.so, c.s);
     c.term_floats = P.term_floats;
@@ -470,13 +561,13 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     c.D = D; c.Dw = (Dm + 31) / 32;
     c.magicD = div_magic(D); c.magicW = div_magic((D + 31) / 32);   // before the wait: off the chain of dependent frames
     const int Dw = c.Dw;
-    float* det_w = P.det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
+    float* det_w = det_in_smem ? s.det : (tb.det_poses_scratch + (size_t)b * Dm * POSE_F);
     const float* src_pose = FUSED ? det_w : src.poses + (size_t)b * src.stride * POSE_F;
     const float* src_score = FUSED ? s.dscore : src.scores + (size_t)b * src.stride;
     // Detections in shared memory: copied now.  In the global scratch (large max_detections) they are copied after the
     // wait below: the predecessor of this video stream — possibly still running on another lane — reads the same
     // scratch until its first release.
-    if (!FUSED && P.det_in_smem) {
+    if (!FUSED && det_in_smem) {
 #pragma unroll 1
         for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
     }
@@ -508,8 +599,12 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     // here).  Launches are issued in sequence order and the host keeps at most `lanes` of them in flight; the
     // oldest never waits and the younger ones hold fewer SMs than the device has, so the oldest always runs to
     // completion; the time-out only guards against misuse.
-    if (tid == 0) {
-        const int want = P.seq - 1;
+    if (FUSED && wait_mode == 1 && tid == 0) {
+        // waiting CTA: the frames before this one have been run and their owner yields at its state release
+        if (!chain_take_over(tb.chain + b, seq)) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; }
+    }
+    if (!FUSED && tid == 0) {
+        const int want = seq - 1;
         const int* flag = tb.seq_done + b;
         const unsigned long long w0 = globaltimer_ns();
         for (;;) {
@@ -519,7 +614,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
             if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; break; }
         }
         const unsigned long long w1 = globaltimer_ns();
-        if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(P.seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
+        if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
         s.acc[15] += w1 - w0;                        // telemetry: time spent waiting for the predecessor
         s.acc[16] += w0 - t_begin;                   // telemetry: detection-only prologue
         const unsigned long long prev_end = g_ns[18];   // absolute time at which the predecessor released the stream
@@ -533,12 +628,13 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
         // wait again, and let the sticky error flag invalidate the results (every synchronising entry point reports it).
         if (tid == 0) {
             __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(seq) : "memory");
+            if (!FUSED) tb.chain[b] = chain_pack(0u, seq + 1, 0);
         }
-        return;
+        return -1;
     }
-    if (!FUSED && !P.det_in_smem) {
+    if (!FUSED && !det_in_smem) {
 #pragma unroll 1
         for (int i = tid; i < D * POSE_F; i += NT) det_w[i] = src_pose[i];
     }
@@ -572,10 +668,10 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
 #pragma unroll 1
     for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
     c.det = det_w;
-    c.cost = P.cost_in_smem ? s.cost : g_cost;
-    c.warp_auction = P.cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
-    c.pred = P.pred_in_smem ? s.pred : g_pred;
-    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
+    c.cost = cost_in_smem ? s.cost : g_cost;
+    c.warp_auction = cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
+    c.pred = pred_in_smem ? s.pred : g_pred;
+    if (cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
     __syncthreads();
     const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
     stamp(0);
@@ -592,7 +688,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
             const float dt = 1.0f;
             const float px = x + vx * dt, py = y + vy * dt;
             g_pred[po] = px; g_pred[po + 1] = py; g_pred[po + 2] = cf;
-            if (P.pred_in_smem) { s.pred[po] = px; s.pred[po + 1] = py; s.pred[po + 2] = cf; }
+            if (pred_in_smem) { s.pred[po] = px; s.pred[po + 1] = py; s.pred[po + 2] = cf; }
             if (s.states[t] == ST_LOST) { g_vel[vo] = vx * 0.95f; g_vel[vo + 1] = vy * 0.95f; }
             if (k == 0) g_dirty[t] = 1;
         }
@@ -608,7 +704,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
 #pragma unroll 1
         for (int t = tid; t < T; t += NT) {
             if (s.rowbc[t] || (s.active[t] == 1)) {     // predict marks every active slot dirty (below)
-                const float* pp = (P.pred_in_smem && s.active[t] == 1) ? (s.pred + (size_t)t * POSE_F) : (g_pred + (size_t)t * POSE_F);
+                const float* pp = (pred_in_smem && s.active[t] == 1) ? (s.pred + (size_t)t * POSE_F) : (g_pred + (size_t)t * POSE_F);
                 float area;
                 pose_box(pp, &s.tcent[t * 4], &area);
                 s.tarea[t] = area;
@@ -682,8 +778,8 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     // The predecessor's record assembly reads g_poses after it released the state (second release at its end):
     // nothing before this point writes g_poses, tb.outputs or the telemetry slots; wait for it here (it finished
     // long ago unless the launches ran far apart from the usual order).
-    if (tid == 0) {
-        const int want = P.seq - 1;
+    if ((!FUSED || first_of_owner) && tid == 0) {
+        const int want = seq - 1;
         const unsigned long long w0 = globaltimer_ns();
         for (;;) {
             int v;
@@ -696,10 +792,11 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     if (s.misc[10]) {       // see the first wait: no update, no records; only the prediction scratch has been touched
         if (tid == 0) {
             __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(seq) : "memory");
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(seq) : "memory");
+            if (!FUSED) tb.chain[b] = chain_pack(0u, seq + 1, 0);
         }
-        return;
+        return -1;
     }
     // ---------------- update matched (:1438-1472, kernels :141-189, :612-648) -------------
     if (D > 0) {
@@ -732,7 +829,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
             const int h = s.hits[t] + 1;
             s.hits[t] = h;
             s.ages[t] = 0;
-            g_last[t] = P.frame_id;
+            g_last[t] = frame_id;
             const int st = s.states[t];
             if (st == ST_TENTATIVE && h >= P.min_hits) s.states[t] = ST_CONFIRMED;
             else if (st == ST_LOST) s.states[t] = ST_CONFIRMED;
@@ -789,7 +886,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
                     s.ids[sl] = next_id++;
                     s.hits[sl] = 1; s.ages[sl] = 0; s.states[sl] = ST_TENTATIVE;
                     g_scores[sl] = s.dscore[d];
-                    g_last[sl] = P.frame_id;
+                    g_last[sl] = frame_id;
                     s.col[d] = sl;
                 }
             }
@@ -877,7 +974,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     }
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
-    if (P.cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
+    if (cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
     // block-wide sum of cnt_local (update()'s return value, :1130-1136)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cnt_local += __shfl_xor_sync(FULLM, cnt_local, off);
@@ -890,9 +987,12 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
         // the chain of dependent frames.
         g_scal[2] = D; g_scal[3] = s.misc[4];
         g_ns[18] = globaltimer_ns();
-        if (tb.dbg) tb.dbg[((size_t)(P.seq & 63) * P.B + b) * 6 + 2] = g_ns[18];
+        if (tb.dbg) tb.dbg[((size_t)(seq & 63) * P.B + b) * 6 + 2] = g_ns[18];
         __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(P.seq) : "memory");
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(seq) : "memory");
+        // fused path: hand the chain on here — a waiting successor starts its state-dependent stages while this CTA assembles
+        // the records; or keep it (the next frame has arrived: this CTA goes on with it afterwards); or give it up
+        if (FUSED) s.misc[11] = chain_advance(tb.chain + b) ? 1 : 0;
     }
 
     // ---------------- outputs: getActiveTracks (:1594-1636) on the device ------------------
@@ -922,7 +1022,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
         const bool xf = tb.out_xform != nullptr;
         const float sx = xf ? tb.out_xform[b * 4 + 0] : 1.0f, sy = xf ? tb.out_xform[b * 4 + 1] : 1.0f;
         const float px_ = xf ? tb.out_xform[b * 4 + 2] : 0.0f, py_ = xf ? tb.out_xform[b * 4 + 3] : 0.0f;
-        float* outw = reinterpret_cast<float*>(tb.outputs) + (size_t)b * Dm * 57;
+        float* outw = reinterpret_cast<float*>(outputs) + (size_t)b * Dm * 57;
 #pragma unroll 1
         for (int o = c.warp; o < n_out; o += c.nwarps) {
             const int d = s.out_list[o];
@@ -952,7 +1052,7 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     }
 
     if (tid == 0) {
-        tb.num_outputs[b] = n_out;
+        num_outputs[b] = n_out;
         const unsigned long long now = globaltimer_ns();
         s.acc[10] = now - t_begin;
         s.acc[11] = 1ull;
@@ -964,8 +1064,12 @@ __device__ __forceinline__ void tracker_body(const TrackBuffers& tb, const Track
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(P.seq) : "memory");
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(seq) : "memory");
+        // stand-alone launches run with nothing of the fused path in flight (pb_api.cu joins first): a plain store keeps the
+        // chain word of the fused path current (next frame = seq + 1, nothing published, nobody owns the chain)
+        if (!FUSED) tb.chain[b] = chain_pack(0u, seq + 1, 0);
     }
+    return FUSED ? s.misc[11] : 0;      // written before the last barrier above
 }
 
 
