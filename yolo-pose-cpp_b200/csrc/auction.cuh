@@ -33,7 +33,7 @@ __device__ __forceinline__ float hy_unord(unsigned u) {
 __device__ __forceinline__ void auction_solve_cta(const float* cost, int R, int C, const int* active,
                                                   int* row, int* col, float* price,
                                                   unsigned long long* colbid, int* flags,
-                                                  int tid, int nthreads, int max_iters = -1) {
+                                                  int tid, int nthreads, int max_iters = -1, const int* locked = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     for (int t = tid; t < R; t += nthreads) row[t] = -1;
@@ -50,7 +50,9 @@ __device__ __forceinline__ void auction_solve_cta(const float* cost, int R, int 
         int bidx = 0;
         for (int base = 0; base < R; base += 32) {
             const int r = base + lane;
-            const bool bidder = (r < R) && (active == nullptr || active[r] != 0) && (row[r] < 0);
+            // locked (may be null): rows with locked[r] >= 0 were matched in an earlier tier; all their cells are 1e9 (lock_pairs),
+            // so they would scan their row, find nothing above the -1e9 floor and never bid (hungarian.cu:55-69): left out
+            const bool bidder = (r < R) && (active == nullptr || active[r] != 0) && (row[r] < 0) && (locked == nullptr || locked[r] < 0);
             unsigned bm = __ballot_sync(FULL, bidder);
             while (bm) {
                 const int rb = base + __ffs(bm) - 1;

@@ -270,6 +270,19 @@ static int build_handle(pb_handle_st* h) {
         h->post.dbg = t.dbg;
     }
     h->plan = tracker_plan(c.max_tracks, c.max_detections);
+    {
+        int dev = 0, sms = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        tracker_plan_pre(h->plan, c.num_streams, c.max_tracks, c.max_detections, sms, (size_t)optin);
+        if (h->plan.pre_slices > 0) {
+            const size_t Dw = (Dm + 31) / 32;
+            PB_TRY(dev_alloc(h, &t.gate_g, B * T * Dw));
+            PB_TRY(dev_alloc(h, &t.lgate_g, B * T * Dw));
+            PB_TRY(dev_alloc(h, &t.tarea_g, B * T));
+        }
+    }
     if (h->fplan.ok && h->fplan.spill_stride) PB_TRY(dev_alloc(h, &h->d_spill, B * h->fplan.spill_stride));
     PB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     PB_CUDA(launch_tracker_reset(h->trk, c.num_streams, c.max_tracks, c.max_detections, h->trk_seq, h->own_stream));
@@ -458,6 +471,10 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
     TrackParams p = track_params(h, frame_id);
     int e0 = -1, e1 = -1;
     if (h->profiling && (e0 = prof_event(h)) >= 0) cudaEventRecord(h->ev_pool[e0], (cudaStream_t)stream);
+    if (h->plan.pre_slices > 0) {            // large tables: row-sliced predict / gates / tier-1 costs ahead of the per-stream kernel
+        PB_CUDA(launch_tracker_pre(h->trk, p, src, h->plan, (cudaStream_t)stream));
+        p.precomputed = 1;
+    }
     PB_CUDA(launch_tracker(h->trk, p, src, h->plan, (cudaStream_t)stream));
     h->trk_seq = p.seq;
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
@@ -559,7 +576,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     // tracker launches alternating between two.  With a read-back of the records behind every launch
     // (pb_submit_host) the output buffer of step i must not be overwritten before it is copied: one lane then.
     cudaStream_t lane[3] = {h->s_trk, h->s_trk2, h->s_trk3};
-    const bool single = h->rb_tracks || !h->overlap_trackers;
+    const bool single = h->rb_tracks || !h->overlap_trackers || h->plan.pre_slices > 0;   // (the pre-kernel needs the previous frame's final state: stream order)
     cudaStream_t ts, ns;
     if (h->lanes > 0 && !single) { ts = lane[tp.seq % h->lanes]; ns = ts; }
     else {
@@ -582,7 +599,9 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
         PB_CUDA(cudaStreamWaitEvent(ts, h->ring[h->cur].ev_trk, 0));   // the previous step's records are still being copied out
     if (ns != ts) PB_CUDA(cudaStreamWaitEvent(ts, sl.ev_nms, 0));
     DetSource src{sl.post.det_poses, sl.post.det_scores, sl.post.num_keep, c.max_keep};
-    PB_CUDA(launch_tracker(h->trk, tp, src, h->plan, ts));
+    TrackParams tpp = tp;
+    if (h->plan.pre_slices > 0) { PB_CUDA(launch_tracker_pre(h->trk, tpp, src, h->plan, ts)); tpp.precomputed = 1; }
+    PB_CUDA(launch_tracker(h->trk, tpp, src, h->plan, ts));
     h->trk_seq = tp.seq;
     PB_TRY(enqueue_readback(h, ts));
     PB_CUDA(cudaEventRecord(sl.ev_trk, ts));

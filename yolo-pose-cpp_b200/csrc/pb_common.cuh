@@ -68,6 +68,9 @@ struct TrackBuffers {
     int* seq_done;       // [B] sequence number of the last tracker launch whose STATE update this stream has completed (see pb_tracker_kernel)
     int* out_done;       // [B] ... whose TrackOutput records are written as well (second release)
     int* error_flag;     // [1] set when a stream's predecessor did not finish within the time-out
+    unsigned* gate_g;    // [B, T*Dw] large tables: the gates the row-sliced pre-kernel (tracker.cu) computed for this frame
+    unsigned* lgate_g;   // [B, T*Dw]
+    float* tarea_g;      // [B, T] keypoint-box areas of the predicted poses (pre-kernel)
     unsigned long long* chain;   // [B] fused path: who runs the stream's next tracker stage — (published-NMS mask << 32) | next seq << 1 | busy
     unsigned long long* dbg;   // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [0] begin, [1] state acquired, [2] end
 };
@@ -83,6 +86,7 @@ struct TrackParams {
     int seq;             // sequence number of this launch; the CTA of stream b starts once seq_done[b] == seq - 1
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
     int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap;
+    int precomputed;     // predict, centres, gates and the tier-1 cost pass of this frame were done by the pre-kernel (large tables)
     SmemOffsets so;      // shared-memory layout (tracker_plan)
 };
 
@@ -122,10 +126,14 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
 cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 lazy, 2 deferred*/, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
-struct TrackerPlan { size_t smem_bytes, prefix_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap; SmemOffsets so; };
+struct TrackerPlan { size_t smem_bytes, prefix_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap; SmemOffsets so;
+                     int pre_slices; size_t pre_smem; };   // pre_slices > 0: large tables, row-sliced pre-kernel with this many CTAs per stream
 TrackerPlan tracker_plan(int T, int Dm, bool compact = false);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);
+// large tables: predict + centres + gates + tier-1 OKS cost pass, row-sliced over plan.pre_slices CTAs per stream
+cudaError_t launch_tracker_pre(const TrackBuffers& tb, const TrackParams& p, const DetSource& src, const TrackerPlan& plan, cudaStream_t stream);
+void tracker_plan_pre(TrackerPlan& plan, int B, int T, int Dm, int sm_count, size_t smem_optin);
 cudaError_t launch_tracker_reset(const TrackBuffers& tb, int B, int T, int Dm, int seq, cudaStream_t stream);
 
 // Ring of per-step buffers as the fused kernel sees it: a CTA that owns its stream's chain goes on with the following

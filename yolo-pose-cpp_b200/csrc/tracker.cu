@@ -78,6 +78,165 @@ TrackerPlan tracker_plan(int T, int Dm, bool compact) {
     return p;
 }
 
+// =======================================================================================
+// Large tables (the 512 x 512 stress configuration): predict, keypoint-box centres, gates and the tier-1 OKS cost pass are
+// row-parallel and dominate the frame (gate + cost pass: 60 % of a 512 x 512 frame on one SM).  This kernel runs them with
+// plan.pre_slices CTAs per stream, each owning a slice of track slots, ahead of the one-CTA-per-stream kernel, which then
+// takes the centres, areas, gate words and costs from global memory and goes straight to the auction.  Same expressions,
+// same results.  Only for launches that are ordered on one CUDA stream (the state must be the previous frame's final one).
+// =======================================================================================
+constexpr int PRE_THREADS = 512;
+
+__global__ void __launch_bounds__(PRE_THREADS)
+pb_tracker_pre_kernel(TrackBuffers tb, TrackParams P, DetSource src, int rows_per_slice) {
+    extern __shared__ __align__(16) unsigned char pre_smem[];
+    const int b = blockIdx.y, T = P.T, Dm = P.Dm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = PRE_THREADS, nwarps = PRE_THREADS / 32;
+    const int r0 = blockIdx.x * rows_per_slice;
+    const int r1 = (r0 + rows_per_slice < T) ? r0 + rows_per_slice : T;
+    const int nr = r1 > r0 ? r1 - r0 : 0;
+    int n_in = src.num[b];
+    const int D = n_in < Dm ? (n_in < 0 ? 0 : n_in) : Dm;
+    const int Dw = (Dm + 31) / 32, words = (D + 31) / 32;
+    // shared memory: det poses [D*51], dcent [D*4], darea [D], pred slice [rps*51], tcent [rps*4], tarea, tav [rps], flags [rps], cell list
+    float* s_det = reinterpret_cast<float*>(pre_smem);
+    float* s_dcent = s_det + (size_t)Dm * POSE_F;
+    float* s_darea = s_dcent + (size_t)Dm * 4;
+    float* s_pred = s_darea + Dm;
+    float* s_tcent = s_pred + (size_t)rows_per_slice * POSE_F;
+    float* s_tarea = s_tcent + (size_t)rows_per_slice * 4;
+    float* s_tav = s_tarea + rows_per_slice;
+    int* s_act = reinterpret_cast<int*>(s_tav + rows_per_slice);          // 1 active, 2 active and LOST
+    unsigned* s_gate = reinterpret_cast<unsigned*>(s_act + rows_per_slice);   // [rps * Dw] tier-1 gate words of the slice
+    __shared__ float s_sig[KP];
+    float* g_poses = tb.poses + (size_t)b * T * POSE_F;
+    float* g_vel = tb.vel + (size_t)b * T * 34;
+    float* g_pred = tb.predicted + (size_t)b * T * POSE_F;
+    float* g_tcent = tb.tcent + (size_t)b * T * 4;
+    float* g_cost = tb.cost + (size_t)b * T * Dm;
+    const int* g_states = tb.states + (size_t)b * T;
+    const int* g_active = tb.active + (size_t)b * T;
+    int* g_dirty = tb.pred_dirty + (size_t)b * T;
+    unsigned* g_gate = tb.gate_g + (size_t)b * T * Dw;
+    unsigned* g_lgate = tb.lgate_g + (size_t)b * T * Dw;
+    float* g_tarea = tb.tarea_g + (size_t)b * T;
+    const int na_total = tb.scalars[(size_t)b * 4 + 3];                   // active slots at frame start (= the count the previous frame left)
+    if (tid < KP) s_sig[tid] = kSigmas[tid];
+    for (int r = tid; r < nr; r += NT) {
+        const int t = r0 + r;
+        s_act[r] = (g_active[t] == 1) ? ((g_states[t] == ST_LOST) ? 2 : 1) : 0;
+    }
+    __syncthreads();
+    // predict (:102-138): the slice's active rows
+#pragma unroll 1
+    for (int i = tid; i < nr * KP; i += NT) {
+        const int r = i / KP, k = i - r * KP;
+        if (s_act[r] == 0) continue;
+        const int t = r0 + r;
+        const int po = t * POSE_F + k * 3, vo = t * 34 + k * 2;
+        const float x = g_poses[po], y = g_poses[po + 1], cf = g_poses[po + 2];
+        const float vx = g_vel[vo], vy = g_vel[vo + 1];
+        const float dt = 1.0f;
+        const float px = x + vx * dt, py = y + vy * dt;
+        g_pred[po] = px; g_pred[po + 1] = py; g_pred[po + 2] = cf;
+        s_pred[r * POSE_F + k * 3] = px; s_pred[r * POSE_F + k * 3 + 1] = py; s_pred[r * POSE_F + k * 3 + 2] = cf;
+        if (s_act[r] == 2) { g_vel[vo] = vx * 0.95f; g_vel[vo + 1] = vy * 0.95f; }
+        if (k == 0) g_dirty[t] = 1;
+    }
+    const bool assoc12 = (na_total > 0) && (D > 0);
+    if (!assoc12) return;                                                 // uniform over the grid's CTAs of this stream
+    // this frame's detections (all of them, every slice needs them): poses, centres, areas
+    const float* src_pose = src.poses + (size_t)b * src.stride * POSE_F;
+#pragma unroll 1
+    for (int i = tid; i < D * POSE_F; i += NT) s_det[i] = src_pose[i];
+    __syncthreads();                                                      // predict's stores (global, velocity decay) and s_pred, s_det
+#pragma unroll 1
+    for (int d = tid; d < D; d += NT) { float area; pose_box(s_det + (size_t)d * POSE_F, &s_dcent[d * 4], &area); s_darea[d] = area; }
+    // centres (:196-237): every slot of the slice whose predicted pose changed since its centre was derived
+#pragma unroll 1
+    for (int r = tid; r < nr; r += NT) {
+        const int t = r0 + r;
+        if (g_dirty[t] || s_act[r] != 0) {
+            const float* pp = (s_act[r] != 0) ? (s_pred + (size_t)r * POSE_F) : (g_pred + (size_t)t * POSE_F);
+            float area;
+            pose_box(pp, &s_tcent[r * 4], &area);
+            s_tarea[r] = area;
+            g_tarea[t] = area;
+            g_tcent[t * 4] = s_tcent[r * 4]; g_tcent[t * 4 + 1] = s_tcent[r * 4 + 1];
+            g_tcent[t * 4 + 2] = s_tcent[r * 4 + 2]; g_tcent[t * 4 + 3] = s_tcent[r * 4 + 3];
+            g_dirty[t] = 0;
+        }
+        if (s_act[r] != 0) {                                              // mean torso speed (:287-298), after the LOST decay
+            const int torso[4] = {5, 6, 11, 12};
+            float av = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float vx = g_vel[t * 34 + torso[i] * 2], vy = g_vel[t * 34 + torso[i] * 2 + 1];
+                av += sqrtf(vx * vx + vy * vy);
+            }
+            s_tav[r] = av * 0.25f;
+        }
+    }
+    __syncthreads();
+    // gates (:241-317): one warp per (row of the slice, 32 detections); every word of the slice is written (0: inactive row)
+#pragma unroll 1
+    for (int i = warp; i < nr * Dw; i += nwarps) {
+        const int r = i / Dw, w = i - r * Dw;
+        const int t = r0 + r;
+        const int d = w * 32 + lane;
+        const bool act = s_act[r] != 0, lost = s_act[r] == 2;
+        const float base = lost ? (3.0f * 1.3f) : 3.0f;
+        bool g = false;
+        if (act && w < words && d < D) g = gate_cell(&s_tcent[r * 4], &s_dcent[d * 4], s_tav[r], lost, base, P.gating_enabled != 0);
+        const unsigned bm = __ballot_sync(0xffffffffu, g);
+        if (lane == 0) {
+            g_gate[t * Dw + w] = lost ? 0u : bm;
+            g_lgate[t * Dw + w] = lost ? bm : 0u;
+            s_gate[r * Dw + w] = lost ? 0u : bm;
+        }
+    }
+    __syncthreads();
+    // tier-1 cost pass (:333-425) on the gated cells of the slice's rows that are not LOST: one thread per cell
+#pragma unroll 1
+    for (int i = tid; i < nr * words * 32; i += NT) {
+        const int r = i / (words * 32), rem = i - r * (words * 32);
+        const int w = rem >> 5, d = rem;
+        if (d >= D || !((s_gate[r * Dw + w] >> (d & 31)) & 1u)) continue;
+        g_cost[(size_t)(r0 + r) * D + d] = oks_cell_cost(s_pred + (size_t)r * POSE_F, s_det + (size_t)d * POSE_F, s_tarea[r], s_darea[d], s_sig, 0.2f);
+    }
+}
+
+static size_t pre_smem_bytes(int Dm, int rps) {
+    const int Dw = (Dm + 31) / 32;
+    return ((size_t)Dm * (POSE_F + 4 + 1) + (size_t)rps * (POSE_F + 4 + 1 + 1 + 1) + (size_t)rps * Dw) * 4 + 64;
+}
+
+// Decide whether (and how) the pre-kernel is used for a handle: tables of at least 64 K cells whose detections fit the
+// pre-kernel's shared memory; slices so that the grid covers the device about twice.
+void tracker_plan_pre(TrackerPlan& plan, int B, int T, int Dm, int sm_count, size_t smem_optin) {
+    plan.pre_slices = 0; plan.pre_smem = 0;
+    long min_cells = 65536;
+    if (const char* e = getenv("PB_TRACKER_PRE")) { const long v = atol(e); if (v <= 0) return; min_cells = v; }
+    if ((long)T * Dm < min_cells) return;
+    int G = (2 * sm_count + B - 1) / B;
+    if (G < 1) G = 1;
+    if (G > (T + 7) / 8) G = (T + 7) / 8;
+    const int rps = (T + G - 1) / G;
+    G = (T + rps - 1) / rps;
+    const size_t bytes = pre_smem_bytes(Dm, rps);
+    if (bytes > smem_optin) return;
+    plan.pre_slices = G; plan.pre_smem = bytes;
+}
+
+cudaError_t launch_tracker_pre(const TrackBuffers& tb, const TrackParams& p, const DetSource& src, const TrackerPlan& plan, cudaStream_t stream) {
+    const cudaError_t e = ensure_dyn_smem((const void*)pb_tracker_pre_kernel, plan.pre_smem);
+    if (e != cudaSuccess) return e;
+    const int rps = (p.T + plan.pre_slices - 1) / plan.pre_slices;
+    pb_tracker_pre_kernel<<<dim3(plan.pre_slices, p.B), PRE_THREADS, plan.pre_smem, stream>>>(tb, p, src, rps);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int NTHREADS, bool ALLSMEM>
 __global__ void __launch_bounds__(NTHREADS)
 pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {

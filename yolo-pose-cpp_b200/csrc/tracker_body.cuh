@@ -168,10 +168,16 @@ __device__ __forceinline__ bool gate_cell(const float* tc, const float* dc, floa
     if (tw < 1.0f || th < 1.0f || dw < 1.0f || dh < 1.0f) return true;
     if (!gating) return true;
     const float dx = tc[0] - dc[0], dy = tc[1] - dc[1];
-    const float dist = sqrtf(dx * dx + dy * dy);
     const float size = (tw + th + dw + dh) * 0.25f;
-    const float ratio = dist / (size + 1e-6f);
-    const float vf = 1.0f + pb_min(av / (size + 1e-6f), 2.0f);
+    const float den = size + 1e-6f;
+    // Cheap exact rejection (most pairs of a crowded frame): the threshold below is at most base * 3 (* 2 for a lost track)
+    // and the ratio at least max(|dx|, |dy|) / den up to three roundings, so a centre offset beyond that bound by a margin
+    // of 1e-5 cannot pass the test.  NaNs fail both comparisons and take the complete test.
+    const float lim = (base * 3.0f) * (lost ? 2.0f : 1.0f) * den * 1.00001f;
+    if (fabsf(dx) > lim || fabsf(dy) > lim) return false;
+    const float dist = sqrtf(dx * dx + dy * dy);
+    const float ratio = dist / den;
+    const float vf = 1.0f + pb_min(av / den, 2.0f);
     float thr = base * vf;
     if (lost) thr *= 2.0f;
     return ratio < thr;
@@ -262,25 +268,52 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
                            reinterpret_cast<unsigned*>(s.rowbid), c.tid);
     } else {
         auction_solve_cta(c.cost, c.T, c.D, s.active, s.row, s.col, s.price, s.colbid, &s.misc[8],
-                          c.tid, c.nthreads);
+                          c.tid, c.nthreads, -1, after_lock ? s.rowb : nullptr);
     }
+}
+
+// One gated cell of kernelOKSWithGating (:360-424), all 17 keypoints by one thread, keypoint-ordered sum: the expressions of
+// cost_pass_oks below (which spreads the 17 terms of a cell over threads and adds them in the same order; an invisible
+// keypoint adds -0.0f there, i.e. nothing).  Used by the row-sliced pre-kernel of large tables.
+__device__ __forceinline__ float oks_cell_cost(const float* tp, const float* dp, float tarea, float darea, const float* sig, float vis) {
+    const float scale_sq = pb_max((darea + tarea) * 0.5f, 1000.0f);
+    const float t2 = 2.0f * scale_sq;
+    float sum = 0.0f;
+    int cnt = 0;
+#pragma unroll 1
+    for (int k = 0; k < KP; ++k) {
+        if (dp[k * 3 + 2] > vis && tp[k * 3 + 2] > vis) {
+            const float dx = dp[k * 3] - tp[k * 3], dy = dp[k * 3 + 1] - tp[k * 3 + 1];
+            const float d2 = dx * dx + dy * dy;
+            const float sg = sig[k] * 2.0f;
+            const float s2 = sg * sg;
+            sum += pb_expf(-d2 / (t2 * s2));
+            ++cnt;
+        }
+    }
+    const float oks = (cnt >= 3) ? (sum / (float)cnt) : 0.0f;
+    return 1.0f - oks;
 }
 
 // kernelLockMatchedPairs (:540-567) on cost + a bit-packed gate.  Only rows that were active at
 // frame start are touched: the cells of inactive rows are never read by the auction (inactive
 // rows do not bid) and are overwritten with 1.0 by the last cost pass of the frame anyway.
-static __device__ __forceinline__ void lock_pairs(Ctx& c, unsigned* gate, int na) {
+static __device__ __forceinline__ void lock_pairs(Ctx& c, unsigned* gate, int na, bool use_backup) {
+    // use_backup: rowb / colb hold the assignments of the earlier tiers of this frame, whose rows and columns are locked in
+    // the cost matrix already (nothing writes those cells in between: their gate bits were cleared with them) — only the
+    // pairs this tier added need the 1e9 writes; the gate words are cleared for all matched rows and columns either way.
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
 #pragma unroll 1
     for (int ai = c.warp; ai < na; ai += c.nwarps) {
         const int t = s.act_list[ai];
         const bool rowm = s.row[t] >= 0;
+        const bool row_old = use_backup && s.rowb[t] >= 0;
         for (int w = 0; w < words; ++w) {
             const int d = w * 32 + c.lane;
             const bool colm = (d < D) && (s.col[d] >= 0);
             const unsigned bm = __ballot_sync(FULLM, colm);
-            if (d < D && (rowm || colm)) c.cost[(size_t)t * D + d] = 1e9f;
+            if (d < D && (rowm || colm) && !(row_old || (use_backup && s.colb[d] >= 0))) c.cost[(size_t)t * D + d] = 1e9f;
             if (c.lane == 0) gate[t * Dw + w] = rowm ? 0u : (gate[t * Dw + w] & ~bm);
         }
     }
@@ -380,12 +413,16 @@ static __device__ __forceinline__ void cost_pass_oks(Ctx& c, const unsigned* gat
 // Torso-only OKS (kernelTorsoOKS :455-489): four exponentials per cell, one thread per cell.
 static __device__ __forceinline__ void cost_pass_torso(Ctx& c, const unsigned* gate, int na) {
     TkSmem& s = c.s;
-    const int D = c.D, Dw = c.Dw;
+    const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
+    // one warp per (active row, 32 detections): after the tier-1 lock most gate words are empty
 #pragma unroll 1
-    for (int i = c.tid; i < na * D; i += c.nthreads) {
-        const int ai = fast_div(i, c.magicD), d = i - ai * D;
+    for (int i = c.warp; i < na * words; i += c.nwarps) {
+        const int ai = fast_div(i, c.magicW), w = i - ai * words;
         const int t = s.act_list[ai];
-        if ((gate[t * Dw + (d >> 5)] >> (d & 31)) & 1u)
+        const unsigned gw = gate[t * Dw + w];
+        if (gw == 0u) continue;
+        const int d = w * 32 + c.lane;
+        if ((gw >> c.lane) & 1u)
             c.cost[(size_t)t * D + d] = torso_cost(c.pred + (size_t)t * POSE_F, c.det + (size_t)d * POSE_F);
     }
     __syncthreads();
@@ -677,7 +714,13 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     stamp(0);
 
     // ---------------- predict (:1160-1175, kernel :102-138) ----------------
-    if (na > 0) {
+    const bool pre = P.precomputed != 0;            // large tables: done by the row-sliced pre-kernel (tracker.cu) just before this launch
+    if (pre) {
+        if (pred_in_smem) {
+#pragma unroll 1
+            for (int i = tid; i < na * POSE_F; i += NT) { const int ai = i / POSE_F, e = i - ai * POSE_F; const int t = s.act_list[ai]; s.pred[t * POSE_F + e] = g_pred[t * POSE_F + e]; }
+        }
+    } else if (na > 0) {
 #pragma unroll 1
         for (int i = tid; i < na * KP; i += NT) {
             const int ai = i / KP, k = i - ai * KP;
@@ -698,7 +741,16 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
 
     const bool assoc12 = (na > 0) && (D > 0);
     // ---------------- centres + gates (:1177-1208, kernels :196-317) ----------------
-    if (assoc12) {
+    if (assoc12 && pre) {
+        // centres came with the state slab (prologue); areas and gates from the pre-kernel's buffers
+        const float* ga = tb.tarea_g + (size_t)b * T;
+        const unsigned* gg = tb.gate_g + (size_t)b * T * Dw;
+        const unsigned* gl = tb.lgate_g + (size_t)b * T * Dw;
+#pragma unroll 1
+        for (int t = tid; t < T; t += NT) s.tarea[t] = ga[t];
+#pragma unroll 1
+        for (int i = tid; i < T * Dw; i += NT) { s.gate[i] = gg[i]; s.lgate[i] = gl[i]; }
+    } else if (assoc12) {
         // track centres: every slot whose predicted pose changed since its centre was derived
         // (== the reference recomputing all T slots: unchanged slots give unchanged centres)
 #pragma unroll 1
@@ -727,7 +779,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         }
     }
     __syncthreads();
-    if (assoc12) {
+    if (assoc12 && !pre) {
         // gate (base 3.0) minus LOST rows (tier 1 mask, :1231) and lost-tier gate (base 3.0*1.3,
         // only LOST rows survive the two state masks, :1359-1387).  One warp per (row, 32 dets).
         const int words = (D + 31) / 32;
@@ -756,20 +808,20 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         if (run) {
             if (tier > 0) backup_assign(c);
             if (tier == 0) {
-                cost_pass_oks(c, s.gate, na, 0.2f);
+                if (!pre) cost_pass_oks(c, s.gate, na, 0.2f);
                 stamp(12);
             } else if (tier == 1) {
                 cost_pass_torso(c, s.gate, na);
             } else {
                 cost_inactive_rows(c);
-                lock_pairs(c, s.lgate, na);
+                lock_pairs(c, s.lgate, na, true);
                 // the lost-tier gate holds bits of LOST rows only (gate stage): without such a row it is empty
                 if (s.misc[6] > 0) cost_pass_oks(c, s.lgate, na, 0.2f);
             }
             auction_solve(c, na, tier > 0);
             if (tier == 0) stamp(13);
             if (tier > 0) merge_assign(c);
-            if (tier < 2) lock_pairs(c, s.gate, na);
+            if (tier < 2) lock_pairs(c, s.gate, na, tier > 0);
             if (tier == 0) stamp(14);
         }
         stamp(3 + tier);
@@ -870,27 +922,81 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         }
         __syncthreads();
         const bool newborn = s.misc[7] != 0;
-        if (newborn && tid == 0) {
-            int hint = g_scal[1], next_id = g_scal[0];
-            for (int d = 0; d < D; ++d) {
-                if (s.col[d] >= 0) continue;
-                if (s.dscore[d] < P.new_track_thresh) continue;
-                const int start = hint % T;
-                ++hint;
-                for (int i = 0; i < T; ++i) {
-                    int sl = start + i; if (sl >= T) sl -= T;
-                    if (s.active[sl] == 0) { s.active[sl] = 1; s.slot_for_det[d] = sl; break; }
+        if (newborn) {
+            // R3/R4 in parallel.  The reference's rule, made sequential (ascending detection index; the k-th qualifying
+            // detection starts at slot (hint + k) mod T and takes the first free slot from there, circularly), has a
+            // closed form: starts advance by one per detection and free slots are distinct, so the k-th free slot in
+            // circular order from s0 = hint mod T lies at least k slots beyond s0 and is never overtaken — the k-th
+            // qualifying detection gets exactly the k-th free slot from s0, until the free slots run out (later
+            // detections get none; the hint still advances for each of them).  Ids are issued in the same order.
+            const int hint0 = g_scal[1], id0 = g_scal[0];
+            const int s0 = hint0 % T;
+            int* free_by_rank = s.elig_list;         // [T], idle until the de-duplication stage
+            int* det_rank = s.out_list;              // [Dm], idle until the output stage
+            if (tid < 32) {                           // free slots in all, and in [s0, T)
+                int all = 0, up = 0;
+#pragma unroll 1
+                for (int pb = 0; pb < T; pb += 32) {
+                    const int u = pb + c.lane;
+                    const bool f = (u < T) && s.active[u] == 0;
+                    all += __popc(__ballot_sync(FULLM, f));
+                    up += __popc(__ballot_sync(FULLM, f && u >= s0));
                 }
-                const int sl = s.slot_for_det[d];
-                if (sl >= 0) {
-                    s.ids[sl] = next_id++;
-                    s.hits[sl] = 1; s.ages[sl] = 0; s.states[sl] = ST_TENTATIVE;
-                    g_scores[sl] = s.dscore[d];
-                    g_last[sl] = frame_id;
-                    s.col[d] = sl;
-                }
+                if (c.lane == 0) { s.misc[13] = all; s.misc[14] = up; }
             }
-            g_scal[1] = hint; g_scal[0] = next_id;
+            __syncthreads();
+            const int nfree = s.misc[13], upper = s.misc[14];
+            // rank of every free slot in circular order from s0: slots >= s0 first (ascending), then the slots below s0
+#pragma unroll 1
+            for (int base = c.warp * 32; base < T; base += c.nwarps * 32) {
+                int lo = 0, ge = 0;
+#pragma unroll 1
+                for (int pb = 0; pb < base; pb += 32) {
+                    const int u = pb + c.lane;
+                    const bool f = s.active[u] == 0;
+                    lo += __popc(__ballot_sync(FULLM, f && u < s0));
+                    ge += __popc(__ballot_sync(FULLM, f && u >= s0));
+                }
+                const int t = base + c.lane;
+                const bool fr = (t < T) && s.active[t] == 0;
+                const unsigned mlo = __ballot_sync(FULLM, fr && t < s0), mge = __ballot_sync(FULLM, fr && t >= s0);
+                const unsigned below = (1u << c.lane) - 1u;
+                if (fr) free_by_rank[(t >= s0) ? (ge + __popc(mge & below)) : (upper + lo + __popc(mlo & below))] = t;
+            }
+            // rank of every qualifying detection (ascending detection index)
+#pragma unroll 1
+            for (int base = c.warp * 32; base < D; base += c.nwarps * 32) {
+                int start = 0;
+#pragma unroll 1
+                for (int pb = 0; pb < base; pb += 32) {
+                    const int u = pb + c.lane;
+                    start += __popc(__ballot_sync(FULLM, s.col[u] < 0 && !(s.dscore[u] < P.new_track_thresh)));
+                }
+                const int d = base + c.lane;
+                const bool q = (d < D) && s.col[d] < 0 && !(s.dscore[d] < P.new_track_thresh);
+                const unsigned bm = __ballot_sync(FULLM, q);
+                if (d < D) det_rank[d] = q ? (start + __popc(bm & ((1u << c.lane) - 1u))) : -1;
+                if (base + 32 >= D && c.lane == 0) s.misc[12] = start + __popc(bm);            // qualifying detections in all
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int d = tid; d < D; d += NT) {
+                const int k = det_rank[d];
+                if (k < 0 || k >= nfree) continue;                   // not qualifying, or no free slot left for it
+                const int sl = free_by_rank[k];
+                s.slot_for_det[d] = sl;
+                s.active[sl] = 1;
+                s.ids[sl] = id0 + k;
+                s.hits[sl] = 1; s.ages[sl] = 0; s.states[sl] = ST_TENTATIVE;
+                g_scores[sl] = s.dscore[d];
+                g_last[sl] = frame_id;
+                s.col[d] = sl;
+            }
+            if (tid == 0) {
+                const int nq = s.misc[12];
+                g_scal[1] = hint0 + nq;
+                g_scal[0] = id0 + (nq < nfree ? nq : nfree);
+            }
         }
         if (newborn) {
         __syncthreads();
@@ -926,11 +1032,18 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         }
         __syncthreads();
         const int ne = s.misc[1];
+        const unsigned magic_ne = div_magic(ne);
 #pragma unroll 1
         for (int i = tid; i < ne * ne; i += NT) {
-            const int ia = i / ne, ib = i - ia * ne;
+            const int ia = fast_div(i, magic_ne), ib = i - ia * ne;
             const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
-            if (t1 < t2 && center_iou(&s.tcent[t1 * 4], &s.tcent[t2 * 4]) > 0.7f) {
+            if (t1 >= t2) continue;
+            // boxes whose centres are further apart than the sum of their half extents (plus a margin far above any rounding
+            // of the corner arithmetic) do not intersect: IoU 0, never above 0.7.  NaNs fail the comparison and take the test.
+            const float* a4 = &s.tcent[t1 * 4]; const float* b4 = &s.tcent[t2 * 4];
+            const float hw = (fabsf(a4[2]) + fabsf(b4[2])) * 0.5f, hh = (fabsf(a4[3]) + fabsf(b4[3])) * 0.5f;
+            if (fabsf(a4[0] - b4[0]) > hw * 1.001f + 1.0f || fabsf(a4[1] - b4[1]) > hh * 1.001f + 1.0f) continue;
+            if (center_iou(a4, b4) > 0.7f) {
                 const int pos = atomicAdd(&s.misc[2], 1);
                 if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
             }
