@@ -376,8 +376,12 @@ class Workload:
         self.f += 1
 
     def run(self, n):
-        for _ in range(n):
-            self.step()
+        if self.c["kind"] == "head":          # n steps through one C call (pb_step_seq == n x pb_step without n ctypes crossings)
+            self.pipe.step_seq(self.d_heads, self.f % self.F, n, self.f, CONF, NMS)
+            self.f += n
+        else:
+            for _ in range(n):
+                self.step()
         self.pipe.join()
 
     def timed(self, steps, barrier, stream):

@@ -21,7 +21,7 @@ namespace cuda {
 class LinearAssignmentCUDA {
 public:
     explicit LinearAssignmentCUDA(int max_size = 256) : max_size_(max_size) {}
-    ~LinearAssignmentCUDA() { cudaFree(d_buf_); }
+    ~LinearAssignmentCUDA() { cudaFree(d_buf_); cudaFree(d_prices_); }
     LinearAssignmentCUDA(const LinearAssignmentCUDA&) = delete;
     LinearAssignmentCUDA& operator=(const LinearAssignmentCUDA&) = delete;
 
@@ -31,16 +31,11 @@ public:
               float threshold = 1.0f) {
         if (num_rows == 0 || num_cols == 0) return 0;                          // :243
         const size_t cells = (size_t)num_rows * num_cols;
-        const size_t bytes = cells * sizeof(float) + ((size_t)num_rows + num_cols + 1) * sizeof(int);
-        if (bytes > buf_bytes_) {
-            cudaFree(d_buf_); d_buf_ = nullptr; buf_bytes_ = 0;
-            detail::cu_check(cudaMalloc(&d_buf_, bytes), "cudaMalloc");
-            buf_bytes_ = bytes;
-        }
+        reserve((size_t)(num_rows > max_size_ ? num_rows : max_size_), (size_t)(num_cols > max_size_ ? num_cols : max_size_));
         float* d_cost = static_cast<float*>(d_buf_);
-        int* d_row = reinterpret_cast<int*>(d_cost + cells);
-        int* d_col = d_row + num_rows;
-        int* d_cnt = d_col + num_cols;
+        int* d_row = reinterpret_cast<int*>(d_cost + cells_cap_);
+        int* d_col = d_row + rows_cap_;
+        int* d_cnt = d_col + cols_cap_;
         detail::cu_check(cudaMemcpy(d_cost, cost_matrix, cells * sizeof(float), cudaMemcpyHostToDevice), "upload");
         detail::pb_check(pb_assign_legacy(d_cost, 1, num_rows, num_cols, threshold, d_row, d_col, d_cnt, nullptr), "pb_assign_legacy");
         int count = 0;
@@ -82,10 +77,36 @@ public:
     void sync(cudaStream_t stream = 0) { detail::cu_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
     int getMaxSize() const { return max_size_; }
 
+    // Device memory access (reference hungarian.h:78-81): the object's own buffers, max_size x max_size cost cells and
+    // max_size assignments per side, valid until the object dies.  solve() stages its problem in them ([rows, cols]
+    // row-major at the start of the cost buffer), so after a solve() they hold its cost matrix and assignments as upstream.
+    // The prices of a solve live in registers / shared memory of the solve kernel and are not written back: the price
+    // buffer is provided for API parity and stays zero.
+    float* getCostMatrixDevice() { reserve((size_t)max_size_, (size_t)max_size_); return static_cast<float*>(d_buf_); }
+    int* getRowAssignmentsDevice() { reserve((size_t)max_size_, (size_t)max_size_); return reinterpret_cast<int*>(static_cast<float*>(d_buf_) + cells_cap_); }
+    int* getColAssignmentsDevice() { return getRowAssignmentsDevice() + rows_cap_; }
+    float* getPricesDevice() {
+        if (!d_prices_) {
+            detail::cu_check(cudaMalloc(&d_prices_, (size_t)max_size_ * sizeof(float)), "cudaMalloc");
+            detail::cu_check(cudaMemset(d_prices_, 0, (size_t)max_size_ * sizeof(float)), "cudaMemset");
+        }
+        return d_prices_;
+    }
+
 private:
+    // one allocation: cost [cells_cap_] | row [rows_cap_] | col [cols_cap_] | count
+    void reserve(size_t rows, size_t cols) {
+        if (d_buf_ && rows <= rows_cap_ && cols <= cols_cap_ && rows * cols <= cells_cap_) return;
+        const size_t r = rows > rows_cap_ ? rows : rows_cap_, c = cols > cols_cap_ ? cols : cols_cap_;
+        const size_t cells = r * c > cells_cap_ ? r * c : cells_cap_;
+        cudaFree(d_buf_); d_buf_ = nullptr;
+        detail::cu_check(cudaMalloc(&d_buf_, cells * sizeof(float) + (r + c + 1) * sizeof(int)), "cudaMalloc");
+        rows_cap_ = r; cols_cap_ = c; cells_cap_ = cells;
+    }
     int max_size_;
-    void* d_buf_ = nullptr;       // staging of solve(): cost matrix + assignments + count
-    size_t buf_bytes_ = 0;
+    void* d_buf_ = nullptr;
+    size_t rows_cap_ = 0, cols_cap_ = 0, cells_cap_ = 0;
+    float* d_prices_ = nullptr;
 };
 
 // GreedyMatcherCUDA: cells below the threshold in ascending (cost, row, col) order, each taken when
@@ -98,9 +119,11 @@ public:
         detail::cu_check(cudaStreamCreate(&stream_), "cudaStreamCreate");
         detail::cu_check(cudaMalloc(&d_costs_, (size_t)max_size * max_size * sizeof(float)), "cudaMalloc");
         detail::cu_check(cudaMalloc(&d_row_, (size_t)max_size * sizeof(int)), "cudaMalloc");
+        detail::cu_check(cudaMalloc(&d_col_, (size_t)max_size * sizeof(int)), "cudaMalloc");
+        detail::cu_check(cudaMemset(d_col_, 0xff, (size_t)max_size * sizeof(int)), "cudaMemset");
     }
     ~GreedyMatcherCUDA() {
-        cudaFree(d_costs_); cudaFree(d_row_);
+        cudaFree(d_costs_); cudaFree(d_row_); cudaFree(d_col_);
         cudaStreamDestroy(stream_);
     }
     GreedyMatcherCUDA(const GreedyMatcherCUDA&) = delete;
@@ -116,7 +139,9 @@ public:
         std::vector<int> rows((size_t)num_rows);
         detail::cu_check(cudaMemcpyAsync(rows.data(), d_row_, rows.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_), "download");
         detail::cu_check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
-        for (int r = 0; r < num_rows; ++r) if (rows[r] >= 0) out.push_back({r, rows[r]});
+        std::vector<int> cols((size_t)num_cols, -1);
+        for (int r = 0; r < num_rows; ++r) if (rows[r] >= 0) { out.push_back({r, rows[r]}); cols[(size_t)rows[r]] = r; }
+        detail::cu_check(cudaMemcpy(d_col_, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice), "upload");   // getColMatchedDevice()
         return out;
     }
     // d_row_matched [num_rows] = matched column or -1; asynchronous
@@ -126,10 +151,17 @@ public:
     }
     void sync(cudaStream_t stream = 0) { detail::cu_check(cudaStreamSynchronize(stream ? stream : stream_), "cudaStreamSynchronize"); }
 
+    // Device memory access (reference hungarian.h:149-151): the buffers match() stages its problem in; after match() they
+    // hold its cost matrix, the matched column of every row and the matched row of every column (-1: unmatched).
+    float* getCostsDevice() { return d_costs_; }
+    int* getRowMatchedDevice() { return d_row_; }
+    int* getColMatchedDevice() { return d_col_; }
+
 private:
     int max_size_;
     float* d_costs_ = nullptr;
     int* d_row_ = nullptr;
+    int* d_col_ = nullptr;
     cudaStream_t stream_ = nullptr;
 };
 

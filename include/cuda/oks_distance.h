@@ -21,9 +21,15 @@ public:
         detail::cu_check(cudaMalloc(&d_tracks_, (size_t)max_tracks * 51 * sizeof(float)), "cudaMalloc");
         detail::cu_check(cudaMalloc(&d_detections_, (size_t)max_detections * 51 * sizeof(float)), "cudaMalloc");
         detail::cu_check(cudaMalloc(&d_costs_, (size_t)max_tracks * max_detections * sizeof(float)), "cudaMalloc");
+        detail::cu_check(cudaMalloc(&d_sigmas_, NUM_KEYPOINTS * sizeof(float)), "cudaMalloc");
+        detail::cu_check(cudaMemcpy(d_sigmas_, COCO_SIGMAS, NUM_KEYPOINTS * sizeof(float), cudaMemcpyHostToDevice), "upload");   // oks_distance.cu: ctor
+        detail::cu_check(cudaMalloc(&d_track_bboxes_, (size_t)max_tracks * 4 * sizeof(float)), "cudaMalloc");
+        detail::cu_check(cudaMalloc(&d_det_bboxes_, (size_t)max_detections * 4 * sizeof(float)), "cudaMalloc");
+        detail::cu_check(cudaMemset(d_track_bboxes_, 0, (size_t)max_tracks * 4 * sizeof(float)), "cudaMemset");
+        detail::cu_check(cudaMemset(d_det_bboxes_, 0, (size_t)max_detections * 4 * sizeof(float)), "cudaMemset");
     }
     ~OKSDistanceCUDA() {
-        cudaFree(d_tracks_); cudaFree(d_detections_); cudaFree(d_costs_);
+        cudaFree(d_tracks_); cudaFree(d_detections_); cudaFree(d_costs_); cudaFree(d_sigmas_); cudaFree(d_track_bboxes_); cudaFree(d_det_bboxes_);
         cudaStreamDestroy(stream_);
     }
     OKSDistanceCUDA(const OKSDistanceCUDA&) = delete;
@@ -59,6 +65,12 @@ public:
     float* getCostsDevice() { return d_costs_; }
     float* getTracksDevice() { return d_tracks_; }
     float* getDetectionsDevice() { return d_detections_; }
+    // reference oks_distance.h:86-88.  The sigma table is the one the kernels use (COCO_SIGMAS, types.h).  Upstream stages
+    // keypoint boxes in the two bbox buffers on the way to the IoU distance; here boxes stay in registers inside
+    // pb_pose_distance, so the buffers exist (sized as upstream, zero-filled) but are not written.
+    float* getSigmasDevice() { return d_sigmas_; }
+    float* getTrackBboxesDevice() { return d_track_bboxes_; }
+    float* getDetBboxesDevice() { return d_det_bboxes_; }
     int getMaxTracks() const { return max_tracks_; }
     int getMaxDetections() const { return max_detections_; }
     cudaStream_t getStream() const { return stream_; }
@@ -84,6 +96,7 @@ private:
     }
     int max_tracks_, max_detections_;
     float *d_tracks_ = nullptr, *d_detections_ = nullptr, *d_costs_ = nullptr;
+    float *d_sigmas_ = nullptr, *d_track_bboxes_ = nullptr, *d_det_bboxes_ = nullptr;
     cudaStream_t stream_ = nullptr;
 };
 

@@ -110,6 +110,12 @@ int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_de
 int pb_step(pb_handle_t h, const float* d_heads, float conf_threshold, float nms_threshold,
             int frame_id, pb_stream_t stream);
 
+/* n_steps consecutive pb_step calls in one: step i takes the head batch d_heads + ((first + i) % period) * step_stride
+ * (floats) and frame id frame0 + i.  For callers that hold several batches in device memory (offline video, benchmarks):
+ * one library call instead of n_steps crossings of the language boundary.  Same semantics as the loop it replaces. */
+int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int period, int first, int n_steps,
+                float conf_threshold, float nms_threshold, int frame0, pb_stream_t stream);
+
 /* With pipeline_depth > 1 pb_step returns with NMS and tracker work still running on internal
  * streams.  pb_join makes `stream` wait for all of it (asynchronous, no host blocking); every
  * pb_get_* function and the stage-level entry points join implicitly. */

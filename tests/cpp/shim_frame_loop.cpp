@@ -15,6 +15,7 @@
 #include "cuda/preprocess.h"
 #include "cuda/kalman_filter.h"
 #include "cuda/nms.h"
+#include "cuda/oks_distance.h"
 
 using namespace posebyte;
 using namespace posebyte::cuda;
@@ -88,6 +89,26 @@ int main(int argc, char** argv) {
         int hrow[3], hcol[3];
         const int nsolved = la.solve(cost, 3, 3, hrow, hcol, 0.25f);
         std::printf("solve %d : %d %d %d\n", nsolved, hrow[0], hrow[1], hrow[2]);
+        // the public device accessors of the class API (reference hungarian.h:78-81,149-151, oks_distance.h:86-88)
+        {
+            int drow[3], dcol[3];
+            float dcost[9], prices[8], sig[NUM_KEYPOINTS];
+            cudaMemcpy(drow, la.getRowAssignmentsDevice(), 12, cudaMemcpyDeviceToHost);
+            cudaMemcpy(dcol, la.getColAssignmentsDevice(), 12, cudaMemcpyDeviceToHost);
+            cudaMemcpy(dcost, la.getCostMatrixDevice(), sizeof(dcost), cudaMemcpyDeviceToHost);
+            cudaMemcpy(prices, la.getPricesDevice(), sizeof(prices), cudaMemcpyDeviceToHost);
+            bool ok = std::memcmp(drow, hrow, 12) == 0 && std::memcmp(dcol, hcol, 12) == 0 && std::memcmp(dcost, cost, sizeof(cost)) == 0 && prices[0] == 0.0f;
+            GreedyMatcherCUDA gm(8);
+            auto pairs = gm.match(cost, 3, 3, 0.5f);
+            int grow[3], gcol[3];
+            cudaMemcpy(grow, gm.getRowMatchedDevice(), 12, cudaMemcpyDeviceToHost);
+            cudaMemcpy(gcol, gm.getColMatchedDevice(), 12, cudaMemcpyDeviceToHost);
+            ok = ok && pairs.size() == 3 && grow[0] == 0 && grow[1] == 1 && grow[2] == 2 && gcol[0] == 0 && gcol[2] == 2 && gm.getCostsDevice() != nullptr;
+            OKSDistanceCUDA od(8, 8);
+            cudaMemcpy(sig, od.getSigmasDevice(), sizeof(sig), cudaMemcpyDeviceToHost);
+            ok = ok && sig[0] == COCO_SIGMAS[0] && sig[16] == COCO_SIGMAS[16] && od.getTrackBboxesDevice() != nullptr && od.getDetBboxesDevice() != nullptr;
+            std::printf("accessors %s\n", ok ? "ok" : "MISMATCH");
+        }
 
         // PreprocessorCUDA: a 4x2 BGR frame into a 8x8 letterbox
         PreprocessorCUDA pp(16, 16, 8, 8);

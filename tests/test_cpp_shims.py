@@ -74,6 +74,7 @@ def test_reference_frame_loop_through_shims_equals_checker(pb, orc, cuda, tmp_pa
     cost3 = np.array([[0.1, 0.9, 0.8], [0.7, 0.2, 0.9], [0.9, 0.8, 0.3]], np.float32)
     wr, _, wn = orc.assign_legacy(cost3, 0.25)
     assert rest["solve"] == f"solve {wn} : {wr[0]} {wr[1]} {wr[2]}", rest["solve"]
+    assert rest["accessors"] == "accessors ok"        # getCostMatrixDevice / getRow..Device / getPricesDevice / getRowMatchedDevice / getSigmasDevice ...
     # PreprocessorCUDA on a 4x2 frame: scale 2, bars of 2 rows above and below
     img = (10 * np.arange(24)).astype(np.uint8).reshape(2, 4, 3)
     lb, xf = orc.letterbox(img, 8, 8)

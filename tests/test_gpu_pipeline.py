@@ -274,3 +274,19 @@ def test_config3_crowd_16_streams(pb, orc, cuda):
     got, total = gpu_hashes(pb, cuda, heads, max_tracks=256, max_detections=128)
     ref = orc.run_streams(heads, True, threads=8, max_tracks=256, max_detections=128)
     assert np.array_equal(got, ref["hashes"]) and total == ref["tracks_total"] > 2000
+
+
+@pytest.mark.gpu
+def test_step_seq_equals_step_loop(pb, cuda):
+    torch = cuda
+    B, F = 5, 6
+    scfg = pb.synth_config(canvas=640, persons=9, period=16)
+    heads = torch.from_numpy(pb.synth_heads(scfg, 3, B, 0, F, frame_major=True)).cuda()
+    a = pb.Pipeline(num_streams=B, pipeline_depth=4); b = pb.Pipeline(num_streams=B, pipeline_depth=4)
+    for f in range(15):
+        a.step(heads[(2 + f) % F], 100 + f)
+    b.step_seq(heads, 2, 15, 100)
+    a.join(); b.join()
+    o1, c1 = a.get_tracks_all(); o2, c2 = b.get_tracks_all()
+    assert np.array_equal(c1, c2) and c1.sum() > 0 and valid_records(o1, c1) == valid_records(o2, c2)
+    assert a.state_save()[24:] == b.state_save()[24:]

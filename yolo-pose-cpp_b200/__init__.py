@@ -69,7 +69,7 @@ class SynthConfig(C.Structure):
 # Every symbol include/posebyte_b200.h declares (tests check the library exports them all).
 ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
-    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
+    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_step_seq", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
     "pb_get_timing", "pb_get_stream_stage_ns", "pb_debug_timeline", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_set_output_transform", "pb_state_size", "pb_state_save", "pb_state_load", "pb_pose_distance", "pb_greedy_match",
@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
         L.pb_postprocess.argtypes = [vp, vp, fp, fp, vp]
         L.pb_tracker_update.argtypes = [vp, vp, vp, vp, ip, ip, vp]
         L.pb_step.argtypes = [vp, vp, fp, fp, ip, vp]
+        L.pb_step_seq.argtypes = [vp, vp, C.c_size_t, ip, ip, ip, fp, fp, ip, vp]
         L.pb_step_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
         L.pb_join.argtypes = [vp, vp]
         L.pb_submit_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
@@ -247,6 +248,12 @@ class Pipeline:
 
     def step(self, heads, frame_id, conf=0.30, nms=0.65, stream=None):
         check(lib().pb_step(self._h, _dev_f32(heads, self._head_numel, self.cfg.device, "heads"), conf, nms, frame_id, _stream_ptr(stream)))
+
+    def step_seq(self, heads, first, n_steps, frame0, conf=0.30, nms=0.65, stream=None):
+        """n_steps steps on the batches heads[(first + i) % len(heads)] ([F,B,56,N] CUDA tensor), frame ids frame0 + i."""
+        F = heads.shape[0]
+        ptr = _dev_f32(heads, F * self._head_numel, self.cfg.device, "heads")
+        check(lib().pb_step_seq(self._h, ptr, self._head_numel, F, first % F, n_steps, conf, nms, frame0, _stream_ptr(stream)))
 
     def join(self, stream=None):
         """Make `stream` wait for work a pipelined step left on the internal streams."""

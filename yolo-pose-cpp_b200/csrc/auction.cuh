@@ -63,10 +63,21 @@ __device__ __forceinline__ void auction_solve_cta(const float* cost, int R, int 
                 const float* cr = cost + (size_t)rb * C;
                 float bv = -1e9f, sv = -1e9f;
                 int bc = -1;
-                for (int d = lane; d < C; d += 32) {
-                    const float v = -cr[d] - price[d];                     // :61
-                    if (v > bv) { sv = bv; bv = v; bc = d; }
-                    else if (v > sv) { sv = v; }
+                // eight independent loads in flight per lane (the cost matrix of large tables lives in global memory / L2:
+                // one round trip per group instead of one per element)
+                for (int d0 = lane; d0 < C; d0 += 32 * 8) {
+                    float cv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int d = d0 + 32 * u; cv[u] = (d < C) ? cr[d] : 0.0f; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int d = d0 + 32 * u;
+                        if (d < C) {
+                            const float v = -cv[u] - price[d];             // :61
+                            if (v > bv) { sv = bv; bv = v; bc = d; }
+                            else if (v > sv) { sv = v; }
+                        }
+                    }
                 }
                 // warp-level top-2 with three CREDUX reductions on order-preserving integer keys (see the lean
                 // solve below): best value, lowest column holding it (:63), best of the other columns (:67-69)

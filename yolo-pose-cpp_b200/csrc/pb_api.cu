@@ -624,6 +624,14 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int fram
     return enqueue_readback(h, (cudaStream_t)stream);
 }
 
+int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int period, int first, int n_steps,
+                float conf, float nms, int frame0, pb_stream_t stream) {
+    if (!h || !d_heads || period < 1 || first < 0 || n_steps < 0) { pb_set_error("pb_step_seq: bad argument"); return PB_ERR_INVALID; }
+    for (int i = 0; i < n_steps; ++i)
+        PB_TRY(pb_step(h, d_heads + (size_t)((first + i) % period) * step_stride, conf, nms, frame0 + i, stream));
+    return PB_OK;
+}
+
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                  void* h_tracks, int* h_counts) {
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_step_host: null argument"); return PB_ERR_INVALID; }

@@ -304,18 +304,35 @@ static __device__ __forceinline__ void lock_pairs(Ctx& c, unsigned* gate, int na
     // pairs this tier added need the 1e9 writes; the gate words are cleared for all matched rows and columns either way.
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
+    // column masks, one pass: matched columns (colmask) and the ones whose cells still need the write (price buffer words are
+    // idle between solves: reused as the second mask)
+    unsigned* colnew = reinterpret_cast<unsigned*>(s.price);
 #pragma unroll 1
-    for (int ai = c.warp; ai < na; ai += c.nwarps) {
+    for (int w = c.warp; w < words; w += c.nwarps) {
+        const int d = w * 32 + c.lane;
+        const bool colm = (d < D) && (s.col[d] >= 0);
+        const bool cold = colm && use_backup && (s.colb[d] >= 0);
+        const unsigned bm = __ballot_sync(FULLM, colm), bo = __ballot_sync(FULLM, cold);
+        if (c.lane == 0) { s.colmask[w] = bm; colnew[w] = bm & ~bo; }
+    }
+    __syncthreads();
+    // gate words: one thread per (active row, word)
+#pragma unroll 1
+    for (int i = c.tid; i < na * words; i += c.nthreads) {
+        const int ai = fast_div(i, c.magicW), w = i - ai * words;
         const int t = s.act_list[ai];
-        const bool rowm = s.row[t] >= 0;
-        const bool row_old = use_backup && s.rowb[t] >= 0;
-        for (int w = 0; w < words; ++w) {
-            const int d = w * 32 + c.lane;
-            const bool colm = (d < D) && (s.col[d] >= 0);
-            const unsigned bm = __ballot_sync(FULLM, colm);
-            if (d < D && (rowm || colm) && !(row_old || (use_backup && s.colb[d] >= 0))) c.cost[(size_t)t * D + d] = 1e9f;
-            if (c.lane == 0) gate[t * Dw + w] = rowm ? 0u : (gate[t * Dw + w] & ~bm);
-        }
+        gate[t * Dw + w] = (s.row[t] >= 0) ? 0u : (gate[t * Dw + w] & ~s.colmask[w]);
+    }
+    // cost cells: one warp per (active row that was not locked before, word with something to write)
+#pragma unroll 1
+    for (int i = c.warp; i < na * words; i += c.nwarps) {
+        const int ai = fast_div(i, c.magicW), w = i - ai * words;
+        const int t = s.act_list[ai];
+        if (use_backup && s.rowb[t] >= 0) continue;                   // whole row locked by an earlier tier
+        const unsigned valid = (D - w * 32 >= 32) ? 0xffffffffu : ((1u << (D - w * 32)) - 1u);
+        const unsigned old_cols = use_backup ? (s.colmask[w] & ~colnew[w]) : 0u;   // columns locked by an earlier tier
+        const unsigned m = (s.row[t] >= 0) ? (valid & ~old_cols) : colnew[w];
+        if ((m >> c.lane) & 1u) c.cost[(size_t)t * D + w * 32 + c.lane] = 1e9f;
     }
     __syncthreads();
 }
@@ -1032,20 +1049,30 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         }
         __syncthreads();
         const int ne = s.misc[1];
-        const unsigned magic_ne = div_magic(ne);
+        // pairs (a, b > a) of the eligible list: one thread per (a, chunk of 64 b's)
+        const int chunks = (ne + 63) >> 6;
+        const unsigned magic_ch = div_magic(chunks);
 #pragma unroll 1
-        for (int i = tid; i < ne * ne; i += NT) {
-            const int ia = fast_div(i, magic_ne), ib = i - ia * ne;
-            const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
-            if (t1 >= t2) continue;
-            // boxes whose centres are further apart than the sum of their half extents (plus a margin far above any rounding
-            // of the corner arithmetic) do not intersect: IoU 0, never above 0.7.  NaNs fail the comparison and take the test.
-            const float* a4 = &s.tcent[t1 * 4]; const float* b4 = &s.tcent[t2 * 4];
-            const float hw = (fabsf(a4[2]) + fabsf(b4[2])) * 0.5f, hh = (fabsf(a4[3]) + fabsf(b4[3])) * 0.5f;
-            if (fabsf(a4[0] - b4[0]) > hw * 1.001f + 1.0f || fabsf(a4[1] - b4[1]) > hh * 1.001f + 1.0f) continue;
-            if (center_iou(a4, b4) > 0.7f) {
-                const int pos = atomicAdd(&s.misc[2], 1);
-                if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
+        for (int i = tid; i < ne * chunks; i += NT) {
+            const int ia = fast_div(i, magic_ch), ch = i - ia * chunks;
+            int ib = ch << 6;
+            const int ie = (ib + 64 < ne) ? ib + 64 : ne;
+            if (ib <= ia) ib = ia + 1;
+            if (ib >= ie) continue;
+            const int t1 = s.elig_list[ia];
+            const float ax = s.tcent[t1 * 4], ay = s.tcent[t1 * 4 + 1], aw = s.tcent[t1 * 4 + 2], ah = s.tcent[t1 * 4 + 3];
+#pragma unroll 1
+            for (; ib < ie; ++ib) {
+                const int t2 = s.elig_list[ib];                       // ascending list: t1 < t2
+                const float* b4 = &s.tcent[t2 * 4];
+                // boxes whose centres are further apart than the sum of their half extents (plus a margin far above any
+                // rounding of the corner arithmetic) do not intersect: IoU 0, never above 0.7.  NaNs take the complete test.
+                const float hw = (fabsf(aw) + fabsf(b4[2])) * 0.5f, hh = (fabsf(ah) + fabsf(b4[3])) * 0.5f;
+                if (fabsf(ax - b4[0]) > hw * 1.001f + 1.0f || fabsf(ay - b4[1]) > hh * 1.001f + 1.0f) continue;
+                if (center_iou(&s.tcent[t1 * 4], b4) > 0.7f) {
+                    const int pos = atomicAdd(&s.misc[2], 1);
+                    if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
+                }
             }
         }
         __syncthreads();
