@@ -304,6 +304,23 @@ static __device__ __forceinline__ void lock_pairs(Ctx& c, unsigned* gate, int na
     // pairs this tier added need the 1e9 writes; the gate words are cleared for all matched rows and columns either way.
     TkSmem& s = c.s;
     const int D = c.D, Dw = c.Dw, words = (D + 31) >> 5;
+    if (c.warp_auction) {
+        // small tables (cost matrix in shared memory): one pass, one barrier — a warp per active row, the column mask by ballot
+#pragma unroll 1
+        for (int ai = c.warp; ai < na; ai += c.nwarps) {
+            const int t = s.act_list[ai];
+            const bool rowm = s.row[t] >= 0;
+            for (int w = 0; w < words; ++w) {
+                const int d = w * 32 + c.lane;
+                const bool colm = (d < D) && (s.col[d] >= 0);
+                const unsigned bm = __ballot_sync(FULLM, colm);
+                if (d < D && (rowm || colm)) c.cost[(size_t)t * D + d] = 1e9f;
+                if (c.lane == 0) gate[t * Dw + w] = rowm ? 0u : (gate[t * Dw + w] & ~bm);
+            }
+        }
+        __syncthreads();
+        return;
+    }
     // column masks, one pass: matched columns (colmask) and the ones whose cells still need the write (price buffer words are
     // idle between solves: reused as the second mask)
     unsigned* colnew = reinterpret_cast<unsigned*>(s.price);
@@ -1049,29 +1066,43 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         }
         __syncthreads();
         const int ne = s.misc[1];
-        // pairs (a, b > a) of the eligible list: one thread per (a, chunk of 64 b's)
-        const int chunks = (ne + 63) >> 6;
-        const unsigned magic_ch = div_magic(chunks);
+        if (ne <= 96) {
+            // short lists (the usual frame): one thread per ordered pair
+            const unsigned magic_ne = div_magic(ne);
 #pragma unroll 1
-        for (int i = tid; i < ne * chunks; i += NT) {
-            const int ia = fast_div(i, magic_ch), ch = i - ia * chunks;
-            int ib = ch << 6;
-            const int ie = (ib + 64 < ne) ? ib + 64 : ne;
-            if (ib <= ia) ib = ia + 1;
-            if (ib >= ie) continue;
-            const int t1 = s.elig_list[ia];
-            const float ax = s.tcent[t1 * 4], ay = s.tcent[t1 * 4 + 1], aw = s.tcent[t1 * 4 + 2], ah = s.tcent[t1 * 4 + 3];
-#pragma unroll 1
-            for (; ib < ie; ++ib) {
-                const int t2 = s.elig_list[ib];                       // ascending list: t1 < t2
-                const float* b4 = &s.tcent[t2 * 4];
-                // boxes whose centres are further apart than the sum of their half extents (plus a margin far above any
-                // rounding of the corner arithmetic) do not intersect: IoU 0, never above 0.7.  NaNs take the complete test.
-                const float hw = (fabsf(aw) + fabsf(b4[2])) * 0.5f, hh = (fabsf(ah) + fabsf(b4[3])) * 0.5f;
-                if (fabsf(ax - b4[0]) > hw * 1.001f + 1.0f || fabsf(ay - b4[1]) > hh * 1.001f + 1.0f) continue;
-                if (center_iou(&s.tcent[t1 * 4], b4) > 0.7f) {
+            for (int i = tid; i < ne * ne; i += NT) {
+                const int ia = fast_div(i, magic_ne), ib = i - ia * ne;
+                const int t1 = s.elig_list[ia], t2 = s.elig_list[ib];
+                if (t1 < t2 && center_iou(&s.tcent[t1 * 4], &s.tcent[t2 * 4]) > 0.7f) {
                     const int pos = atomicAdd(&s.misc[2], 1);
                     if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
+                }
+            }
+        } else {
+        // pairs (a, b > a) of the eligible list: one thread per (a, chunk of 64 b's)
+            const int chunks = (ne + 63) >> 6;
+            const unsigned magic_ch = div_magic(chunks);
+#pragma unroll 1
+            for (int i = tid; i < ne * chunks; i += NT) {
+                const int ia = fast_div(i, magic_ch), ch = i - ia * chunks;
+                int ib = ch << 6;
+                const int ie = (ib + 64 < ne) ? ib + 64 : ne;
+                if (ib <= ia) ib = ia + 1;
+                if (ib >= ie) continue;
+                const int t1 = s.elig_list[ia];
+                const float ax = s.tcent[t1 * 4], ay = s.tcent[t1 * 4 + 1], aw = s.tcent[t1 * 4 + 2], ah = s.tcent[t1 * 4 + 3];
+#pragma unroll 1
+                for (; ib < ie; ++ib) {
+                    const int t2 = s.elig_list[ib];                       // ascending list: t1 < t2
+                    const float* b4 = &s.tcent[t2 * 4];
+                    // boxes whose centres are further apart than the sum of their half extents (plus a margin far above any
+                    // rounding of the corner arithmetic) do not intersect: IoU 0, never above 0.7.  NaNs take the complete test.
+                    const float hw = (fabsf(aw) + fabsf(b4[2])) * 0.5f, hh = (fabsf(ah) + fabsf(b4[3])) * 0.5f;
+                    if (fabsf(ax - b4[0]) > hw * 1.001f + 1.0f || fabsf(ay - b4[1]) > hh * 1.001f + 1.0f) continue;
+                    if (center_iou(&s.tcent[t1 * 4], b4) > 0.7f) {
+                        const int pos = atomicAdd(&s.misc[2], 1);
+                        if (pos < DUP_CAP) s.dup[pos] = (t1 << 16) | t2;
+                    }
                 }
             }
         }
