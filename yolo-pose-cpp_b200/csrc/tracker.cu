@@ -98,7 +98,7 @@ pb_tracker_pre_kernel(TrackBuffers tb, TrackParams P, DetSource src, int rows_pe
     int n_in = src.num[b];
     const int D = n_in < Dm ? (n_in < 0 ? 0 : n_in) : Dm;
     const int Dw = (Dm + 31) / 32, words = (D + 31) / 32;
-    // shared memory: det poses [D*51], dcent [D*4], darea [D], pred slice [rps*51], tcent [rps*4], tarea, tav [rps], flags [rps], cell list
+    // shared memory: det poses [Dm*51], dcent [Dm*4], darea [Dm], pred slice [rps*51], tcent [rps*4], tarea, tav, flags [rps], gate words [rps*Dw], cell list [rps*Dm]
     float* s_det = reinterpret_cast<float*>(pre_smem);
     float* s_dcent = s_det + (size_t)Dm * POSE_F;
     float* s_darea = s_dcent + (size_t)Dm * 4;
@@ -196,19 +196,35 @@ pb_tracker_pre_kernel(TrackBuffers tb, TrackParams P, DetSource src, int rows_pe
         }
     }
     __syncthreads();
-    // tier-1 cost pass (:333-425) on the gated cells of the slice's rows that are not LOST: one thread per cell
+    // tier-1 cost pass (:333-425) on the gated cells of the slice's rows that are not LOST.  The gated cells (a sixth of the
+    // table with the gate on) are compacted first — warp-aggregated appends, any order: cells are independent — so that the
+    // 17-exponential loop runs on dense lanes.
+    int* s_cells = reinterpret_cast<int*>(s_gate + (size_t)rows_per_slice * Dw);      // [rps * Dm]
+    __shared__ int s_ncell;
+    if (tid == 0) s_ncell = 0;
+    __syncthreads();
 #pragma unroll 1
-    for (int i = tid; i < nr * words * 32; i += NT) {
-        const int r = i / (words * 32), rem = i - r * (words * 32);
-        const int w = rem >> 5, d = rem;
-        if (d >= D || !((s_gate[r * Dw + w] >> (d & 31)) & 1u)) continue;
+    for (int i = warp; i < nr * words; i += nwarps) {
+        const int r = i / words, w = i - r * words;
+        const unsigned gw = s_gate[r * Dw + w];
+        if (gw == 0u) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_ncell, __popc(gw));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((gw >> lane) & 1u) s_cells[base + __popc(gw & ((1u << lane) - 1u))] = (r << 16) | (w * 32 + lane);
+    }
+    __syncthreads();
+    const int ncell = s_ncell;
+#pragma unroll 1
+    for (int i = tid; i < ncell; i += NT) {
+        const int r = s_cells[i] >> 16, d = s_cells[i] & 0xffff;
         g_cost[(size_t)(r0 + r) * D + d] = oks_cell_cost(s_pred + (size_t)r * POSE_F, s_det + (size_t)d * POSE_F, s_tarea[r], s_darea[d], s_sig, 0.2f);
     }
 }
 
 static size_t pre_smem_bytes(int Dm, int rps) {
     const int Dw = (Dm + 31) / 32;
-    return ((size_t)Dm * (POSE_F + 4 + 1) + (size_t)rps * (POSE_F + 4 + 1 + 1 + 1) + (size_t)rps * Dw) * 4 + 64;
+    return ((size_t)Dm * (POSE_F + 4 + 1) + (size_t)rps * (POSE_F + 4 + 1 + 1 + 1) + (size_t)rps * Dw + (size_t)rps * Dm) * 4 + 64;
 }
 
 // Decide whether (and how) the pre-kernel is used for a handle: tables of at least 64 K cells whose detections fit the
