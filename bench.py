@@ -592,7 +592,7 @@ def main():
     extra = []
     if world == 1 and cid == "2" and not args.no_extra_configs:
         w.close()
-        xsteps = min(max(args.steps, 20), 200)
+        xsteps = min(max(args.steps, 100), 200)         # the other configurations: steady-state figures (the headline keeps the caller's K)
         for xid in ("1", "3", "4", "5a", "5b"):
             xc = CONFIGS[xid]
             xw = Workload(pb, torch, xid, 0, dev, args.pipeline_depth)
