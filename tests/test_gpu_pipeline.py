@@ -290,3 +290,61 @@ def test_step_seq_equals_step_loop(pb, cuda):
     o1, c1 = a.get_tracks_all(); o2, c2 = b.get_tracks_all()
     assert np.array_equal(c1, c2) and c1.sum() > 0 and valid_records(o1, c1) == valid_records(o2, c2)
     assert a.state_save()[24:] == b.state_save()[24:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,occlusion,max_age,chunk", [(6, 1, 4, 0), (6, 1, 4, 16), (64, 0, 10, 16), (70, 1, 30, 7)])
+def test_resident_tracker_sequence_path(pb, orc, cuda, monkeypatch, B, occlusion, max_age, chunk):
+    """pb_step_seq on a pipelined handle takes the resident-tracker path (one tracker CTA per video stream stays on its SM for
+    a chunk of up to 16 steps here, the stream's state in shared memory, and is fed by the decode and NMS kernels of those
+    steps; default up to 49 streams, PB_SEQ=1 up to 74): sequences that are not multiples of the chunk, back-to-back calls
+    without a join, single steps, a reset and a stage-level call in between — states and records must equal the serial
+    handle's bit for bit, and the checker's on some streams."""
+    torch = cuda
+    if chunk:                                      # (0: the handle's defaults — resident path up to 49 streams, chunks of 32)
+        monkeypatch.setenv("PB_SEQ", "1"); monkeypatch.setenv("PB_SEQ_CHUNK", str(chunk))
+    F = 24
+    scfg = pb.synth_config(canvas=640, persons=12, period=48, occlusion=occlusion)
+    host = pb.synth_heads(scfg, 11, B, 0, F, frame_major=True)
+    heads = torch.from_numpy(host).cuda()
+    serial = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=max_age, fuse_stages=0)
+    res = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, max_age=max_age, pipeline_depth=5)
+    f = 0
+    def both_seq(n):
+        nonlocal f
+        for i in range(n):
+            serial.step(heads[(f + i) % F], f + i)
+        res.step_seq(heads, f % F, n, f)
+        f += n
+    def compare(tag, streams=None):
+        o1, c1 = serial.get_tracks_all(); o2, c2 = res.get_tracks_all()
+        assert np.array_equal(c1, c2) and c1.sum() > 0, tag
+        assert valid_records(o1, c1) == valid_records(o2, c2), tag
+        assert serial.state_save()[24:] == res.state_save()[24:], tag
+        for b in (streams or (0, B - 1)):
+            k1, k2 = serial.get_kept(b), res.get_kept(b)
+            assert np.array_equal(k1["keep_anchors"], k2["keep_anchors"]), (tag, b)
+    both_seq(45)                                   # 16 + 16 + 13
+    both_seq(3); both_seq(2); both_seq(37)         # back to back, no join in between
+    compare("after 87 steps in four calls")
+    for i in range(5):                             # single steps (the per-step pipelined path) behind the resident path
+        serial.step(heads[(f + i) % F], f + i); res.step(heads[(f + i) % F], f + i)
+    f += 5
+    both_seq(20)
+    compare("after single steps + 20")
+    serial.reset(); res.reset(); f = 0
+    both_seq(18)
+    serial.postprocess(heads[3]); res.postprocess(heads[3])
+    serial.tracker_update(500); res.tracker_update(500)
+    both_seq(33)
+    compare("after reset, 18 steps, a stage-level call and 33 steps")
+    # the checker on two streams over the last phase
+    for b in (0, B - 1):
+        trk = orc.Tracker(max_age=max_age)
+        for g in range(18):
+            d = orc.postprocess(host[g % F, b]); trk.update(d["poses"], d["scores"], g)
+        d = orc.postprocess(host[3, b]); trk.update(d["poses"], d["scores"], 500)
+        for g in range(18, 51):
+            d = orc.postprocess(host[g % F, b]); trk.update(d["poses"], d["scores"], g)
+        o2, c2 = res.get_tracks_all()
+        assert trk.get_tracks().tobytes() == o2[b, :c2[b]].tobytes(), b

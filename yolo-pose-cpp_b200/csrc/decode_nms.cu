@@ -171,6 +171,114 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     NmSmem s;
     nm_from_offsets(smem_raw, smem_raw, so, s);
     nms_body<NM_THREADS>(s, heads, N, lazy, cs, nseg, segcap, Ccap, Kcap, nms_thr, out, blockIdx.x, gridDim.x, nullptr, nullptr, 0);
+    if (out.ready) {
+        // resident tracker (tracker.cu: pb_tracker_seq_kernel): this stream-frame's kept detections are complete
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(out.ready + blockIdx.x), "r"(out.ready_seq) : "memory");
+        }
+    }
+}
+
+// Tiered variant: half-SM CTAs (512 threads, at most 64 registers, at most ~113 KB of shared memory) so that two of them — or
+// one and a resident tracker CTA (tracker.cu: pb_tracker_seq_kernel) — share an SM.  The shared memory holds the working set of
+// CT candidates; a stream with more (up to Ccap, rule R1) keeps its per-candidate arrays in a global scratch instead (spill
+// path: the same code on generic pointers, same results), exactly as the fused per-stream kernel does (fused.cu).
+constexpr int NMT_THREADS = 512;
+
+struct NmsTierParams {
+    const float* heads;
+    int N, lazy;
+    CandScratch cs;
+    int nseg, segcap, Ccap, CT, Kcap;
+    float nms_thr;
+    PostBuffers out;
+    SmemOffsets so_small, so_big;
+    unsigned char* spill;       // [B, spill_stride] (nullptr when CT == Ccap)
+    size_t spill_stride;
+};
+
+// (cold path, a function of its own: kept out of the register allocation of the common path; the parameters stay in constant memory)
+static __device__ __noinline__ void nms_tier_spill(const NmsTierParams& F, int b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmSmem s;
+    nm_from_offsets(smem_raw, F.spill + (size_t)b * F.spill_stride, F.so_big, s);
+    nms_body<NMT_THREADS>(s, F.heads, F.N, F.lazy, F.cs, F.nseg, F.segcap, F.Ccap, F.Kcap, F.nms_thr, F.out, b, (int)gridDim.x, nullptr, nullptr, 0);
+}
+
+__global__ void __launch_bounds__(NMT_THREADS, 2)
+pb_nms_tier_kernel(const __grid_constant__ NmsTierParams F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    int total = 0;
+    for (int sg = 0; sg < F.nseg; ++sg) total += F.cs.counts[b * F.nseg + sg];
+    if (total <= F.CT || F.spill == nullptr) {
+        NmSmem s;
+        nm_from_offsets(smem_raw, smem_raw, F.so_small, s);
+        nms_body<NMT_THREADS>(s, F.heads, F.N, F.lazy, F.cs, F.nseg, F.segcap, F.CT, F.Kcap, F.nms_thr, F.out, b, gridDim.x, nullptr, nullptr, 0);
+    } else {
+        nms_tier_spill(F, b);
+    }
+    if (F.out.ready) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(F.out.ready + b), "r"(F.out.ready_seq) : "memory");
+        }
+    }
+}
+
+NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin) {
+    NmsTierPlan p{};
+    p.ok = false;
+    size_t target = 113 * 1024;                       // (228 KB - 2 x 1 KB reserved) / 2
+    if (target > smem_optin) target = smem_optin;
+    int ct = 0;
+    for (int c = 64; c <= max_cand; c += 32) {
+        if (nm_carve(nullptr, c, max_keep, nullptr) <= target) ct = c; else break;
+    }
+    if (nm_carve(nullptr, max_cand, max_keep, nullptr) <= target) ct = max_cand;
+    if (ct < 64) return p;
+    p.CT = ct;
+    p.so_small = nm_offsets(ct, max_keep);
+    p.smem_bytes = nm_carve(nullptr, ct, max_keep, nullptr);
+    size_t fixed_bytes = 0, cand_bytes = 0;
+    p.so_big = nm_offsets(max_cand, max_keep, true, &fixed_bytes, &cand_bytes);
+    p.spill_stride = ct < max_cand ? ((cand_bytes + 255) & ~(size_t)255) : 0;
+    if (fixed_bytes > p.smem_bytes) return p;
+    p.ok = true;
+    return p;
+}
+
+cudaError_t launch_nms_tier(const NmsTierPlan& tp, const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
+                            const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, unsigned char* spill, cudaStream_t stream) {
+    NmsTierParams F{};
+    F.heads = d_heads; F.N = N; F.lazy = sweep; F.cs = cs; F.nseg = plan.nseg; F.segcap = plan.segcap;
+    F.Ccap = max_cand; F.CT = tp.CT; F.Kcap = max_keep; F.nms_thr = nms_thr; F.out = out;
+    F.so_small = tp.so_small; F.so_big = tp.so_big; F.spill = tp.spill_stride ? spill : nullptr; F.spill_stride = tp.spill_stride;
+    if (tp.spill_stride && !spill) return cudaErrorInvalidValue;
+    const cudaError_t e = ensure_dyn_smem((const void*)pb_nms_tier_kernel, tp.smem_bytes);
+    if (e != cudaSuccess) return e;
+    pb_nms_tier_kernel<<<B, NMT_THREADS, tp.smem_bytes, stream>>>(F);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// The resident tracker kernel waits on the device for these kernels.  With CUDA's lazy module loading the FIRST launch of a
+// kernel loads its code, which may have to wait for running kernels: a kernel that spins until that launch has run would
+// wait for its time-out.  The host layer therefore loads (and sizes) them before it enqueues a resident tracker launch.
+cudaError_t preload_post_kernels(int max_cand, int max_keep, const NmsTierPlan* tier) {
+    cudaFuncAttributes a{};
+    cudaError_t e = cudaFuncGetAttributes(&a, (const void*)pb_decode_gather_kernel<HEAD_ROWS>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, (const void*)pb_decode_gather_kernel<BOX_ROWS>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, (const void*)pb_nms_kernel);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pb_nms_kernel, decode_nms_smem_bytes(max_cand, max_keep));
+    if (e == cudaSuccess && tier && tier->ok) {
+        e = cudaFuncGetAttributes(&a, (const void*)pb_nms_tier_kernel);
+        if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pb_nms_tier_kernel, tier->smem_bytes);
+    }
+    return e;
 }
 
 // =======================================================================================

@@ -50,6 +50,8 @@ using namespace pb;
 // One slot of the step pipeline: candidate scratch (decode+gather -> NMS) and kept detections
 // (NMS -> tracker) with the events that order their reuse.
 struct PipeSlot {
+    unsigned char* spill = nullptr;   // resident-tracker path: spill scratch of the tiered NMS kernel (per slot: NMS launches of several steps overlap)
+    int* ready = nullptr;          // [B] resident-tracker path: sequence number of the step whose kept detections the slot holds (per stream)
     PostBuffers post{};
     CandScratch cand{};
     void* outputs = nullptr;       // [B,Dm] TrackOutput of the step that used this slot (a read-back may still be copying them
@@ -81,6 +83,23 @@ struct pb_handle_st {
     TrackerPlan plan{};
     FusedPlan fplan{};             // fused per-stream kernel (fused.cu); fplan.ok == false: separate NMS and tracker kernels
     unsigned char* d_spill = nullptr;
+    // resident-tracker path of pb_step_seq (tracker.cu: pb_tracker_seq_kernel): its own ring of 2 * seq_chunk slots, allocated at the
+    // first use; a chunk of steps = decode + NMS launches per step and ONE tracker launch; the two halves of the ring alternate
+    std::vector<PipeSlot> seq_ring;
+    int seq_chunk = 0;             // steps per tracker launch (0: path not available for this handle)
+    int seq_half = 0;              // half of the ring the next chunk uses
+    bool seq_half_used[2] = {false, false};
+    bool seq_inflight = false;     // kernels of the resident path may still be running
+    cudaEvent_t ev_seq_trk[2] = {nullptr, nullptr};   // per half: the tracker launch of the last chunk that used it
+    static constexpr int SEQ_MAX_LANES = 4;
+    int seq_lanes = 3;             // step i's decode and NMS kernels run back to back on lane i % seq_lanes
+    cudaEvent_t ev_seq_nms[SEQ_MAX_LANES] = {};       // per lane: its last NMS launch
+    cudaEvent_t ev_seq_dec[SEQ_MAX_LANES] = {};       // per lane: its last decode launch (the last reader of a borrowed head tensor)
+    cudaEvent_t ev_seq_start = nullptr;
+    cudaStream_t s_seq_nms[SEQ_MAX_LANES] = {}, s_seq_trk = nullptr;
+    TrackerPlan seq_plan{};
+    NmsTierPlan exp_tier{}; unsigned char* exp_spill = nullptr;   // PB_NMS_TIER experiment (serial path)
+    NmsTierPlan seq_nms{};         // ok: the steps of the resident path use the tiered (half-SM) NMS kernel
     std::vector<void*> allocs;
     // host-buffer path
     float* d_stage = nullptr;      // [B,56,N] device staging
@@ -184,6 +203,8 @@ void pb_default_config(pb_config* c) {
     c->fuse_stages = 2;
 }
 
+static void seq_configure(pb_handle_st* h, int sm_count);
+
 static int build_handle(pb_handle_st* h) {
     const pb_config& c = h->cfg;
     const size_t B = c.num_streams, T = c.max_tracks, Dm = c.max_detections, K = c.max_keep;
@@ -282,6 +303,12 @@ static int build_handle(pb_handle_st* h) {
             PB_TRY(dev_alloc(h, &t.lgate_g, B * T * Dw));
             PB_TRY(dev_alloc(h, &t.tarea_g, B * T));
         }
+    }
+    {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        seq_configure(h, sms);
     }
     if (h->fplan.ok && h->fplan.spill_stride) PB_TRY(dev_alloc(h, &h->d_spill, B * h->fplan.spill_stride));
     PB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -386,6 +413,19 @@ int pb_destroy(pb_handle_t h) {
     if (h->s_trk3) cudaStreamDestroy(h->s_trk3);
     for (cudaStream_t q : h->f_lane) if (q) cudaStreamDestroy(q);
     if (h->s_rb) cudaStreamDestroy(h->s_rb);
+    for (int i = 0; i < 2; ++i) if (h->ev_seq_trk[i]) cudaEventDestroy(h->ev_seq_trk[i]);
+    for (int i = 0; i < pb_handle_st::SEQ_MAX_LANES; ++i) {
+        if (h->s_seq_nms[i]) cudaStreamDestroy(h->s_seq_nms[i]);
+        if (h->ev_seq_nms[i]) cudaEventDestroy(h->ev_seq_nms[i]);
+        if (h->ev_seq_dec[i]) cudaEventDestroy(h->ev_seq_dec[i]);
+    }
+    if (h->s_seq_trk) cudaStreamDestroy(h->s_seq_trk);
+    if (h->ev_seq_start) cudaEventDestroy(h->ev_seq_start);
+    for (PipeSlot& sl : h->seq_ring) {
+        if (sl.ev_gather) cudaEventDestroy(sl.ev_gather);
+        if (sl.ev_nms) cudaEventDestroy(sl.ev_nms);
+        if (sl.ev_trk) cudaEventDestroy(sl.ev_trk);
+    }
     for (PipeSlot& sl : h->ring) {
         if (sl.ev_gather) cudaEventDestroy(sl.ev_gather);
         if (sl.ev_nms) cudaEventDestroy(sl.ev_nms);
@@ -397,7 +437,18 @@ int pb_destroy(pb_handle_t h) {
 }
 
 // Make `stream` wait for everything a pipelined pb_step left running on the internal streams.
+// ... and for the kernels of the resident-tracker path (pb_step_seq)
+static int join_seq(pb_handle_st* h, cudaStream_t stream) {
+    if (!h->seq_inflight) return PB_OK;
+    for (int i = 0; i < 2; ++i)
+        if (h->seq_half_used[i]) PB_CUDA(cudaStreamWaitEvent(stream, h->ev_seq_trk[i], 0));
+    for (int i = 0; i < h->seq_lanes; ++i) PB_CUDA(cudaStreamWaitEvent(stream, h->ev_seq_nms[i], 0));
+    h->seq_inflight = false;
+    return PB_OK;
+}
+
 static int join_on(pb_handle_st* h, cudaStream_t stream) {
+    PB_TRY(join_seq(h, stream));
     if (!h->inflight) return PB_OK;
     for (PipeSlot& sl : h->ring)
         if (sl.used) { PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0)); PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_trk, 0)); }
@@ -434,6 +485,18 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
         cudaEventRecord(h->ev_pool[em], (cudaStream_t)stream);
         h->ev_gather.push_back({e0, em});
     }
+    static const bool tier_exp = getenv("PB_NMS_TIER") != nullptr;          // experiment: the tiered (half-SM) kernel on the serial path
+    if (tier_exp) {
+        if (!h->exp_tier.ok) {
+            int dev = 0, optin = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            h->exp_tier = nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin);
+            if (h->exp_tier.ok && h->exp_tier.spill_stride) PB_TRY(dev_alloc(h, &h->exp_spill, (size_t)c.num_streams * h->exp_tier.spill_stride));
+        }
+        PB_CUDA(launch_nms_tier(h->exp_tier, d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan,
+                                h->cand, h->post, h->exp_spill, (cudaStream_t)stream));
+    } else
     PB_CUDA(launch_nms(d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
         cudaEventRecord(h->ev_pool[e1], (cudaStream_t)stream);
@@ -506,6 +569,7 @@ static int enqueue_readback(pb_handle_st* h, cudaStream_t stream) {
 static int step_fused(pb_handle_st* h, const float* d_heads, float conf, float nms, int frame_id, cudaStream_t stream) {
     const pb_config& c = h->cfg;
     const bool piped = c.pipeline_depth > 1;
+    PB_TRY(join_seq(h, stream));            // (the lane's kernel follows the decode on the caller's stream)
     TrackParams tp = track_params(h, frame_id);
     const int depth = (int)h->ring.size();
     const int pos = tp.seq % depth;
@@ -561,6 +625,7 @@ static int step_fused(pb_handle_st* h, const float* d_heads, float conf, float n
 // frame).  Results are complete for the caller after pb_join or any pb_get_* call.
 static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, float nms, int frame_id, cudaStream_t stream) {
     const pb_config& c = h->cfg;
+    PB_TRY(join_seq(h, stream));            // (NMS and tracker follow the decode on the caller's stream)
     const int pos = h->inflight || h->ring[h->cur].used ? (h->cur + 1) % (int)h->ring.size() : h->cur;
     PipeSlot& sl = h->ring[pos];
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0));          // scratch still being read
@@ -624,9 +689,176 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int fram
     return enqueue_readback(h, (cudaStream_t)stream);
 }
 
+// ---- resident-tracker path of pb_step_seq ------------------------------------------------------------------------------
+// A sequence of steps is cut into chunks of at most seq_chunk steps.  Per chunk: ONE tracker launch (one CTA per video stream,
+// resident for the whole chunk, the stream's state in shared memory from the first frame to the last) on its own stream,
+// enqueued FIRST, then per step the decode+gather and NMS kernels back to back on internal lane (step mod lanes).  The tracker
+// CTA of a stream runs frame i as soon as the NMS kernel of step i has published that stream's kept detections in the step's
+// slot (a per-stream flag, release / acquire): no launch, no hand-over between CTAs and no event between the frames of a
+// stream, and no stream waits for another.  The decode and NMS kernels depend on nothing the tracker kernel does (their slots
+// belong to the half of the ring the previous chunk did not use), so its waits cannot deadlock as long as its CTAs leave SMs
+// free (seq_configure); the kernels it waits for are loaded before the first launch (preload_post_kernels).  Chunks alternate
+// between the two halves of the ring; a half is reused when the tracker launch that read it has completed (event).  The
+// borrowed head tensors are read by the decode kernels only: the caller's stream is ordered behind the last of them.
+static int alloc_slot(pb_handle_st* h, PipeSlot& sl, unsigned long long* post_ns) {
+    const pb_config& c = h->cfg;
+    const size_t B = c.num_streams, Dm = c.max_detections, K = c.max_keep;
+    const size_t nsc = B * (size_t)h->dplan.nseg * (size_t)h->dplan.segcap;
+    PB_TRY(dev_alloc(h, &sl.post.det_poses, B * K * POSE_F));
+    PB_TRY(dev_alloc(h, &sl.post.det_bboxes, B * K * 4));
+    PB_TRY(dev_alloc(h, &sl.post.det_scores, B * K));
+    PB_TRY(dev_alloc(h, &sl.post.keep_slots, B * K));
+    PB_TRY(dev_alloc(h, &sl.post.keep_anchors, B * K));
+    PB_TRY(dev_alloc(h, &sl.post.num_keep, B));
+    PB_TRY(dev_alloc(h, &sl.post.num_cand, B));
+    sl.post.stage_ns = post_ns;
+    PB_TRY(dev_alloc(h, &sl.cand.records, nsc * HEAD_ROWS));
+    PB_TRY(dev_alloc(h, &sl.cand.anchors, nsc));
+    PB_TRY(dev_alloc(h, &sl.cand.counts, B * (size_t)h->dplan.nseg));
+    unsigned char* outp = nullptr;
+    PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
+    sl.outputs = outp;
+    PB_TRY(dev_alloc(h, &sl.num_outputs, B));
+    PB_TRY(dev_alloc(h, &sl.ready, B));
+    if (h->seq_nms.ok && h->seq_nms.spill_stride) PB_TRY(dev_alloc(h, &sl.spill, B * h->seq_nms.spill_stride));
+    PB_CUDA(cudaEventCreateWithFlags(&sl.ev_gather, cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&sl.ev_nms, cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&sl.ev_trk, cudaEventDisableTiming));
+    return PB_OK;
+}
+
+// Can this handle use the resident path, and with which tracker plan?  Small tables only (the auction runs in one warp, the
+// frame is a chain of short stages: exactly what a resident CTA is good at; large tables keep the row-sliced pre-kernel), and
+// the tracker CTAs must leave at least half of the SMs to the decode and NMS kernels they wait for.
+static void seq_configure(pb_handle_st* h, int sm_count) {
+    const pb_config& c = h->cfg;
+    h->seq_chunk = 0;
+    if (c.pipeline_depth < 2 || h->plan.pre_slices > 0) return;
+    bool forced = false;
+    if (const char* e = getenv("PB_SEQ")) { if (atoi(e) == 0) return; forced = true; }
+    bool resident = true, compact = false;
+    if (const char* e = getenv("PB_SEQ_RESIDENT_STATE")) resident = atoi(e) != 0;
+    if (const char* e = getenv("PB_SEQ_COMPACT")) compact = atoi(e) != 0;
+    TrackerPlan p = tracker_plan(c.max_tracks, c.max_detections, compact, resident);
+    if (compact) p.threads = 512;
+    if (const char* e = getenv("PB_SEQ_THREADS")) { const int t = atoi(e); if (t == 256 || t == 512 || t == 1024) p.threads = t; }
+    if (!(p.cost_in_smem && p.det_in_smem && p.pred_in_smem)) return;
+    if ((long)c.max_tracks * c.max_detections > 16384) return;
+    // One tracker CTA per SM (1024 threads), resident for a whole chunk: the decode and NMS kernels that feed them get the other
+    // SMs.  Measured (tools/seq_probe.py, 640x640 heads, 20 persons): up to 48 streams the tracker CTAs are never kept waiting and
+    // the step takes 25.9-26.9 us against 28.9-29.6 us for the per-step path; at 64 streams the 84 SMs left cannot feed them
+    // (38.8 us against 32.3), so the per-step path stays the default there.  PB_SEQ=1 asks for the resident path wherever it
+    // cannot deadlock (half of the SMs free).
+    if (2 * c.num_streams > sm_count) return;
+    if (!forced && 3 * c.num_streams > sm_count) return;
+    h->seq_plan = p;
+    h->seq_nms = NmsTierPlan{};
+    if (const char* e = getenv("PB_SEQ_NMS_TIER")) {
+        if (atoi(e) != 0) {
+            int dev = 0, optin = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            h->seq_nms = nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin);
+        }
+    }
+    if (const char* e = getenv("PB_SEQ_LANES")) { const int v = atoi(e); if (v >= 1 && v <= pb_handle_st::SEQ_MAX_LANES) h->seq_lanes = v; }
+    int chunk = PB_SEQ_MAX;
+    if (const char* e = getenv("PB_SEQ_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= PB_SEQ_MAX) chunk = v; }
+    h->seq_chunk = chunk;
+}
+
+static int seq_prepare(pb_handle_st* h) {
+    if (!h->seq_ring.empty()) return PB_OK;
+    PB_CUDA(preload_post_kernels(h->cfg.max_candidates, h->cfg.max_keep, &h->seq_nms));
+    std::vector<PipeSlot> ring((size_t)2 * h->seq_chunk);
+    for (PipeSlot& sl : ring) PB_TRY(alloc_slot(h, sl, h->ring[0].post.stage_ns));
+    for (int i = 0; i < 2; ++i) PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_trk[i], cudaEventDisableTiming));
+    for (int i = 0; i < h->seq_lanes; ++i) {
+        PB_CUDA(cudaStreamCreateWithFlags(&h->s_seq_nms[i], cudaStreamNonBlocking));
+        PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_nms[i], cudaEventDisableTiming));
+        PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_dec[i], cudaEventDisableTiming));
+        PB_CUDA(cudaEventRecord(h->ev_seq_nms[i], h->s_seq_nms[i]));
+    }
+    PB_CUDA(cudaStreamCreateWithFlags(&h->s_seq_trk, cudaStreamNonBlocking));
+    PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_start, cudaEventDisableTiming));
+    h->seq_ring.swap(ring);
+    return PB_OK;
+}
+
+static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_stride, int period, int first, int n_steps,
+                             float conf, float nms, int frame0, cudaStream_t stream) {
+    const pb_config& c = h->cfg;
+    PB_TRY(seq_prepare(h));
+    if (h->inflight) {
+        // steps of the other paths may still run on their internal streams: everything of this call is ordered behind them
+        for (PipeSlot& sl : h->ring)
+            if (sl.used) { PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_nms, 0)); PB_CUDA(cudaStreamWaitEvent(stream, sl.ev_trk, 0)); }
+        h->inflight = false;
+    }
+    // the internal streams follow whatever the caller's stream holds now (and, through it, the steps joined above)
+    PB_CUDA(cudaEventRecord(h->ev_seq_start, stream));
+    PB_CUDA(cudaStreamWaitEvent(h->s_seq_trk, h->ev_seq_start, 0));
+    const int L = h->seq_lanes;
+    for (int l = 0; l < L; ++l) PB_CUDA(cudaStreamWaitEvent(h->s_seq_nms[l], h->ev_seq_start, 0));
+    const int M = h->seq_chunk;
+    for (int s0 = 0; s0 < n_steps; s0 += M) {
+        const int n = (n_steps - s0 < M) ? (n_steps - s0) : M;
+        const int half = h->seq_half;
+        TrackParams tp = track_params(h, frame0 + s0);
+        SeqTable q{};
+        q.n = n; q.stride = c.max_keep;
+        for (int i = 0; i < n; ++i) {
+            PipeSlot& sl = h->seq_ring[(size_t)half * M + i];
+            q.det_poses[i] = sl.post.det_poses; q.det_scores[i] = sl.post.det_scores; q.num_keep[i] = sl.post.num_keep;
+            q.ready[i] = sl.ready; q.outputs[i] = sl.outputs; q.num_outputs[i] = sl.num_outputs;
+        }
+        // the slots of this half are free once the tracker launch that read them has completed: every lane waits for it
+        // before its first kernel of this chunk
+        const bool wait_half = h->seq_half_used[half];
+        if (wait_half)
+            for (int l = 0; l < L && l < n; ++l) PB_CUDA(cudaStreamWaitEvent(h->s_seq_nms[(tp.seq + l) % L], h->ev_seq_trk[half], 0));
+        // the tracker launch first: its CTAs are resident (and waiting for frame 0) while the host enqueues the steps
+        PB_CUDA(launch_tracker_seq(h->trk, tp, q, h->seq_plan, h->s_seq_trk));
+        PB_CUDA(cudaEventRecord(h->ev_seq_trk[half], h->s_seq_trk));
+        h->seq_half_used[half] = true;
+        h->seq_inflight = true;
+        for (int i = 0; i < n; ++i) {
+            PipeSlot& sl = h->seq_ring[(size_t)half * M + i];
+            const int seq = tp.seq + i;
+            const int lane = seq % L;
+            cudaStream_t ns = h->s_seq_nms[lane];
+            const float* heads = d_heads + (size_t)((first + s0 + i) % period) * step_stride;
+            PB_CUDA(launch_decode_gather(heads, c.num_streams, c.num_anchors, conf, false, h->dplan, sl.cand, ns));
+            if (s0 + i >= n_steps - L) PB_CUDA(cudaEventRecord(h->ev_seq_dec[lane], ns));
+            sl.post.ready = sl.ready; sl.post.ready_seq = seq;
+            sl.post.dbg_slot = seq & 63;
+            if (h->seq_nms.ok)
+                PB_CUDA(launch_nms_tier(h->seq_nms, heads, c.num_anchors, 0, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand,
+                                        sl.post, sl.spill, ns));
+            else
+                PB_CUDA(launch_nms(heads, c.num_anchors, 0, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
+            if (s0 + i >= n_steps - L) PB_CUDA(cudaEventRecord(h->ev_seq_nms[lane], ns));
+            if (i == n - 1) {
+                h->post = sl.post; h->cand = sl.cand;
+                h->trk.outputs = sl.outputs; h->trk.num_outputs = sl.num_outputs;
+            }
+        }
+        h->trk_seq = tp.seq + n - 1;
+        h->frames += n;
+        h->seq_half ^= 1;
+    }
+    // the borrowed head tensors: later work on the caller's stream is ordered behind their last readers (the decode kernels)
+    for (int l = 0; l < L && l < n_steps; ++l) PB_CUDA(cudaStreamWaitEvent(stream, h->ev_seq_dec[(h->trk_seq - l) % L], 0));
+    return PB_OK;
+}
+
 int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int period, int first, int n_steps,
                 float conf, float nms, int frame0, pb_stream_t stream) {
     if (!h || !d_heads || period < 1 || first < 0 || n_steps < 0) { pb_set_error("pb_step_seq: bad argument"); return PB_ERR_INVALID; }
+    if (h->seq_chunk > 0 && n_steps >= 2 && !h->profiling && !h->lazy_keypoints && !h->rb_tracks) {
+        DevGuard dev_guard(h->cfg.device);
+        return step_seq_resident(h, d_heads, step_stride, period, first, n_steps, conf, nms, frame0, (cudaStream_t)stream);
+    }
     for (int i = 0; i < n_steps; ++i)
         PB_TRY(pb_step(h, d_heads + (size_t)((first + i) % period) * step_stride, conf, nms, frame0 + i, stream));
     return PB_OK;

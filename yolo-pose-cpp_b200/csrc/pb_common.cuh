@@ -30,6 +30,8 @@ struct PostBuffers {
     unsigned long long* stage_ns;  // [B, 16] list, rank, load, nms, output (ns sums), [7] = launches
     unsigned long long* dbg;       // optional timeline [64 launches][B][6] (PB_TIMELINE=1): [3] NMS begin, [4] NMS end
     int dbg_slot;
+    int* ready;          // [B] or nullptr: the stand-alone NMS kernel stores ready_seq here (release) once a stream's kept detections are
+    int ready_seq;       //     written — the resident tracker kernel (tracker.cu: pb_tracker_seq_kernel) acquires it per stream-frame
 };
 
 // ---- candidate scratch between the decode+gather kernel and the NMS kernel (L2 resident) ----
@@ -126,9 +128,17 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
 cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 lazy, 2 deferred*/, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
+// tiered NMS kernel (decode_nms.cu: pb_nms_tier_kernel): half-SM CTAs, shared memory for CT candidates, spill path beyond
+struct NmsTierPlan { bool ok; int CT; size_t smem_bytes, spill_stride; SmemOffsets so_small, so_big; };
+NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin);
+cudaError_t launch_nms_tier(const NmsTierPlan& tp, const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
+                            const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, unsigned char* spill, cudaStream_t stream);
+
+cudaError_t preload_post_kernels(int max_cand, int max_keep, const NmsTierPlan* tier);
+
 struct TrackerPlan { size_t smem_bytes, prefix_bytes; int threads; int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap; SmemOffsets so;
-                     int pre_slices; size_t pre_smem; };   // pre_slices > 0: large tables, row-sliced pre-kernel with this many CTAs per stream
-TrackerPlan tracker_plan(int T, int Dm, bool compact = false);
+                     int pre_slices; size_t pre_smem; int resident; };   // pre_slices > 0: large tables, row-sliced pre-kernel with this many CTAs per stream
+TrackerPlan tracker_plan(int T, int Dm, bool compact = false, bool resident = false);
 cudaError_t launch_tracker(const TrackBuffers& tb, TrackParams p, const DetSource& src,
                            const TrackerPlan& plan, cudaStream_t stream);
 // large tables: predict + centres + gates + tier-1 OKS cost pass, row-sliced over plan.pre_slices CTAs per stream
@@ -149,6 +159,21 @@ struct RingTable {
     int depth;
     int wait_window;                       // a CTA whose frame is fewer than this many frames from the head of its chain waits for its turn (tracker_body.cuh)
 };
+
+// Resident tracker (tracker.cu: pb_tracker_seq_kernel): one CTA per video stream runs the tracker stages of `n` consecutive
+// frames in ONE launch; frame i's kept detections come from slot i of this table as soon as the NMS kernel of that step has
+// published them (PostBuffers::ready).  Frame i has sequence number TrackParams::seq + i and frame id TrackParams::frame_id + i.
+constexpr int PB_SEQ_MAX = 32;
+struct SeqTable {
+    const float* det_poses[PB_SEQ_MAX];    // [B, stride, 51]
+    const float* det_scores[PB_SEQ_MAX];   // [B, stride]
+    const int* num_keep[PB_SEQ_MAX];       // [B]
+    const int* ready[PB_SEQ_MAX];          // [B]
+    void* outputs[PB_SEQ_MAX];             // [B, Dm] TrackOutput
+    int* num_outputs[PB_SEQ_MAX];          // [B]
+    int n, stride;
+};
+cudaError_t launch_tracker_seq(const TrackBuffers& tb, TrackParams p, const SeqTable& q, const TrackerPlan& plan, cudaStream_t stream);
 
 // fused per-stream kernel (fused.cu): NMS + tracker of one stream-frame in one CTA
 struct FusedPlan {

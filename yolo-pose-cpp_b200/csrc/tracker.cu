@@ -5,9 +5,12 @@
 
 namespace pb {
 
-static void tk_offsets(int T, int Dm, int cost_s, int det_s, int pred_s, int term_floats, int cell_cap, SmemOffsets& o) {
+static void tk_offsets(int T, int Dm, int cost_s, int det_s, int pred_s, int term_floats, int cell_cap, SmemOffsets& o, int res_s = 0) {
     TkSmem t;
-    tk_carve(nullptr, T, Dm, cost_s, det_s, pred_s, term_floats, cell_cap, &t);
+    tk_carve(nullptr, T, Dm, cost_s, det_s, pred_s, term_floats, cell_cap, &t, nullptr, res_s);
+    o.off[36] = (unsigned)(uintptr_t)t.poses;
+    o.off[37] = (unsigned)(uintptr_t)t.vel;
+    o.off[38] = (unsigned)(uintptr_t)t.dirty;
     o.off[0] = (unsigned)(uintptr_t)t.active;
     o.off[1] = (unsigned)(uintptr_t)t.states;
     o.off[2] = (unsigned)(uintptr_t)t.hits;
@@ -50,7 +53,9 @@ static void tk_offsets(int T, int Dm, int cost_s, int det_s, int pred_s, int ter
 // round instead of 481+ and a cell list of 2048 instead of 4096 entries (more rounds for large frames, same results:
 // cells are independent).  The term buffer also holds the compacted cost rows of the single-warp auction
 // (at most 32 rows x 64 columns).
-TrackerPlan tracker_plan(int T, int Dm, bool compact) {
+// resident: the layout of the resident tracker (pb_tracker_seq_kernel) — everything in shared memory, plus the stream's poses,
+// velocities and dirty flags; plan.resident stays 0 when that does not fit.
+TrackerPlan tracker_plan(int T, int Dm, bool compact, bool resident) {
     TrackerPlan p{};
     const size_t budget = 200 * 1024;
     p.cost_in_smem = p.det_in_smem = p.pred_in_smem = 0;
@@ -67,8 +72,11 @@ TrackerPlan tracker_plan(int T, int Dm, bool compact) {
     if (used + cost_b <= budget) { p.cost_in_smem = 1; used += cost_b; }
     if (used + det_b <= budget) { p.det_in_smem = 1; used += det_b; }
     if (used + pred_b <= budget) { p.pred_in_smem = 1; used += pred_b; }
-    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.cell_cap, nullptr, &p.prefix_bytes);
-    tk_offsets(T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.cell_cap, p.so);
+    p.resident = 0;
+    if (resident && p.cost_in_smem && p.det_in_smem && p.pred_in_smem &&
+        tk_carve(nullptr, T, Dm, 1, 1, 1, term_floats, p.cell_cap, nullptr, nullptr, 1) <= 224 * 1024) p.resident = 1;
+    p.smem_bytes = tk_carve(nullptr, T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.cell_cap, nullptr, &p.prefix_bytes, p.resident);
+    tk_offsets(T, Dm, p.cost_in_smem, p.det_in_smem, p.pred_in_smem, term_floats, p.cell_cap, p.so, p.resident);
     const long cells = (long)T * Dm;
     // small tables (the tracker's 128 x 64 case): 1024 threads — the auction runs in one warp whatever the
     // block size, every other stage (copies, gate, cost passes, outputs) is data-parallel and measured
@@ -258,6 +266,101 @@ __global__ void __launch_bounds__(NTHREADS)
 pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tracker_body<NTHREADS, ALLSMEM, false>(tb, P, src, blockIdx.x, smem_raw, 0, P.seq, P.frame_id, tb.outputs, tb.num_outputs);
+}
+
+// =======================================================================================
+// Resident tracker: the tracker stages of Q.n consecutive frames of every video stream in ONE launch, one CTA per stream
+// (the per-stream pipeline of the north star: a stream's CTA stays on its SM while the decode and NMS kernels of the following
+// steps feed it).  Frame i is run as soon as the NMS kernel of its step has published the stream's kept detections
+// (PostBuffers::ready, release / acquire per stream).  Streams never wait for each other; a frame whose auction runs to the
+// iteration limit delays only the later frames of its own stream; frames 1.. of a launch need no hand-over between CTAs.
+// The only device-side wait is for a kernel that was enqueued without any dependency on this one (pb_api.cu), so it cannot
+// deadlock while the grid leaves SMs free for that kernel (the host layer checks); a 0.5 s time-out guards against misuse.
+// =======================================================================================
+template <int NTHREADS, bool ALLSMEM, bool RES>
+__global__ void __launch_bounds__(NTHREADS, (ALLSMEM && NTHREADS <= 512) ? 1024 / NTHREADS : 1)   // at most 64 registers: room for other CTAs beside it
+pb_tracker_seq_kernel(const __grid_constant__ TrackBuffers tb, const __grid_constant__ TrackParams P, const __grid_constant__ SeqTable Q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ok;
+    const int b = blockIdx.x;
+    unsigned long long waited = 0ull;                // telemetry: time spent waiting for the NMS kernels (thread 0)
+#pragma unroll 1
+    for (int i = 0; i < Q.n; ++i) {
+        const int seq = P.seq + i;
+        if (threadIdx.x == 0) {
+            const int* flag = Q.ready[i] + b;
+            const unsigned long long w0 = globaltimer_ns();
+            unsigned long long w1 = w0;
+            int ok = 1;
+            for (;;) {
+                int v;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (v == seq) break;
+                w1 = globaltimer_ns();
+                if (w1 - w0 > 500000000ull) { ok = 0; break; }
+                __nanosleep(64);
+            }
+            waited += w1 - w0;
+            s_ok = ok;
+        }
+        __syncthreads();
+        int r = -1;
+        if (s_ok) {
+            const DetSource src{Q.det_poses[i], Q.det_scores[i], Q.num_keep[i], Q.stride};
+            r = tracker_body<NTHREADS, ALLSMEM, false, RES>(tb, P, src, b, smem_raw, 0, seq, P.frame_id + i, Q.outputs[i], Q.num_outputs[i], i == 0 ? 0 : 2,
+                                                            true, i == 0, i == Q.n - 1);
+        }
+        if (r < 0) {
+            // time-out (here or inside the frame): the state stays as it is, the sequence numbers of the launch are passed on
+            // and the sticky error flag invalidates the results (every synchronising entry point reports it)
+            if (threadIdx.x == 0) {
+                atomicExch(tb.error_flag, 1);
+                const int last = P.seq + Q.n - 1;
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.seq_done + b), "r"(last) : "memory");
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(tb.out_done + b), "r"(last) : "memory");
+                tb.chain[b] = chain_pack(0u, last + 1, 0);
+            }
+            return;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tb.stage_ns[(size_t)b * 20 + 15] += waited;      // (slot 15: waits for a predecessor / for the detections)
+}
+
+cudaError_t launch_tracker_seq(const TrackBuffers& tb, TrackParams p, const SeqTable& q, const TrackerPlan& plan, cudaStream_t stream) {
+    const bool allsmem = plan.cost_in_smem && plan.det_in_smem && plan.pred_in_smem;
+    // variants: 1024 threads (one CTA per SM) or 512 threads (two per SM) with everything in shared memory, state resident
+    // (plan.resident) or reloaded per frame; 256 / 512 / 1024 threads with parts of the working set in global memory
+    int v;
+    if (allsmem && plan.threads == 1024) v = plan.resident ? 5 : 3;
+    else if (allsmem && plan.threads == 512) v = plan.resident ? 6 : 4;
+    else if (allsmem && plan.threads == 256 && plan.resident) v = 7;
+    else v = plan.threads == 256 ? 0 : (plan.threads == 512 ? 1 : 2);
+    const void* fn = v == 0 ? (const void*)pb_tracker_seq_kernel<256, false, false> : v == 1 ? (const void*)pb_tracker_seq_kernel<512, false, false>
+                   : v == 2 ? (const void*)pb_tracker_seq_kernel<1024, false, false> : v == 3 ? (const void*)pb_tracker_seq_kernel<1024, true, false>
+                   : v == 4 ? (const void*)pb_tracker_seq_kernel<512, true, false> : v == 5 ? (const void*)pb_tracker_seq_kernel<1024, true, true>
+                   : v == 6 ? (const void*)pb_tracker_seq_kernel<512, true, true> : (const void*)pb_tracker_seq_kernel<256, true, true>;
+    {
+        const cudaError_t e = ensure_dyn_smem(fn, plan.smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    p.cost_in_smem = plan.cost_in_smem; p.det_in_smem = plan.det_in_smem; p.pred_in_smem = plan.pred_in_smem;
+    p.term_floats = plan.term_floats; p.cell_cap = plan.cell_cap;
+    p.so = plan.so;
+    p.precomputed = 0;
+    switch (v) {
+        case 0: pb_tracker_seq_kernel<256, false, false><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, q); break;
+        case 1: pb_tracker_seq_kernel<512, false, false><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, q); break;
+        case 2: pb_tracker_seq_kernel<1024, false, false><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, q); break;
+        case 3: pb_tracker_seq_kernel<1024, true, false><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, q); break;
+        case 4: pb_tracker_seq_kernel<512, true, false><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, q); break;
+        case 5: pb_tracker_seq_kernel<1024, true, true><<<p.B, 1024, plan.smem_bytes, stream>>>(tb, p, q); break;
+        case 6: pb_tracker_seq_kernel<512, true, true><<<p.B, 512, plan.smem_bytes, stream>>>(tb, p, q); break;
+        default: pb_tracker_seq_kernel<256, true, true><<<p.B, 256, plan.smem_bytes, stream>>>(tb, p, q); break;
+    }
+    count_launch();
+    return cudaGetLastError();
 }
 
 __global__ void pb_tracker_reset_kernel(TrackBuffers tb, int B, int T, int Dm, int seq) {

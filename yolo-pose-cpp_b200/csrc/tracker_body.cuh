@@ -46,6 +46,7 @@ struct TkSmem {
     int* cell_list;                                                                   // [cell_cap] gated cells compacted per chunk of active rows
     int* aowner;                                                                      // [Dm] auction scratch
     float *cost, *det, *pred;                                                         // optional
+    float *poses, *vel; int* dirty;                                                   // optional (resident tracker): [T*51], [T*34], [T]
 };
 
 __host__ __device__ inline size_t tk_align(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -53,7 +54,7 @@ __host__ __device__ inline size_t tk_align(size_t x) { return (x + 15) & ~(size_
 // The arrays that receive this frame's detections (scores, poses) come first: in the fused per-stream kernel they are
 // written by the NMS stage while the rest of the layout is still the NMS stage's own (`prefix`: their size).
 __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, int cost_s, int det_s,
-                                           int pred_s, int term_floats, int cell_cap, TkSmem* s, size_t* prefix = nullptr) {
+                                           int pred_s, int term_floats, int cell_cap, TkSmem* s, size_t* prefix = nullptr, int res_s = 0) {
     const int Dw = (Dm + 31) / 32;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = tk_align(off + bytes); return o; };
@@ -72,6 +73,8 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
     size_t o_aown = take((size_t)Dm * 4);
     size_t o_cost = cost_s ? take((size_t)T * Dm * 4) : 0;
     size_t o_pred = pred_s ? take((size_t)T * POSE_F * 4) : 0;
+    // resident tracker: the stream's poses, velocities and dirty flags stay in shared memory over the frames of a launch
+    size_t o_poses = res_s ? take((size_t)T * POSE_F * 4) : 0, o_vel = res_s ? take((size_t)T * 34 * 4) : 0, o_dirty = res_s ? take((size_t)T * 4) : 0;
     if (s) {
         s->colbid = (unsigned long long*)(base + o_colbid);
         s->acc = (unsigned long long*)(base + o_acc);
@@ -93,6 +96,9 @@ __host__ __device__ inline size_t tk_carve(unsigned char* base, int T, int Dm, i
         s->cost = cost_s ? (float*)(base + o_cost) : nullptr;
         s->det = det_s ? (float*)(base + o_det) : nullptr;
         s->pred = pred_s ? (float*)(base + o_pred) : nullptr;
+        s->poses = res_s ? (float*)(base + o_poses) : nullptr;
+        s->vel = res_s ? (float*)(base + o_vel) : nullptr;
+        s->dirty = res_s ? (int*)(base + o_dirty) : nullptr;
     }
     return off;
 }
@@ -138,6 +144,9 @@ __device__ __forceinline__ void tk_from_offsets(unsigned char* base, const SmemO
     s.cost = reinterpret_cast<float*>(base + o.off[33]);
     s.det = reinterpret_cast<float*>(base + o.off[34]);
     s.pred = reinterpret_cast<float*>(base + o.off[35]);
+    s.poses = reinterpret_cast<float*>(base + o.off[36]);
+    s.vel = reinterpret_cast<float*>(base + o.off[37]);
+    s.dirty = reinterpret_cast<int*>(base + o.off[38]);
 }
 // ---------------------------------------------------------------------------------------
 // keypoint-box statistics of one pose (17 lanes of a warp would be overkill: T+D poses)
@@ -583,13 +592,23 @@ __device__ __forceinline__ bool chain_advance(unsigned long long* w) {
     }
 }
 
+// wait_mode (stand-alone): 2 = the previous frame of this video stream was run by this very CTA (resident tracker,
+// tracker.cu: pb_tracker_seq_kernel): both waits for the predecessor are skipped.
 // wait_mode (fused): 1 = this CTA waits for its turn and takes the chain at the wait point; first_of_owner: the first
 // frame this CTA runs (the previous owner may still be assembling its records: second wait).  Returns (fused) 1 when the
 // CTA keeps the chain and the stream's next frame has arrived, 0 when the chain was handed on or given up, -1 on a time-out.
-template <int NTHREADS, bool ALLSMEM, bool FUSED>
+// RES (resident tracker, tracker.cu: pb_tracker_seq_kernel; stand-alone mode only): the CTA runs consecutive frames of its
+// stream and the stream's state stays in shared memory between them — poses, velocities and dirty flags in arrays of their
+// own, the small slabs, centres and the cost matrix where the stages keep them anyway.  res_first: load the state from
+// global memory (first frame of the launch); res_last: write it back and release the stream (last frame).  In between a
+// frame reads nothing but its detections from global memory and stores only what nobody on the device waits for
+// (predictions, centres, scores, records).  Same expressions on the same values: same results.
+template <int NTHREADS, bool ALLSMEM, bool FUSED, bool RES = false>
 __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackParams& P, const DetSource& src, const int b,
                                              unsigned char* smem_raw, const int D_fused, const int seq, const int frame_id,
-                                             void* outputs, int* num_outputs, const int wait_mode = 0, const bool first_of_owner = true) {
+                                             void* outputs, int* num_outputs, const int wait_mode = 0, const bool first_of_owner = true,
+                                             const bool res_first = true, const bool res_last = true) {
+    const bool st_load = !RES || res_first, st_store = !RES || res_last;
     // (no local copy of the parameter block: it stays in constant memory)
     const bool cost_in_smem = ALLSMEM || P.cost_in_smem, det_in_smem = ALLSMEM || P.det_in_smem, pred_in_smem = ALLSMEM || P.pred_in_smem;
     Ctx c;
@@ -602,9 +621,12 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     c.warp = threadIdx.x >> 5; c.nwarps = NTHREADS >> 5;
     const int tid = c.tid, NT = c.nthreads;
 
-    // per-stream slabs
-    float* g_poses = tb.poses + (size_t)b * T * POSE_F;
-    float* g_vel = tb.vel + (size_t)b * T * 34;
+    // per-stream slabs (resident tracker: poses, velocities and dirty flags are the shared-memory copies)
+    float* const gm_poses = tb.poses + (size_t)b * T * POSE_F;
+    float* const gm_vel = tb.vel + (size_t)b * T * 34;
+    int* const gm_dirty = tb.pred_dirty + (size_t)b * T;
+    float* g_poses = RES ? s.poses : gm_poses;
+    float* g_vel = RES ? s.vel : gm_vel;
     float* g_scores = tb.scores + (size_t)b * T;
     float* g_pred = tb.predicted + (size_t)b * T * POSE_F;
     float* g_tcent = tb.tcent + (size_t)b * T * 4;
@@ -613,7 +635,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     int* g_states = tb.states + (size_t)b * T; int* g_ids = tb.ids + (size_t)b * T;
     int* g_hits = tb.hits + (size_t)b * T; int* g_ages = tb.ages + (size_t)b * T;
     int* g_last = tb.last_frame + (size_t)b * T; int* g_active = tb.active + (size_t)b * T;
-    int* g_dirty = tb.pred_dirty + (size_t)b * T;
+    int* g_dirty = RES ? s.dirty : gm_dirty;
     int* g_scal = tb.scalars + (size_t)b * 4;
     unsigned long long* g_ns = tb.stage_ns + (size_t)b * 20;
 
@@ -645,7 +667,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) { if (!FUSED) s.dscore[d] = src_score[d]; s.col[d] = -1; }
     if (tid < 32) s.misc[tid] = 0;
-    if (tid < 20) s.acc[tid] = 0ull;
+    if (tid < 20 && st_load) s.acc[tid] = 0ull;     // (resident tracker: accumulated over the frames of the launch)
     if (tid < KP) s.sig[tid] = kSigmas[tid];
     if (D > 0) {
         // detection centres / areas (kernelComputeBboxCenters on the detections, :1180-1186) and the cleared gate
@@ -674,7 +696,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         // waiting CTA: the frames before this one have been run and their owner yields at its state release
         if (!chain_take_over(tb.chain + b, seq)) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; }
     }
-    if (!FUSED && tid == 0) {
+    if (!FUSED && wait_mode != 2 && tid == 0) {
         const int want = seq - 1;
         const int* flag = tb.seq_done + b;
         const unsigned long long w0 = globaltimer_ns();
@@ -721,14 +743,22 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         const int t = t0 + c.lane;
         int a = 0, st = 0;
         if (t < T) {
-            a = g_active[t]; st = g_states[t];
-            s.active[t] = a; s.states[t] = st; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
+            if (st_load) {
+                a = g_active[t]; st = g_states[t];
+                s.active[t] = a; s.states[t] = st; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
+                const int dy = gm_dirty[t];
+                if (RES) s.dirty[t] = dy;
+                s.rowbc[t] = dy;            // predicted pose changed since its centre was derived (idle auction scratch)
+            } else {                        // resident tracker: the previous frame left the slabs in shared memory
+                a = s.active[t]; st = s.states[t];
+                s.rowbc[t] = s.dirty[t];
+            }
             s.row[t] = -1;
-            s.rowbc[t] = g_dirty[t];        // predicted pose changed since its centre was derived (idle auction scratch)
         }
+        const int* act_src = st_load ? g_active : s.active;
         int start = 0;
 #pragma unroll 1
-        for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, g_active[pb + c.lane] == 1));
+        for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, act_src[pb + c.lane] == 1));
         const bool act = (a == 1);
         const unsigned bm = __ballot_sync(FULLM, act);
         const unsigned lm = __ballot_sync(FULLM, act && st == ST_LOST);
@@ -736,13 +766,22 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         if (act) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
         if (c.lane == 0 && t0 + 32 >= T) s.misc[0] = start + __popc(bm);
     }
+    if (st_load) {
 #pragma unroll 1
-    for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
+        for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
+        if (RES) {
+#pragma unroll 1
+            for (int i = tid; i < T * POSE_F; i += NT) s.poses[i] = gm_poses[i];
+#pragma unroll 1
+            for (int i = tid; i < T * 34; i += NT) s.vel[i] = gm_vel[i];
+        }
+    }
     c.det = det_w;
     c.cost = cost_in_smem ? s.cost : g_cost;
     c.warp_auction = cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
     c.pred = pred_in_smem ? s.pred : g_pred;
-    if (cost_in_smem) for (int i = tid; i < T * D; i += NT) s.cost[i] = g_cost[i];
+    // (resident tracker: the whole persistent matrix is loaded once — later frames index it with their own D, quirk Q1)
+    if (cost_in_smem && st_load) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
     __syncthreads();
     const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
     stamp(0);
@@ -864,7 +903,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     // The predecessor's record assembly reads g_poses after it released the state (second release at its end):
     // nothing before this point writes g_poses, tb.outputs or the telemetry slots; wait for it here (it finished
     // long ago unless the launches ran far apart from the usual order).
-    if ((!FUSED || first_of_owner) && tid == 0) {
+    if ((FUSED ? first_of_owner : wait_mode != 2) && tid == 0) {
         const int want = seq - 1;
         const unsigned long long w0 = globaltimer_ns();
         for (;;) {
@@ -1135,17 +1174,27 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     stamp(9);
 
     // ---------------- write back state ----------------
+    // (resident tracker: after the last frame of the launch only — nobody reads the stream's state in between)
+    // (the column assignments are stored every frame: a frame writes its own D entries and the tail keeps older frames' values)
+#pragma unroll 1
+    for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
+    if (st_store) {
     int cnt_local = 0;
 #pragma unroll 1
     for (int t = tid; t < T; t += NT) {
         g_active[t] = s.active[t]; g_states[t] = s.states[t]; g_hits[t] = s.hits[t]; g_ids[t] = s.ids[t];
         g_ages[t] = s.ages[t];
+        if (RES) gm_dirty[t] = s.dirty[t];
         tb.row_assign[(size_t)b * T + t] = s.row[t];
         cnt_local += (s.active[t] == 1);
     }
+    if (cost_in_smem) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) g_cost[i] = s.cost[i];
+    if (RES) {
 #pragma unroll 1
-    for (int d = tid; d < D; d += NT) tb.col_assign[(size_t)b * Dm + d] = s.col[d];
-    if (cost_in_smem) for (int i = tid; i < T * D; i += NT) g_cost[i] = s.cost[i];
+        for (int i = tid; i < T * POSE_F; i += NT) gm_poses[i] = s.poses[i];
+#pragma unroll 1
+        for (int i = tid; i < T * 34; i += NT) gm_vel[i] = s.vel[i];
+    }
     // block-wide sum of cnt_local (update()'s return value, :1130-1136)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cnt_local += __shfl_xor_sync(FULLM, cnt_local, off);
@@ -1165,6 +1214,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         // the records; or keep it (the next frame has arrived: this CTA goes on with it afterwards); or give it up
         if (FUSED) s.misc[11] = chain_advance(tb.chain + b) ? 1 : 0;
     }
+    }   // st_store
 
     // ---------------- outputs: getActiveTracks (:1594-1636) on the device ------------------
     if (tid < 32) {
@@ -1225,10 +1275,11 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     if (tid == 0) {
         num_outputs[b] = n_out;
         const unsigned long long now = globaltimer_ns();
-        s.acc[10] = now - t_begin;
-        s.acc[11] = 1ull;
+        s.acc[10] += now - t_begin;
+        s.acc[11] += 1ull;
     }
     __syncthreads();
+    if (!st_store) return 0;            // resident tracker: the next frame follows in this CTA
     if (tid < 18 && s.acc[tid] != 0ull) g_ns[tid] += s.acc[tid];
     if (tid == 19 && s.acc[19] != 0ull) g_ns[19] += s.acc[19];
     // second release: records and telemetry written, g_poses no longer read
