@@ -62,9 +62,5 @@ for w in which:
     occ, age = (1, 30) if B == 128 else (0, 10)
     name = f"B{B}"
     run(name, B, occ, age, 5, {"PB_SEQ": "0", "PB_NO_FUSED": "1"})
-    run(name, B, occ, age, 5, {"PB_SEQ_THREADS": "512"})
-    run(name, B, occ, age, 5, {"PB_SEQ_THREADS": "512", "PB_SEQ_LANES": "2"})
-    run(name, B, occ, age, 5, {"PB_SEQ_THREADS": "512", "PB_SEQ_LANES": "1"})
-    run(name, B, occ, age, 5, {"PB_SEQ_THREADS": "256"})
-    run(name, B, occ, age, 5, {"PB_SEQ_THREADS": "256", "PB_SEQ_LANES": "2"})
-    run(name, B, occ, age, 5, {"PB_SEQ_THREADS": "512", "PB_SEQ_CHUNK": "32"})
+    run(name, B, occ, age, 5, {"PB_SEQ": "1"})
+    run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_COMPACT": "1", "PB_SEQ_NMS_TIER": "1"})

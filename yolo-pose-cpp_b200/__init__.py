@@ -18,7 +18,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libposebyte_b200.so")
+LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(LIB_DIR, "libposebyte_b200.so")   # PB_LIB_PATH: development builds (telemetry)
 SYNTH_PATH = os.path.join(LIB_DIR, "libpb_synth.so")
 
 PB_OK, PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_UNSUPPORTED, PB_ERR_NO_DEVICE = 0, -1, -2, -3, -4

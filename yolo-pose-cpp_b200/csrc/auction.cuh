@@ -370,13 +370,15 @@ static __device__ __noinline__ void auction_solve_hybrid32(const float* cost_s, 
 // can never bid again; they stay unassigned exactly as upstream).
 // With more than eight bidders (iteration 0 of a solve) lane = row scans the compacted rows.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned lean_ord(float f) {          // f is never -0.0 here (callers add +0.0f)
-    const unsigned b = __float_as_uint(f);
-    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+// sm_100a warp reductions on fp32 (CREDUX.MAX.F32): no order-preserving integer keys, no conversions on the chain
+__device__ __forceinline__ float warp_max_f32(float v) {
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
 }
 
 // value of the lane's columns for bidder row j: fmaxf drops NaN and everything at or below the -1e9 floor
-// (never best, never second: :55-69); + 0.0f folds -0.0 into +0.0 so the integer keys order like the floats
+// (never best, never second: :55-69).  -0.0 and +0.0 compare equal below, as in the reference's comparisons.
 template <int NC>
 __device__ __forceinline__ void lean_values(const float* cc, int C, int j, const float (&p)[NC], int lane,
                                             float& bv, float& sv, int& bsel) {
@@ -384,7 +386,7 @@ __device__ __forceinline__ void lean_values(const float* cc, int C, int j, const
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int d = lane + 32 * c;
-        v[c] = (d < C) ? (fmaxf(-cc[j * C + d] - p[c], -1e9f) + 0.0f) : -1e9f;             // :61
+        v[c] = (d < C) ? fmaxf(-cc[j * C + d] - p[c], -1e9f) : -1e9f;                      // :61
     }
     bv = v[0]; sv = -1e9f; bsel = 0;
     if (NC == 2) {
@@ -398,19 +400,24 @@ __device__ unsigned long long g_prof[8];
 #else
 #define LEAN_T(x)
 #endif
-struct LeanBid { unsigned m; int rk; unsigned bits; };   // warp-uniform: best-value key, (column << 8 | owner + 1), bid bits
+struct LeanBid { float m; int rk; unsigned bits; };   // warp-uniform: best value, (column << 8 | owner + 1), bid bits
 
+// After the first reduction (best value m) the other three are independent of each other: the lowest column holding m
+// packed with its owner (:63), the best of the values that are not a lane's own m, and the lanes holding m.  With two or
+// more such lanes the second value is m itself (multiset second maximum, :67-69), otherwise the best of the rest.
 template <int NC>
 __device__ __forceinline__ LeanBid lean_bid(float bv, float sv, int bsel, const int (&own)[NC], int lane, float eps) {
     const unsigned FULL = 0xffffffffu;
     LeanBid r;
-    const unsigned kb = lean_ord(bv);
-    r.m = __reduce_max_sync(FULL, kb);                                                     // best value
+    r.m = warp_max_f32(bv);                                                                // best value
+    const bool top = (bv == r.m);
     const int osel = (NC == 2 && bsel) ? own[NC - 1] : own[0];
-    const int key = (kb == r.m) ? (((lane + 32 * bsel) << 8) | (osel + 1)) : 0x7fffffff;
+    const int key = top ? (((lane + 32 * bsel) << 8) | (osel + 1)) : 0x7fffffff;
     r.rk = __reduce_min_sync(FULL, key);                                                   // lowest column holding it (:63) + its owner
-    const unsigned m2 = __reduce_max_sync(FULL, (key == r.rk) ? lean_ord(sv) : kb);        // best of the other columns
-    r.bits = __float_as_uint(hy_unord(r.m) - hy_unord(m2) + eps);                          // :99 (positive)
+    const float m2p = warp_max_f32(top ? sv : bv);
+    const unsigned ties = __ballot_sync(FULL, top);
+    const float m2 = (ties & (ties - 1u)) ? r.m : m2p;                                     // best of the other columns
+    r.bits = __float_as_uint(r.m - m2 + eps);                                              // :99 (positive)
     return r;
 }
 
@@ -419,7 +426,7 @@ __device__ __forceinline__ LeanBid lean_bid(float bv, float sv, int bsel, const 
 template <int NB, int NC>
 __device__ __forceinline__ bool lean_iter(const float* cc, int C, unsigned& ub, const unsigned (&bit)[NB], float eps,
                                           float (&p)[NC], int (&own)[NC], int lane) {
-    const unsigned ORD_FLOOR = lean_ord(-1e9f);
+    const float ORD_FLOOR = -1e9f;
     LEAN_T(t0)
     int j[NB];
 #pragma unroll
@@ -489,18 +496,38 @@ __device__ __forceinline__ bool lean_regime(const float* cc, int C, unsigned& ub
     }
 }
 
+// The bids of a solve's FIRST iteration (prices 0, nobody assigned) depend on a row's own costs only: one warp per row,
+// lane = column, the arithmetic of lean_bid.  The tracker computes them with the whole CTA while it compacts the cost
+// rows, so the single-warp solve below does not start with a 32-lane row scan (measured: ~2 250 of the ~4 300 cycles
+// of a typical tier-1 solve).  cr: the row's costs [C]; bc (-1: no column above the floor) and bid bits as lean32 wants them.
+template <int NC>
+__device__ __forceinline__ void lean_first_bid(const float* cr, int C, int R, int lane, int& bc, unsigned& bits) {
+    float p0[NC];
+    int own0[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p0[c] = 0.0f; own0[c] = -1; }
+    float bv, sv;
+    int bsel;
+    lean_values<NC>(cr, C, 0, p0, lane, bv, sv, bsel);
+    const LeanBid q = lean_bid<NC>(bv, sv, bsel, own0, lane, 1.0f / (float)(R + 1));
+    bc = (q.m != -1e9f) ? (q.rk >> 8) : -1;
+    bits = q.bits;
+}
+
+// pre_bc / pre_bits (may be null): the first iteration's bids of the active rows, by position in act_list (lean_first_bid)
 template <int NC>
 static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R, int C, const int* act_list, int na,
                                                          int* row, int* col, float* price, int* owner,
                                                          unsigned* colbid, int* colrow, unsigned ub0 = 0xffffffffu,
-                                                         unsigned long long* tele = nullptr) {
+                                                         unsigned long long* tele = nullptr,
+                                                         const int* pre_bc = nullptr, const unsigned* pre_bits = nullptr) {
 #ifdef PB_AUCTION_TELE
 #define LEAN_COUNT(slot) if (tele && lane == 0) tele[slot] += 1000ull;
 #else
 #define LEAN_COUNT(slot)
 #endif
     const unsigned FULL = 0xffffffffu;
-    const unsigned ORD_FLOOR = lean_ord(-1e9f);
+    const float ORD_FLOOR = -1e9f;
     const int lane = threadIdx.x & 31;
     for (int t = lane; t < R; t += 32) row[t] = -1;
     for (int d = lane; d < C; d += 32) { col[d] = -1; colbid[d] = 0u; colrow[d] = 0x7fffffff; }
@@ -517,6 +544,43 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
     const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
     const int C4 = C & ~3;
     int it = 0;
+    if (pre_bc != nullptr && ub != 0u && iters > 0) {
+        // ---- iteration 0 from the caller's first bids (lean_first_bid): every lane takes, for its own columns, the highest
+        // bid (ascending rows + '>' = lowest row among equal bids, :100) out of broadcast loads; nobody is evicted yet ----
+        unsigned best[NC];
+        int w[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { best[c] = 0u; w[c] = -1; }
+        unsigned drop = 0u;
+#pragma unroll 1
+        for (int j0 = 0; j0 < na; j0 += 8) {                                               // eight rows per round: independent broadcast loads
+            int bcj[8];
+            unsigned bj[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jb = j0 + u;
+                const bool in = (jb < na) && ((ub >> jb) & 1u);
+                bcj[u] = in ? pre_bc[jb] : -2;
+                bj[u] = in ? pre_bits[jb] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (bcj[u] == -1) drop |= 1u << (j0 + u);                                  // no column above -1e9: leaves for good
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (bcj[u] == lane + 32 * c && bj[u] > best[c]) { best[c] = bj[u]; w[c] = j0 + u; }
+            }
+        }
+        unsigned tog = 0u;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (w[c] >= 0) { tog |= 1u << w[c]; own[c] = w[c]; p[c] += __uint_as_float(best[c]); }   // :107-121
+        tog = __reduce_or_sync(FULL, tog);
+        ub = (ub & ~drop) ^ tog;                                                           // winners leave
+        if (tog == 0u) ub = 0u;                                                            // no bid: fixed point
+        eps *= 0.9f;                                                                       // :402
+        it = 1;
+    }
 #pragma unroll 1
     while (it < iters && ub != 0u) {
 #ifdef LEAN_PROFILE

@@ -253,6 +253,17 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
         const int D = c.D;
 #pragma unroll 1
         for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = fast_div(i, c.magicD); cc[i] = s.cost[s.act_list[ai] * D + (i - ai * D)]; }
+        // ... and the first iteration's bids (prices 0, nobody assigned: a row's own costs decide), one warp per active row
+        int* pre_bc = s.rowbc;                                       // [T], idle since the centre stage
+        unsigned* pre_bits = reinterpret_cast<unsigned*>(s.rowbid);
+#pragma unroll 1
+        for (int ai = c.warp; ai < na; ai += c.nwarps) {
+            const float* cr0 = s.cost + (size_t)s.act_list[ai] * D;
+            int bc;
+            unsigned bits;
+            if (D <= 32) lean_first_bid<1>(cr0, D, c.T, c.lane, bc, bits); else lean_first_bid<2>(cr0, D, c.T, c.lane, bc, bits);
+            if (c.lane == 0) { pre_bc[ai] = bc; pre_bits[ai] = bits; }
+        }
         __syncthreads();
         if (c.tid < 32) {
             unsigned* cb = reinterpret_cast<unsigned*>(s.colbid);
@@ -260,8 +271,8 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
             // rows matched in an earlier tier are locked: all their cells are 1e9 (lock_pairs), they can never bid
             const bool may_bid = c.tid < na && !(after_lock && s.rowb[s.act_list[c.tid]] >= 0);
             const unsigned ub0 = __ballot_sync(FULLM, may_bid);
-            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc);
-            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc);
+            if (D <= 32) auction_solve_lean32<1>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc, pre_bc, pre_bits);
+            else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc, pre_bc, pre_bits);
         }
         __syncthreads();
     } else if (c.warp_auction && na <= 32) {
