@@ -607,7 +607,7 @@ def main():
             v = xw.B * xsteps / (xms / 1e3)
             rec = {"config_id": xid, "workload": xc["workload"], "value": v, "unit": "stream-frames/s", "steps": xsteps,
                    "us_per_batch": xms / xsteps * 1e3, "us_per_stream_frame": xms / xsteps * 1e3 / xw.B, "us_per_batch_latency": xlat,
-                   "streams_per_gpu": xw.B, "kernel_us": {k: v_ for k, v_ in xk.items() if k != "launches"},
+                   "streams_per_gpu": xw.B, "step_path": xw.pipe.step_path(), "kernel_us": {k: v_ for k, v_ in xk.items() if k != "launches"},
                    "roofline_step": {"bound": "hbm", "achieved": v * bsf / 1e9, "peak": peak, "unit": "GB/s", "frac": v * bsf / 1e9 / peak,
                                      "bytes_per_stream_frame": bsf},
                    "e2e": {"value": xw.B * xe["steps"] / xe["seconds"], "unit": "stream-frames/s", "steps": xe["steps"],
@@ -687,7 +687,7 @@ def main():
                    "l2": f"{w.F} distinct input batches rotate ({w.F * B * (56 * w.N * 4 if c['kind'] == 'head' else c['Dm'] * 208) / 1e9:.2f} GB per GPU"
                          + (" > 126 MB L2)" if c["kind"] == "head" else "; the tracker's own state is the working set)"),
                    "conf": CONF, "nms": NMS, "max_tracks": c["T"], "max_detections": c["Dm"], "max_age": c["max_age"],
-                   "pipeline_depth": args.pipeline_depth,
+                   "pipeline_depth": args.pipeline_depth, "step_path": w.pipe.step_path(),
                    "timing": "value: K steps back to back + pb_join between CUDA events (steps overlap on internal streams); "
                              "us_per_batch_latency: median of single isolated steps; roofline: per-launch CUDA events on the serial path"},
         "roofline": dominant,

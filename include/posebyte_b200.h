@@ -112,9 +112,20 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf_threshold, float nms
 
 /* n_steps consecutive pb_step calls in one: step i takes the head batch d_heads + ((first + i) % period) * step_stride
  * (floats) and frame id frame0 + i.  For callers that hold several batches in device memory (offline video, benchmarks):
- * one library call instead of n_steps crossings of the language boundary.  Same semantics as the loop it replaces. */
+ * one library call instead of n_steps crossings of the language boundary.  Same results as the loop it replaces.
+ * Knowing the frames ahead lets the library keep every video stream's tracker state ON ITS SM for the whole sequence
+ * (the reference's per-stream frame loop, main.cpp:207-224, as one resident CTA per stream): with pipeline_depth > 1 and
+ * at most a third of the SMs' worth of streams (PB_SEQ=1 in the environment: up to half), chunks of up to 32 steps run
+ * with ONE tracker launch each, whose CTAs take every frame's kept detections from the NMS kernel of its step as soon as
+ * they are published.  pb_step_path tells which path a handle takes.  The head batches are borrowed until the work
+ * enqueued on `stream` by this call has run (as for pb_step). */
 int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int period, int first, int n_steps,
                 float conf_threshold, float nms_threshold, int frame0, pb_stream_t stream);
+
+/* How this handle runs its steps: *per_step 0 serial (three launches on the caller's stream), 1 pipelined three-kernel
+ * step (lanes), 2 fused per-stream kernel; *seq_chunk steps per resident tracker launch of pb_step_seq (0: pb_step_seq
+ * is a loop of pb_step). */
+int pb_step_path(pb_handle_t h, int* per_step, int* seq_chunk);
 
 /* With pipeline_depth > 1 pb_step returns with NMS and tracker work still running on internal
  * streams.  pb_join makes `stream` wait for all of it (asynchronous, no host blocking); every

@@ -710,4 +710,228 @@ static __device__ __noinline__ void auction_solve_lean32(const float* cc, int R,
         if (own[c] >= 0) { const int slot = act_list[own[c]]; col[lane + 32 * c] = slot; row[slot] = lane + 32 * c; }
 }
 
+// ---------------------------------------------------------------------------------------
+// Wide single-warp solve: up to 128 active rows and 128 columns (the crowd tables: 80 tracks x 85 detections), where the
+// CTA-wide solve above pays two block barriers per iteration for the one to four rows that still bid after the first few
+// iterations (measured: 85 us per solve).  Same decisions as auction_solve_cta bit for bit; the mapping of the lean solve:
+// lane = column (NC columns per lane, prices and owners in registers), the bidder set a warp-uniform mask of NW words,
+// bidders evaluated one after the other (two at a time: independent chains) with the arithmetic of lean_bid, per-lane
+// highest bid (ascending rows + '>' = lowest row among equal bids), winners / evicted owners toggled through one
+// REDUX.OR per mask word.  The first iteration takes the caller's first bids (lean_first_bid, one warp per row).
+// cc: compacted cost rows [na, C] (position in act_list); pre_bc / pre_bits: first bids by position.
+// ---------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void lean_values_n(const float* cc, int C, int j, const float (&p)[NC], int lane, float& bv, float& sv, int& bsel) {
+    bv = -1e9f; sv = -1e9f; bsel = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int d = lane + 32 * c;
+        const float v = (d < C) ? fmaxf(-cc[j * C + d] - p[c], -1e9f) : -1e9f;              // :61
+        if (c == 0) bv = v;
+        else if (v > bv) { sv = bv; bv = v; bsel = c; }                                    // ascending columns: lowest column on ties (:63)
+        else if (v > sv) sv = v;
+    }
+}
+template <int NC>
+__device__ __forceinline__ LeanBid lean_bid_n(float bv, float sv, int bsel, const int (&own)[NC], int lane, float eps) {
+    const unsigned FULL = 0xffffffffu;
+    LeanBid r;
+    r.m = warp_max_f32(bv);
+    const bool top = (bv == r.m);
+    int osel = own[0];
+#pragma unroll
+    for (int c = 1; c < NC; ++c) osel = (bsel == c) ? own[c] : osel;
+    const int key = top ? (((lane + 32 * bsel) << 8) | (osel + 1)) : 0x7fffffff;            // owner + 1 <= 128
+    r.rk = __reduce_min_sync(FULL, key);
+    const float m2p = warp_max_f32(top ? sv : bv);
+    const unsigned ties = __ballot_sync(FULL, top);
+    const float m2 = (ties & (ties - 1u)) ? r.m : m2p;
+    r.bits = __float_as_uint(r.m - m2 + eps);                                              // :99
+    return r;
+}
+template <int NC>
+__device__ __forceinline__ void lean_first_bid_n(const float* cr, int C, int R, int lane, int& bc, unsigned& bits) {
+    float p0[NC];
+    int own0[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p0[c] = 0.0f; own0[c] = -1; }
+    float bv, sv;
+    int bsel;
+    lean_values_n<NC>(cr, C, 0, p0, lane, bv, sv, bsel);
+    const LeanBid q = lean_bid_n<NC>(bv, sv, bsel, own0, lane, 1.0f / (float)(R + 1));
+    bc = (q.m != -1e9f) ? (q.rk >> 8) : -1;
+    bits = q.bits;
+}
+
+constexpr int WIDE_NW = 4, WIDE_NC = 4;            // 128 rows, 128 columns
+
+__device__ __forceinline__ void wide_mask_xor(unsigned (&m)[WIDE_NW], int r, bool on) {   // r warp-uniform
+    const unsigned bit = on ? (1u << (r & 31)) : 0u;
+    const int w = r >> 5;
+#pragma unroll
+    for (int k = 0; k < WIDE_NW; ++k) m[k] ^= (w == k) ? bit : 0u;
+}
+__device__ __forceinline__ int wide_next(unsigned (&rem)[WIDE_NW]) {                       // lowest set bit, cleared; -1: none
+#pragma unroll
+    for (int k = 0; k < WIDE_NW; ++k)
+        if (rem[k]) { const int j = 32 * k + __ffs(rem[k]) - 1; rem[k] &= rem[k] - 1u; return j; }
+    return -1;
+}
+
+// One iteration with NB (1..4) bidders j[0] < ... < j[NB-1]: the structure of lean_iter — every lane ends up with the same
+// (column, bid, evicted owner) of every bidder, so winners (highest bid, lowest row, :100), the bidder mask and the price /
+// owner updates are warp-uniform arithmetic: no reduction, no shared-memory traffic besides the cost rows.
+template <int NB>
+__device__ __forceinline__ bool wide_iter(const float* cc, int C, unsigned (&ub)[WIDE_NW], const int (&j)[NB], float eps,
+                                          float (&p)[WIDE_NC], int (&own)[WIDE_NC], int lane) {
+    constexpr int NC = WIDE_NC;
+    float bv[NB], sv[NB];
+    int bs[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) lean_values_n<NC>(cc, C, j[b], p, lane, bv[b], sv[b], bs[b]);
+    LeanBid q[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) q[b] = lean_bid_n<NC>(bv[b], sv[b], bs[b], own, lane, eps);
+    int bc[NB];
+    bool vm[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { vm[b] = q[b].m != -1e9f; bc[b] = vm[b] ? (q[b].rk >> 8) : (-1 - b); }
+    bool anyw = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        bool lose = false;
+#pragma unroll
+        for (int o = 0; o < NB; ++o) {
+            if (o < b) lose |= (bc[o] == bc[b] && q[o].bits >= q[b].bits);
+            if (o > b) lose |= (bc[o] == bc[b] && q[o].bits > q[b].bits);
+        }
+        const bool win = vm[b] && !lose;
+        const int ow = (q[b].rk & 0xff) - 1;                                               // the column's owner so far (-1: none)
+        wide_mask_xor(ub, j[b], win || !vm[b]);                                            // winners and rows without a column leave
+        wide_mask_xor(ub, ow < 0 ? 0 : ow, win && ow >= 0);                                // evicted owners enter (:109-111)
+        anyw |= win;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (win && bc[b] == lane + 32 * c) { p[c] += __uint_as_float(q[b].bits); own[c] = j[b]; }   // :113-118
+    }
+    return anyw;
+}
+
+// colkey: [C] the first iteration's highest bid per column, (bid bits << 32) | ~row position (0: no bid), gathered by the
+// caller with atomicMax while it computed the first bids (lean_first_bid_n); pre_bc: [na] first-bid columns (-1: none).
+static __device__ __noinline__ void auction_solve_wide(const float* cc, int R, int C, const int* act_list, int na,
+                                                       int* row, int* col, const unsigned (&ub0)[WIDE_NW],
+                                                       const int* pre_bc, const unsigned long long* colkey) {
+    constexpr int NC = WIDE_NC, NW = WIDE_NW;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < R; t += 32) row[t] = -1;
+    for (int d = lane; d < C; d += 32) col[d] = -1;
+    if (na <= 0 || C <= 0) return;
+    float p[NC];
+    int own[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p[c] = 0.0f; own[c] = -1; }
+    unsigned ub[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int lo = 32 * w;
+        const unsigned all = (na >= lo + 32) ? FULL : (na > lo ? ((1u << (na - lo)) - 1u) : 0u);
+        ub[w] = all & ub0[w];
+    }
+    __syncwarp();
+    float eps = 1.0f / (float)(R + 1);                                                     // :378
+    const int iters = (R * 3 < 50) ? R * 3 : 50;                                           // :379
+    int it = 0;
+    if ((ub[0] | ub[1] | ub[2] | ub[3]) != 0u && iters > 0) {
+        // ---- iteration 0: the caller's first bids, already reduced per column; nobody is evicted yet ----
+        unsigned any = 0u;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int d = lane + 32 * c;
+            const unsigned long long key = (d < C) ? colkey[d] : 0ull;
+            if (key != 0ull) { own[c] = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)); p[c] += __uint_as_float((unsigned)(key >> 32)); }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int i = 32 * w + lane;
+            const bool in = (i < na) && ((ub[w] >> lane) & 1u);
+            const int bci = in ? pre_bc[i] : -2;
+            unsigned won = 0u;                                                             // rows that won a column: position bits of this word
+#pragma unroll
+            for (int c = 0; c < NC; ++c) won |= (own[c] >= 0 && (own[c] >> 5) == w) ? (1u << (own[c] & 31)) : 0u;
+            won = __reduce_or_sync(FULL, won);
+            const unsigned nobid = __ballot_sync(FULL, bci == -1);                         // no column above -1e9: leave for good
+            ub[w] &= ~(won | nobid);
+            any |= won;
+        }
+        if (any == 0u) { ub[0] = 0u; ub[1] = 0u; ub[2] = 0u; ub[3] = 0u; }                 // no bid: fixed point
+        eps *= 0.9f;                                                                       // :402
+        it = 1;
+    }
+#pragma unroll 1
+    for (; it < iters; ++it) {
+        const int nb = __popc(ub[0]) + __popc(ub[1]) + __popc(ub[2]) + __popc(ub[3]);
+        if (nb == 0) break;                                                                // everybody assigned or out: fixed point
+        bool any;
+        if (nb <= 4) {
+            unsigned rem[NW] = {ub[0], ub[1], ub[2], ub[3]};
+            if (nb == 1) { const int j[1] = {wide_next(rem)}; any = wide_iter<1>(cc, C, ub, j, eps, p, own, lane); }
+            else if (nb == 2) { int j[2]; j[0] = wide_next(rem); j[1] = wide_next(rem); any = wide_iter<2>(cc, C, ub, j, eps, p, own, lane); }
+            else if (nb == 3) { int j[3]; j[0] = wide_next(rem); j[1] = wide_next(rem); j[2] = wide_next(rem); any = wide_iter<3>(cc, C, ub, j, eps, p, own, lane); }
+            else { int j[4]; j[0] = wide_next(rem); j[1] = wide_next(rem); j[2] = wide_next(rem); j[3] = wide_next(rem); any = wide_iter<4>(cc, C, ub, j, eps, p, own, lane); }
+        } else {
+            // many bidders: one after the other, per-lane highest bid of the lane's columns (ascending rows + '>' = lowest
+            // row among equal bids), winners / evicted owners toggled through one REDUX.OR per mask word
+            unsigned best[NC];
+            int wr[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { best[c] = 0u; wr[c] = -1; }
+            unsigned drop[NW] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                unsigned rem = ub[w];
+#pragma unroll 1
+                while (rem) {
+                    const int jb = 32 * w + __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    float bv, sv;
+                    int bs;
+                    lean_values_n<NC>(cc, C, jb, p, lane, bv, sv, bs);
+                    const LeanBid q = lean_bid_n<NC>(bv, sv, bs, own, lane, eps);
+                    if (q.m == -1e9f) { drop[w] |= 1u << (jb & 31); continue; }            // no column above -1e9: leaves for good
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        if ((q.rk >> 8) == lane + 32 * c && q.bits > best[c]) { best[c] = q.bits; wr[c] = jb; }
+                }
+            }
+            unsigned tog[NW] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (wr[c] >= 0) {                                                          // :107-121
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        if ((wr[c] >> 5) == w) tog[w] |= 1u << (wr[c] & 31);
+                        if (own[c] >= 0 && (own[c] >> 5) == w) tog[w] |= 1u << (own[c] & 31);
+                    }
+                    own[c] = wr[c];
+                    p[c] += __uint_as_float(best[c]);
+                }
+            unsigned anyb = 0u;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                tog[w] = __reduce_or_sync(FULL, tog[w]);
+                anyb |= tog[w];
+                ub[w] = (ub[w] & ~drop[w]) ^ tog[w];                                       // winners leave, evicted owners enter
+            }
+            any = anyb != 0u;
+        }
+        if (!any) break;                                                                   // no bid: fixed point
+        eps *= 0.9f;                                                                       // :402
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        if (own[c] >= 0) { const int slot = act_list[own[c]]; col[lane + 32 * c] = slot; row[slot] = lane + 32 * c; }
+}
+
 }  // namespace pb

@@ -864,6 +864,13 @@ int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int per
     return PB_OK;
 }
 
+int pb_step_path(pb_handle_t h, int* per_step, int* seq_chunk) {
+    if (!h) { pb_set_error("pb_step_path: null handle"); return PB_ERR_INVALID; }
+    if (per_step) *per_step = h->fplan.ok ? 2 : (h->cfg.pipeline_depth > 1 ? 1 : 0);
+    if (seq_chunk) *seq_chunk = h->seq_chunk;
+    return PB_OK;
+}
+
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                  void* h_tracks, int* h_counts) {
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_step_host: null argument"); return PB_ERR_INVALID; }

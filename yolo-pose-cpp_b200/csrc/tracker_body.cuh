@@ -275,6 +275,41 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
             else auction_solve_lean32<2>(cc, c.T, D, s.act_list, na, s.row, s.col, s.price, s.aowner, cb, cr, ub0, s.acc, pre_bc, pre_bits);
         }
         __syncthreads();
+    } else if (na <= 32 * WIDE_NW && c.D <= 32 * WIDE_NC && na * c.D <= c.term_floats && !(c.warp_auction && na <= 32)) {
+        // Crowd tables (up to 128 active rows x 128 detections): the wide single-warp solve.  The whole CTA compacts the
+        // active rows into the idle term buffer and computes the first iteration's bids, one warp per row, reducing them
+        // per column with a 64-bit atomicMax (highest bid, lowest row).
+        const int D = c.D;
+        int* pre_bc = s.rowbc;                                       // [T], idle since the centre stage
+        float* cc = s.terms;
+#pragma unroll 1
+        for (int d = c.tid; d < D; d += c.nthreads) s.colbid[d] = 0ull;
+#pragma unroll 1
+        for (int i = c.tid; i < na * D; i += c.nthreads) { const int ai = fast_div(i, c.magicD); cc[i] = c.cost[(size_t)s.act_list[ai] * D + (i - ai * D)]; }
+        __syncthreads();
+#pragma unroll 1
+        for (int ai = c.warp; ai < na; ai += c.nwarps) {
+            if (after_lock && s.rowb[s.act_list[ai]] >= 0) { if (c.lane == 0) pre_bc[ai] = -1; continue; }   // locked: all cells 1e9, no bid
+            int bc;
+            unsigned bits;
+            lean_first_bid_n<WIDE_NC>(cc + (size_t)ai * D, D, c.T, c.lane, bc, bits);
+            if (c.lane == 0) {
+                pre_bc[ai] = bc;
+                if (bc >= 0) atomicMax(&s.colbid[bc], ((unsigned long long)bits << 32) | (unsigned long long)(0xffffffffu - (unsigned)ai));
+            }
+        }
+        __syncthreads();
+        if (c.tid < 32) {
+            unsigned ub0[WIDE_NW];
+#pragma unroll
+            for (int w = 0; w < WIDE_NW; ++w) {
+                const int i = 32 * w + c.lane;
+                // rows matched in an earlier tier are locked: all their cells are 1e9 (lock_pairs), they can never bid
+                ub0[w] = __ballot_sync(FULLM, i < na && !(after_lock && s.rowb[s.act_list[i]] >= 0));
+            }
+            auction_solve_wide(cc, c.T, D, s.act_list, na, s.row, s.col, ub0, pre_bc, s.colbid);
+        }
+        __syncthreads();
     } else if (c.warp_auction && na <= 32) {
         if (c.tid < 32)
             auction_solve_hybrid32(s.cost, c.T, c.D, s.act_list, na, s.row, s.col, s.price, s.aowner,
