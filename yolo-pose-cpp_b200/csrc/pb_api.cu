@@ -817,10 +817,15 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
         const bool wait_half = h->seq_half_used[half];
         if (wait_half)
             for (int l = 0; l < L && l < n; ++l) PB_CUDA(cudaStreamWaitEvent(h->s_seq_nms[(tp.seq + l) % L], h->ev_seq_trk[half], 0));
-        // the tracker launch first: its CTAs are resident (and waiting for frame 0) while the host enqueues the steps
-        PB_CUDA(launch_tracker_seq(h->trk, tp, q, h->seq_plan, h->s_seq_trk));
-        PB_CUDA(cudaEventRecord(h->ev_seq_trk[half], h->s_seq_trk));
-        h->seq_half_used[half] = true;
+        // The tracker launch first: its CTAs are resident (and waiting for frame 0) while the host enqueues the steps.  Where
+        // kernels cannot overlap — a profiler that replays kernels one at a time (ncu), CUDA_LAUNCH_BLOCKING=1 — a kernel must
+        // not wait for one launched after it: PB_SEQ_TRACKER_LAST=1 (or CUDA_LAUNCH_BLOCKING) enqueues it behind the chunk's steps.
+        static const bool tracker_last = (getenv("PB_SEQ_TRACKER_LAST") && atoi(getenv("PB_SEQ_TRACKER_LAST")) != 0) ||
+                                         (getenv("CUDA_LAUNCH_BLOCKING") && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
+        if (!tracker_last) {
+            PB_CUDA(launch_tracker_seq(h->trk, tp, q, h->seq_plan, h->s_seq_trk));
+            PB_CUDA(cudaEventRecord(h->ev_seq_trk[half], h->s_seq_trk));
+        }
         h->seq_inflight = true;
         for (int i = 0; i < n; ++i) {
             PipeSlot& sl = h->seq_ring[(size_t)half * M + i];
@@ -843,6 +848,16 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
                 h->trk.outputs = sl.outputs; h->trk.num_outputs = sl.num_outputs;
             }
         }
+        if (tracker_last) {
+            // (serialising tools run the steps' kernels to completion first; otherwise the lanes' work is simply ahead)
+            for (int l = 0; l < L && l < n; ++l) {
+                PB_CUDA(cudaEventRecord(h->ev_seq_nms[(tp.seq + n - 1 - l) % L], h->s_seq_nms[(tp.seq + n - 1 - l) % L]));
+                PB_CUDA(cudaStreamWaitEvent(h->s_seq_trk, h->ev_seq_nms[(tp.seq + n - 1 - l) % L], 0));
+            }
+            PB_CUDA(launch_tracker_seq(h->trk, tp, q, h->seq_plan, h->s_seq_trk));
+            PB_CUDA(cudaEventRecord(h->ev_seq_trk[half], h->s_seq_trk));
+        }
+        h->seq_half_used[half] = true;
         h->trk_seq = tp.seq + n - 1;
         h->frames += n;
         h->seq_half ^= 1;

@@ -942,6 +942,20 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
             if (tier > 0) merge_assign(c);
             if (tier < 2) lock_pairs(c, s.gate, na, tier > 0);
             if (tier == 0) stamp(14);
+            if (tier == 0 && c.warp_auction && na <= 32) {
+                // Every active row matched in tier 1 (the usual frame: everybody found its detection)?  Tiers 2 and 3 then
+                // change nothing but the cells of the inactive rows (cost <- 1.0, :351-354): the locked rows own no gate bit
+                // (lock_pairs), so neither cost pass writes a cell, both solves clear the assignments and stop before
+                // their first iteration, the merges restore them and the locks rewrite the 1e9 cells of tier 1.  Do just
+                // that write and leave the loop: six block barriers less on the chain of dependent frames.
+                const bool unmatched = c.lane < na && s.row[s.act_list[c.lane]] < 0;
+                if (__ballot_sync(FULLM, unmatched) == 0u) {           // the same in every warp (row is final: lock_pairs ended with a barrier)
+                    cost_inactive_rows(c);
+                    __syncthreads();
+                    stamp(3);
+                    break;
+                }
+            }
         }
         stamp(3 + tier);
     }
