@@ -1,4 +1,5 @@
-"""Per-launch CUDA-event times of the NMS kernel (full: 1024 threads, one CTA per SM) against the tiered kernel (512 threads, two per SM)."""
+"""Per-launch CUDA-event times of the NMS kernel (full: 1024 threads, one CTA per SM) against the tiered kernels (PB_NMS_TIER = 1: 2 x 512
+threads per SM, 2: 3 x 384, 3: 3 x 256, 4: 4 x 256); 592 streams = 4 CTAs on every SM, SM-time per stream-frame = kernel time * 148 / B."""
 import os, sys, json, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,8 +16,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     k = pp.kernel_us()
     print(json.dumps({"B": B, "tier": os.environ.get("PB_NMS_TIER"), "kernel_us": k, "post_stage_us": pp.post_stage_us()}))
 else:
-    for B in (64, 148, 296):
-        for tier in (None, "1"):
+    for B in (64, 296, 592):
+        for tier in (None, "1", "2", "3", "4"):
             env = dict(os.environ)
             if tier: env["PB_NMS_TIER"] = tier
             subprocess.run([sys.executable, __file__, "child", str(B)], env=env)

@@ -63,4 +63,14 @@ for w in which:
     name = f"B{B}"
     run(name, B, occ, age, 5, {"PB_SEQ": "0", "PB_NO_FUSED": "1"})
     run(name, B, occ, age, 5, {"PB_SEQ": "1"})
-    run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_COMPACT": "1", "PB_SEQ_NMS_TIER": "1"})
+    if os.environ.get("SEQ_PROBE_OLD"): run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_COMPACT": "1", "PB_SEQ_NMS_TIER": "1"})
+    if os.environ.get("SEQ_PROBE_QUICK"):
+        for lanes in ("3", "4"):
+            for tier in ("0", "1"):
+                run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_NMS_TIER": tier, "PB_SEQ_LANES": lanes})
+        continue
+    # resident tracker CTAs of 512 / 256 threads leave registers and thread slots of their SM to decode CTAs
+    for thr in ("512", "256"):
+        for tier in ("0", "1", "2"):
+            for lanes in ("3", "4"):
+                run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_THREADS": thr, "PB_SEQ_NMS_TIER": tier, "PB_SEQ_LANES": lanes})

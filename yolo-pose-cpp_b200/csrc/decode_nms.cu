@@ -164,7 +164,11 @@ constexpr int NM_THREADS = 1024;
 
 size_t decode_nms_smem_bytes(int max_cand, int max_keep) { return nm_carve(nullptr, max_cand, max_keep, nullptr); }
 
+#ifdef PB_NMS_MAXNREG
+__global__ void __maxnreg__(PB_NMS_MAXNREG)
+#else
 __global__ void __launch_bounds__(NM_THREADS, 1)
+#endif
 pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, int nseg, int segcap, int Ccap, int Kcap, float nms_thr,
               PostBuffers out, SmemOffsets so) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,12 +185,13 @@ pb_nms_kernel(const float* __restrict__ heads, int N, int lazy, CandScratch cs, 
     }
 }
 
-// Tiered variant: half-SM CTAs (512 threads, at most 64 registers, at most ~113 KB of shared memory) so that two of them — or
-// one and a resident tracker CTA (tracker.cu: pb_tracker_seq_kernel) — share an SM.  The shared memory holds the working set of
-// CT candidates; a stream with more (up to Ccap, rule R1) keeps its per-candidate arrays in a global scratch instead (spill
-// path: the same code on generic pointers, same results), exactly as the fused per-stream kernel does (fused.cu).
-constexpr int NMT_THREADS = 512;
-
+// Tiered variants: CTAs that share an SM — half-SM (512 threads, at most ~113 KB of shared memory: two of them, or one and a
+// compact resident tracker CTA, tracker.cu: pb_tracker_seq_kernel), third-SM (384 or 256 threads, ~75 KB) and quarter-SM
+// (256 threads, ~56 KB).  The NMS stage is not on a video stream's chain of dependent frames, so what counts for it is SM-time
+// per stream-frame, not latency: a 1024-thread CTA keeps an SM's issue slots 39 % busy for 33 us at 136 candidates, and most
+// of its warps only walk through barriers; smaller CTAs packed three or four to an SM fill the slots.  The shared memory holds
+// the working set of CT candidates; a stream with more (up to Ccap, rule R1) keeps its per-candidate arrays in a global scratch
+// instead (spill path: the same code on generic pointers, same results), exactly as the fused per-stream kernel does (fused.cu).
 struct NmsTierParams {
     const float* heads;
     int N, lazy;
@@ -200,14 +205,16 @@ struct NmsTierParams {
 };
 
 // (cold path, a function of its own: kept out of the register allocation of the common path; the parameters stay in constant memory)
+template <int NT>
 static __device__ __noinline__ void nms_tier_spill(const NmsTierParams& F, int b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmSmem s;
     nm_from_offsets(smem_raw, F.spill + (size_t)b * F.spill_stride, F.so_big, s);
-    nms_body<NMT_THREADS>(s, F.heads, F.N, F.lazy, F.cs, F.nseg, F.segcap, F.Ccap, F.Kcap, F.nms_thr, F.out, b, (int)gridDim.x, nullptr, nullptr, 0);
+    nms_body<NT>(s, F.heads, F.N, F.lazy, F.cs, F.nseg, F.segcap, F.Ccap, F.Kcap, F.nms_thr, F.out, b, (int)gridDim.x, nullptr, nullptr, 0);
 }
 
-__global__ void __launch_bounds__(NMT_THREADS, 2)
+template <int NT, int PER_SM>
+__global__ void __launch_bounds__(NT, PER_SM)
 pb_nms_tier_kernel(const __grid_constant__ NmsTierParams F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
@@ -216,9 +223,9 @@ pb_nms_tier_kernel(const __grid_constant__ NmsTierParams F) {
     if (total <= F.CT || F.spill == nullptr) {
         NmSmem s;
         nm_from_offsets(smem_raw, smem_raw, F.so_small, s);
-        nms_body<NMT_THREADS>(s, F.heads, F.N, F.lazy, F.cs, F.nseg, F.segcap, F.CT, F.Kcap, F.nms_thr, F.out, b, gridDim.x, nullptr, nullptr, 0);
+        nms_body<NT>(s, F.heads, F.N, F.lazy, F.cs, F.nseg, F.segcap, F.CT, F.Kcap, F.nms_thr, F.out, b, gridDim.x, nullptr, nullptr, 0);
     } else {
-        nms_tier_spill(F, b);
+        nms_tier_spill<NT>(F, b);
     }
     if (F.out.ready) {
         __syncthreads();
@@ -229,13 +236,25 @@ pb_nms_tier_kernel(const __grid_constant__ NmsTierParams F) {
     }
 }
 
-NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin) {
+static const void* nms_tier_func(int threads, int per_sm) {
+    if (threads == 512) return (const void*)pb_nms_tier_kernel<512, 2>;
+    if (threads == 384) return (const void*)pb_nms_tier_kernel<384, 3>;
+    if (threads == 256 && per_sm == 3) return (const void*)pb_nms_tier_kernel<256, 3>;
+    if (threads == 256 && per_sm == 4) return (const void*)pb_nms_tier_kernel<256, 4>;
+    return nullptr;
+}
+
+// per_sm CTAs of `threads` threads per SM: 2 x 512 (the default), 3 x 384, 3 x 256 or 4 x 256
+NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin, int threads, int per_sm) {
     NmsTierPlan p{};
     p.ok = false;
-    size_t target = 113 * 1024;                       // (228 KB - 2 x 1 KB reserved) / 2
+    p.threads = threads; p.per_sm = per_sm;
+    if (!nms_tier_func(threads, per_sm)) return p;
+    size_t target = (size_t)(228 - per_sm) * 1024 / (size_t)per_sm;      // 228 KB per SM, 1 KB reserved per resident CTA
+    target &= ~(size_t)1023;
     if (target > smem_optin) target = smem_optin;
     int ct = 0;
-    for (int c = 64; c <= max_cand; c += 32) {
+    for (int c = 64; c <= max_cand; c += 16) {
         if (nm_carve(nullptr, c, max_keep, nullptr) <= target) ct = c; else break;
     }
     if (nm_carve(nullptr, max_cand, max_keep, nullptr) <= target) ct = max_cand;
@@ -258,9 +277,14 @@ cudaError_t launch_nms_tier(const NmsTierPlan& tp, const float* d_heads, int N, 
     F.Ccap = max_cand; F.CT = tp.CT; F.Kcap = max_keep; F.nms_thr = nms_thr; F.out = out;
     F.so_small = tp.so_small; F.so_big = tp.so_big; F.spill = tp.spill_stride ? spill : nullptr; F.spill_stride = tp.spill_stride;
     if (tp.spill_stride && !spill) return cudaErrorInvalidValue;
-    const cudaError_t e = ensure_dyn_smem((const void*)pb_nms_tier_kernel, tp.smem_bytes);
+    const void* fn = nms_tier_func(tp.threads, tp.per_sm);
+    if (!fn) return cudaErrorInvalidValue;
+    const cudaError_t e = ensure_dyn_smem(fn, tp.smem_bytes);
     if (e != cudaSuccess) return e;
-    pb_nms_tier_kernel<<<B, NMT_THREADS, tp.smem_bytes, stream>>>(F);
+    if (tp.threads == 512) pb_nms_tier_kernel<512, 2><<<B, 512, tp.smem_bytes, stream>>>(F);
+    else if (tp.threads == 384) pb_nms_tier_kernel<384, 3><<<B, 384, tp.smem_bytes, stream>>>(F);
+    else if (tp.per_sm == 3) pb_nms_tier_kernel<256, 3><<<B, 256, tp.smem_bytes, stream>>>(F);
+    else pb_nms_tier_kernel<256, 4><<<B, 256, tp.smem_bytes, stream>>>(F);
     count_launch();
     return cudaGetLastError();
 }
@@ -275,8 +299,9 @@ cudaError_t preload_post_kernels(int max_cand, int max_keep, const NmsTierPlan* 
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, (const void*)pb_nms_kernel);
     if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pb_nms_kernel, decode_nms_smem_bytes(max_cand, max_keep));
     if (e == cudaSuccess && tier && tier->ok) {
-        e = cudaFuncGetAttributes(&a, (const void*)pb_nms_tier_kernel);
-        if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pb_nms_tier_kernel, tier->smem_bytes);
+        const void* fn = nms_tier_func(tier->threads, tier->per_sm);
+        e = fn ? cudaFuncGetAttributes(&a, fn) : cudaErrorInvalidValue;
+        if (e == cudaSuccess) e = ensure_dyn_smem(fn, tier->smem_bytes);
     }
     return e;
 }

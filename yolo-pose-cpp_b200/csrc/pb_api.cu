@@ -204,6 +204,7 @@ void pb_default_config(pb_config* c) {
 }
 
 static void seq_configure(pb_handle_st* h, int sm_count);
+static NmsTierPlan tier_plan_by_id(const pb_config& c, int id);
 
 static int build_handle(pb_handle_st* h) {
     const pb_config& c = h->cfg;
@@ -488,10 +489,7 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
     static const bool tier_exp = getenv("PB_NMS_TIER") != nullptr;          // experiment: the tiered (half-SM) kernel on the serial path
     if (tier_exp) {
         if (!h->exp_tier.ok) {
-            int dev = 0, optin = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            h->exp_tier = nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin);
+            h->exp_tier = tier_plan_by_id(c, atoi(getenv("PB_NMS_TIER")) > 0 ? atoi(getenv("PB_NMS_TIER")) : 1);
             if (h->exp_tier.ok && h->exp_tier.spill_stride) PB_TRY(dev_alloc(h, &h->exp_spill, (size_t)c.num_streams * h->exp_tier.spill_stride));
         }
         PB_CUDA(launch_nms_tier(h->exp_tier, d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan,
@@ -510,6 +508,8 @@ static TrackParams track_params(pb_handle_st* h, int frame_id) {
     TrackParams p{};
     p.seq = h->trk_seq + 1;                 // committed (h->trk_seq = p.seq) once the launch has succeeded: no gap on failure
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
+    static const int sub_off = getenv("PB_NO_SUB_SOLVE") ? 1 : 0;
+    p.sub_solve_off = sub_off;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
     return p;
@@ -730,6 +730,16 @@ static int alloc_slot(pb_handle_st* h, PipeSlot& sl, unsigned long long* post_ns
 // Can this handle use the resident path, and with which tracker plan?  Small tables only (the auction runs in one warp, the
 // frame is a chain of short stages: exactly what a resident CTA is good at; large tables keep the row-sliced pre-kernel), and
 // the tracker CTAs must leave at least half of the SMs to the decode and NMS kernels they wait for.
+// Tiered NMS kernel variants by number: 1 = 2 x 512 threads per SM, 2 = 3 x 384, 3 = 3 x 256, 4 = 4 x 256 (0: none)
+static NmsTierPlan tier_plan_by_id(const pb_config& c, int id) {
+    static const int threads[5] = {0, 512, 384, 256, 256}, per_sm[5] = {0, 2, 3, 3, 4};
+    if (id < 1 || id > 4) return NmsTierPlan{};
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin, threads[id], per_sm[id]);
+}
+
 static void seq_configure(pb_handle_st* h, int sm_count) {
     const pb_config& c = h->cfg;
     h->seq_chunk = 0;
@@ -753,14 +763,7 @@ static void seq_configure(pb_handle_st* h, int sm_count) {
     if (!forced && 3 * c.num_streams > sm_count) return;
     h->seq_plan = p;
     h->seq_nms = NmsTierPlan{};
-    if (const char* e = getenv("PB_SEQ_NMS_TIER")) {
-        if (atoi(e) != 0) {
-            int dev = 0, optin = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            h->seq_nms = nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin);
-        }
-    }
+    if (const char* e = getenv("PB_SEQ_NMS_TIER")) h->seq_nms = tier_plan_by_id(c, atoi(e));
     if (const char* e = getenv("PB_SEQ_LANES")) { const int v = atoi(e); if (v >= 1 && v <= pb_handle_st::SEQ_MAX_LANES) h->seq_lanes = v; }
     int chunk = PB_SEQ_MAX;
     if (const char* e = getenv("PB_SEQ_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= PB_SEQ_MAX) chunk = v; }

@@ -89,6 +89,7 @@ struct TrackParams {
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
     int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap;
     int precomputed;     // predict, centres, gates and the tier-1 cost pass of this frame were done by the pre-kernel (large tables)
+    int sub_solve_off;   // 1: tiers 2 and 3 of larger tables keep the CTA-wide / wide solve (A/B switch, PB_NO_SUB_SOLVE)
     SmemOffsets so;      // shared-memory layout (tracker_plan)
 };
 
@@ -128,9 +129,10 @@ cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_
 cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 lazy, 2 deferred*/, int B, int max_cand, int max_keep, float nms_thr,
                        const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, cudaStream_t stream);
 
-// tiered NMS kernel (decode_nms.cu: pb_nms_tier_kernel): half-SM CTAs, shared memory for CT candidates, spill path beyond
-struct NmsTierPlan { bool ok; int CT; size_t smem_bytes, spill_stride; SmemOffsets so_small, so_big; };
-NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin);
+// tiered NMS kernel (decode_nms.cu: pb_nms_tier_kernel): per_sm CTAs of `threads` threads share an SM (2 x 512, 3 x 384, 3 x 256,
+// 4 x 256), shared memory for CT candidates, spill path beyond
+struct NmsTierPlan { bool ok; int CT; size_t smem_bytes, spill_stride; SmemOffsets so_small, so_big; int threads, per_sm; };
+NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin, int threads = 512, int per_sm = 2);
 cudaError_t launch_nms_tier(const NmsTierPlan& tp, const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
                             const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, unsigned char* spill, cudaStream_t stream);
 

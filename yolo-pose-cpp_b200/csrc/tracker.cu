@@ -262,7 +262,11 @@ cudaError_t launch_tracker_pre(const TrackBuffers& tb, const TrackParams& p, con
 }
 
 template <int NTHREADS, bool ALLSMEM>
+#ifdef PB_TRK_MAXNREG
+__global__ void __maxnreg__(PB_TRK_MAXNREG)
+#else
 __global__ void __launch_bounds__(NTHREADS)
+#endif
 pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tracker_body<NTHREADS, ALLSMEM, false>(tb, P, src, blockIdx.x, smem_raw, 0, P.seq, P.frame_id, tb.outputs, tb.num_outputs);
@@ -278,7 +282,11 @@ pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
 // deadlock while the grid leaves SMs free for that kernel (the host layer checks); a 0.5 s time-out guards against misuse.
 // =======================================================================================
 template <int NTHREADS, bool ALLSMEM, bool RES>
+#ifdef PB_TRK_MAXNREG
+__global__ void __maxnreg__(PB_TRK_MAXNREG)
+#else
 __global__ void __launch_bounds__(NTHREADS, (ALLSMEM && NTHREADS <= 512) ? 1024 / NTHREADS : 1)   // at most 64 registers: room for other CTAs beside it
+#endif
 pb_tracker_seq_kernel(const __grid_constant__ TrackBuffers tb, const __grid_constant__ TrackParams P, const __grid_constant__ SeqTable Q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ok;

@@ -218,6 +218,7 @@ struct Ctx {
     int T, D, Dw, tid, nthreads, lane, warp, nwarps;
     unsigned magicD, magicW;   // ceil(2^32 / D), ceil(2^32 / words): i / D == __umulhi(i, magicD) for i * D < 2^32 (0: divisor 1)
     bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
+    bool sub_solve;     // tiers 2 and 3 of larger tables: solve the unmatched rows x unmatched detections only (auction_solve_unlocked)
     int term_floats, cell_cap;
     float* cost;        // shared or global, flat [t*D + d]
     const float* det;   // shared or global scratch [d*51]
@@ -229,10 +230,91 @@ struct Ctx {
 __device__ __forceinline__ int fast_div(int i, unsigned magic) { return magic ? (int)__umulhi((unsigned)i, magic) : i; }
 __device__ __forceinline__ unsigned div_magic(int d) { return d > 1 ? (0xffffffffu / (unsigned)d + 1u) : 0u; }
 
+// Tiers 2 and 3 on tables beyond the lean solve's own case (crowd tables, the 512 x 512 stress tables).  Rows matched in
+// an earlier tier are locked — all their cells are 1e9 (lock_pairs), they never bid — and so are the matched columns: their
+// cells are 1e9 for every active row, so for a bidder they sit at the -1e9 floor, never best and never second
+// (hungarian.cu:55-69).  What is left is the auction of the unmatched active rows over the unmatched detections, usually a
+// handful of each: same eps0 = 1/(T+1), same iteration limit, same tie-breaks (both index maps are ascending).  With at most
+// 32 such rows and 64 such columns it is compacted into the idle term buffer and solved by the lean single-warp solve
+// instead of the CTA-wide one (two block barriers and a pass over all columns per iteration; an eviction chase among the
+// left-over rows runs to the 50-iteration limit: 68 + 30 us per 512 x 512 frame).  false: too many left, nothing was done.
+struct SubSolveArgs {        // by value: a reference to the CTA's context would force it into local memory
+    const float* cost; int T, D, na, tid, nthreads;
+    const int *act_list, *rowb, *colb;
+    int *row, *col, *cell_list, *rowbc, *aowner;
+    float *terms, *price;
+    unsigned long long* colbid;
+};
+static __device__ __noinline__ bool auction_solve_unlocked(const SubSolveArgs a) {
+    int* sub_act = a.cell_list;                 // [32] unmatched active rows (slots, ascending); the cell list is idle between cost passes
+    int* sub_col = a.cell_list + 32;            // [64] unmatched detections (ascending)
+    int* sub_own = a.cell_list + 96;            // [64] the solve's column -> slot
+    int* cnt = a.cell_list + 160;               // [2]
+    const int D = a.D, lane = a.tid & 31;
+    if (a.tid < 32) {
+        int nr = 0, nc = 0;
+#pragma unroll 1
+        for (int a0 = 0; a0 < a.na; a0 += 32) {
+            const int ai = a0 + lane;
+            const int t = ai < a.na ? a.act_list[ai] : 0;
+            const bool un = ai < a.na && a.rowb[t] < 0;
+            const unsigned bm = __ballot_sync(FULLM, un);
+            const int pos = nr + __popc(bm & ((1u << lane) - 1u));
+            if (un && pos < 32) sub_act[pos] = t;
+            nr += __popc(bm);
+        }
+#pragma unroll 1
+        for (int d0 = 0; d0 < D; d0 += 32) {
+            const int d = d0 + lane;
+            const bool un = d < D && a.colb[d] < 0;
+            const unsigned bm = __ballot_sync(FULLM, un);
+            const int pos = nc + __popc(bm & ((1u << lane) - 1u));
+            if (un && pos < 64) sub_col[pos] = d;
+            nc += __popc(bm);
+        }
+        if (lane == 0) { cnt[0] = nr; cnt[1] = nc; }
+    }
+    __syncthreads();
+    const int nr = cnt[0], nc = cnt[1];
+    if (nr > 32 || nc > 64) return false;       // (uniform over the CTA)
+#pragma unroll 1
+    for (int t = a.tid; t < a.T; t += a.nthreads) a.row[t] = -1;                            // :372-376
+#pragma unroll 1
+    for (int d = a.tid; d < D; d += a.nthreads) a.col[d] = -1;
+    if (nr == 0 || nc == 0) { __syncthreads(); return true; }
+    float* cc = a.terms;
+#pragma unroll 1
+    for (int i = a.tid; i < nr * nc; i += a.nthreads) {
+        const int r = i / nc, j = i - r * nc;
+        cc[i] = a.cost[(size_t)sub_act[r] * D + sub_col[j]];
+    }
+    __syncthreads();
+    if (a.tid < 32) {
+        unsigned* cb = reinterpret_cast<unsigned*>(a.colbid);
+        int* cr = reinterpret_cast<int*>(a.colbid) + nc;
+        // (row scratch: rowbc, idle since the centre stage; the solve clears and fills it by slot)
+        if (nc <= 32) auction_solve_lean32<1>(cc, a.T, nc, sub_act, nr, a.rowbc, sub_own, a.price, a.aowner, cb, cr);
+        else auction_solve_lean32<2>(cc, a.T, nc, sub_act, nr, a.rowbc, sub_own, a.price, a.aowner, cb, cr);
+        __syncwarp();
+        for (int j = lane; j < nc; j += 32) {
+            const int slot = sub_own[j];
+            if (slot >= 0) { a.col[sub_col[j]] = slot; a.row[slot] = sub_col[j]; }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 // Auction solve: see auction.cuh.  Leaves row/col in s.row / s.col.
 __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
     TkSmem& s = c.s;
-    if (c.warp_auction && na <= 32 && c.D <= 64) {
+    const bool lean_case = c.warp_auction && na <= 32 && c.D <= 64;
+    if (!lean_case && after_lock && c.sub_solve) {
+        const SubSolveArgs a{c.cost, c.T, c.D, na, c.tid, c.nthreads, s.act_list, s.rowb, s.colb, s.row, s.col, s.cell_list, s.rowbc, s.aowner,
+                             s.terms, s.price, s.colbid};
+        if (auction_solve_unlocked(a)) return;
+    }
+    if (lean_case) {
         if (after_lock) {
             // Rows matched in an earlier tier are locked (all their cells are 1e9, lock_pairs) and can never bid.  When
             // that is every active row — the usual frame: everybody found its detection in tier 1 — the solve would
@@ -825,6 +907,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     c.det = det_w;
     c.cost = cost_in_smem ? s.cost : g_cost;
     c.warp_auction = cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
+    c.sub_solve = P.term_floats >= 2048 && P.cell_cap >= 192 && P.sub_solve_off == 0;
     c.pred = pred_in_smem ? s.pred : g_pred;
     // (resident tracker: the whole persistent matrix is loaded once — later frames index it with their own D, quirk Q1)
     if (cost_in_smem && st_load) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
