@@ -25,6 +25,7 @@
 //     their candidate slots and anchor ids.
 //
 // Arithmetic goes through pb_math.h (see there), compiled with --fmad=false.
+#include <cstdlib>
 #include "nms_body.cuh"
 
 namespace pb {
@@ -315,6 +316,7 @@ DecodePlan decode_plan(int B, int N, int max_cand) {
     int nseg = (2 * 148 + B - 1) / B;                      // >= 2 CTAs per SM in total
     if (nseg < 1) nseg = 1;
     if (nseg > 16) nseg = 16;
+    if (const char* e = getenv("PB_DECODE_NSEG")) { const int v = atoi(e); if (v >= 1 && v <= 16) nseg = v; }   // experiment
     const int min_seg = (ngroups + DG_MAX_CHUNKS * DG_THREADS - 1) / (DG_MAX_CHUNKS * DG_THREADS);
     if (nseg < min_seg) nseg = min_seg;
     p.nseg = nseg;

@@ -99,6 +99,7 @@ struct pb_handle_st {
     cudaStream_t s_seq_nms[SEQ_MAX_LANES] = {}, s_seq_trk = nullptr;
     TrackerPlan seq_plan{};
     NmsTierPlan exp_tier{}; unsigned char* exp_spill = nullptr;   // PB_NMS_TIER experiment (serial path)
+    NmsTierPlan pipe_tier{};       // ok: the pipelined three-kernel step launches the tiered NMS kernel (CTAs that share an SM)
     NmsTierPlan seq_nms{};         // ok: the steps of the resident path use the tiered (half-SM) NMS kernel
     std::vector<void*> allocs;
     // host-buffer path
@@ -230,6 +231,7 @@ static int build_handle(pb_handle_st* h) {
         PB_TRY(dev_alloc(h, &outp, B * Dm * 228));
         sl.outputs = outp;
         PB_TRY(dev_alloc(h, &sl.num_outputs, B));
+        if (h->pipe_tier.ok && h->pipe_tier.spill_stride) PB_TRY(dev_alloc(h, &sl.spill, B * h->pipe_tier.spill_stride));
         PB_CUDA(cudaEventCreateWithFlags(&sl.ev_gather, cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&sl.ev_nms, cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&sl.ev_trk, cudaEventDisableTiming));
@@ -393,6 +395,8 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
         const int l = atoi(e);
         if (l >= 0 && l <= 3 && (l <= 1 || (l - 1) * c.num_streams < prop.multiProcessorCount)) h->lanes = l;
     }
+    if (c.pipeline_depth > 1 && !h->fplan.ok)
+        if (const char* e = getenv("PB_PIPE_NMS_TIER")) h->pipe_tier = tier_plan_by_id(c, atoi(e));
     int r = build_handle(h);
     if (r != PB_OK) { pb_destroy(h); return r; }
     *out = h;
@@ -510,6 +514,8 @@ static TrackParams track_params(pb_handle_st* h, int frame_id) {
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
     static const int sub_off = getenv("PB_NO_SUB_SOLVE") ? 1 : 0;
     p.sub_solve_off = sub_off;
+    static const int bulk_off = getenv("PB_NO_BULK") ? 1 : 0;
+    p.bulk_off = bulk_off;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
     return p;
@@ -654,7 +660,11 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
     PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_gather, 0));
     if (sl.used) PB_CUDA(cudaStreamWaitEvent(ns, sl.ev_trk, 0));              // kept detections still being read
     sl.post.dbg_slot = tp.seq & 63;
-    PB_CUDA(launch_nms(d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
+    if (h->pipe_tier.ok)
+        PB_CUDA(launch_nms_tier(h->pipe_tier, d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan,
+                                sl.cand, sl.post, sl.spill, ns));
+    else
+        PB_CUDA(launch_nms(d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
     PB_CUDA(cudaEventRecord(sl.ev_nms, ns));
     // the lazy NMS sweep fetches keypoints from the borrowed head tensor: later work on the caller's
     // stream (e.g. the engine writing the next batch into the same buffer) is ordered after it then.

@@ -89,6 +89,7 @@ struct TrackParams {
     // where the large per-frame arrays live (1 = shared memory, 0 = global scratch / state)
     int cost_in_smem, det_in_smem, pred_in_smem, term_floats, cell_cap;
     int precomputed;     // predict, centres, gates and the tier-1 cost pass of this frame were done by the pre-kernel (large tables)
+    int bulk_off;        // 1: the stand-alone tracker kernel loads the state slabs element by element instead of by bulk copy (A/B switch, PB_NO_BULK)
     int sub_solve_off;   // 1: tiers 2 and 3 of larger tables keep the CTA-wide / wide solve (A/B switch, PB_NO_SUB_SOLVE)
     SmemOffsets so;      // shared-memory layout (tracker_plan)
 };

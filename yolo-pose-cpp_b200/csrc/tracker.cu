@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NTHREADS)
 #endif
 pb_tracker_kernel(TrackBuffers tb, TrackParams P, DetSource src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tracker_body<NTHREADS, ALLSMEM, false>(tb, P, src, blockIdx.x, smem_raw, 0, P.seq, P.frame_id, tb.outputs, tb.num_outputs);
+    tracker_body<NTHREADS, ALLSMEM, false, false, ALLSMEM>(tb, P, src, blockIdx.x, smem_raw, 0, P.seq, P.frame_id, tb.outputs, tb.num_outputs);
 }
 
 // =======================================================================================

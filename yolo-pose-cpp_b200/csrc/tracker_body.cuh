@@ -293,8 +293,8 @@ static __device__ __noinline__ bool auction_solve_unlocked(const SubSolveArgs a)
         unsigned* cb = reinterpret_cast<unsigned*>(a.colbid);
         int* cr = reinterpret_cast<int*>(a.colbid) + nc;
         // (row scratch: rowbc, idle since the centre stage; the solve clears and fills it by slot)
-        if (nc <= 32) auction_solve_lean32<1>(cc, a.T, nc, sub_act, nr, a.rowbc, sub_own, a.price, a.aowner, cb, cr);
-        else auction_solve_lean32<2>(cc, a.T, nc, sub_act, nr, a.rowbc, sub_own, a.price, a.aowner, cb, cr);
+        if (nc <= 32) auction_solve_lean32<1, 1>(cc, a.T, nc, sub_act, nr, a.rowbc, sub_own, a.price, a.aowner, cb, cr);
+        else auction_solve_lean32<2, 1>(cc, a.T, nc, sub_act, nr, a.rowbc, sub_own, a.price, a.aowner, cb, cr);
         __syncwarp();
         for (int j = lane; j < nc; j += 32) {
             const int slot = sub_own[j];
@@ -720,6 +720,31 @@ __device__ __forceinline__ bool chain_advance(unsigned long long* w) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Bulk asynchronous staging of the state slabs (cp.async.bulk, the 1-D form of the TMA: SASS UBLKCP) for the stand-alone
+// tracker kernel: one thread queues the copies of a stream's slabs right after it has acquired the predecessor's release,
+// the copy engine of the SM moves them into shared memory while the CTA goes on, and an mbarrier (expect-tx byte count)
+// tells everybody when they have landed — instead of one LDG -> STS round trip per element on the issue slots of a
+// latency-bound kernel, with the ordered active list then derived from shared memory instead of from L2.
+// Sizes and addresses must be multiples of 16 bytes (T % 4 == 0; the slabs are cudaMalloc'ed and indexed by b * T).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");     // the initialised barrier is visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // wait_mode (stand-alone): 2 = the previous frame of this video stream was run by this very CTA (resident tracker,
 // tracker.cu: pb_tracker_seq_kernel): both waits for the predecessor are skipped.
 // wait_mode (fused): 1 = this CTA waits for its turn and takes the chain at the wait point; first_of_owner: the first
@@ -731,7 +756,7 @@ __device__ __forceinline__ bool chain_advance(unsigned long long* w) {
 // global memory (first frame of the launch); res_last: write it back and release the stream (last frame).  In between a
 // frame reads nothing but its detections from global memory and stores only what nobody on the device waits for
 // (predictions, centres, scores, records).  Same expressions on the same values: same results.
-template <int NTHREADS, bool ALLSMEM, bool FUSED, bool RES = false>
+template <int NTHREADS, bool ALLSMEM, bool FUSED, bool RES = false, bool BULK = false>
 __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackParams& P, const DetSource& src, const int b,
                                              unsigned char* smem_raw, const int D_fused, const int seq, const int frame_id,
                                              void* outputs, int* num_outputs, const int wait_mode = 0, const bool first_of_owner = true,
@@ -795,6 +820,10 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) { if (!FUSED) s.dscore[d] = src_score[d]; s.col[d] = -1; }
     if (tid < 32) s.misc[tid] = 0;
+    // state slabs by bulk asynchronous copy (stand-alone kernel, everything in shared memory, 16-byte multiples)
+    __shared__ __align__(8) unsigned long long state_bar;
+    const bool bulk = BULK && ALLSMEM && !FUSED && !RES && (T & 3) == 0 && P.bulk_off == 0;
+    if (bulk && tid == 0) mbar_init(&state_bar, 1);
     if (tid < 20 && st_load) s.acc[tid] = 0ull;     // (resident tracker: accumulated over the frames of the launch)
     if (tid < KP) s.sig[tid] = kSigmas[tid];
     if (D > 0) {
@@ -828,11 +857,27 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         const int want = seq - 1;
         const int* flag = tb.seq_done + b;
         const unsigned long long w0 = globaltimer_ns();
+        bool timed_out = false;
         for (;;) {
             int v;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v - want >= 0) break;
-            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; break; }
+            if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; timed_out = true; break; }
+        }
+        if (bulk && !timed_out) {
+            // the predecessor's slabs were written through the generic proxy and released; this thread has acquired them:
+            // order that before the reads of the async proxy, then queue the copies (they complete on state_bar)
+            asm volatile("fence.proxy.async;" ::: "memory");
+            const unsigned tb4 = (unsigned)T * 4u, cost_b = (unsigned)T * (unsigned)D * 4u;
+            mbar_expect_tx(&state_bar, 6u * tb4 + 4u * tb4 + cost_b);
+            bulk_g2s(s.active, g_active, tb4, &state_bar);
+            bulk_g2s(s.states, g_states, tb4, &state_bar);
+            bulk_g2s(s.hits, g_hits, tb4, &state_bar);
+            bulk_g2s(s.ids, g_ids, tb4, &state_bar);
+            bulk_g2s(s.ages, g_ages, tb4, &state_bar);
+            bulk_g2s(s.rowbc, gm_dirty, tb4, &state_bar);          // predicted pose changed since its centre was derived
+            bulk_g2s(s.tcent, g_tcent, 4u * tb4, &state_bar);
+            if (cost_b) bulk_g2s(s.cost, g_cost, cost_b, &state_bar);
         }
         const unsigned long long w1 = globaltimer_ns();
         if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
@@ -861,6 +906,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     }
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
+    if (bulk) mbar_wait(&state_bar, 0u);            // (one use per CTA: phase 0)
     // State slabs -> shared memory, and in the same pass the ordered active list (ascending t).  The list position of
     // a row is its rank among the active rows — the auction breaks ties between equal bids by it (lowest row,
     // hungarian.cu:100) — so it must not depend on which warp gets here first: every warp derives the number of
@@ -871,7 +917,9 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         const int t = t0 + c.lane;
         int a = 0, st = 0;
         if (t < T) {
-            if (st_load) {
+            if (bulk) {                     // the slabs have landed in shared memory (mbarrier above)
+                a = s.active[t]; st = s.states[t];
+            } else if (st_load) {
                 a = g_active[t]; st = g_states[t];
                 s.active[t] = a; s.states[t] = st; s.hits[t] = g_hits[t]; s.ids[t] = g_ids[t]; s.ages[t] = g_ages[t];
                 const int dy = gm_dirty[t];
@@ -883,7 +931,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
             }
             s.row[t] = -1;
         }
-        const int* act_src = st_load ? g_active : s.active;
+        const int* act_src = (st_load && !bulk) ? g_active : s.active;
         int start = 0;
 #pragma unroll 1
         for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, act_src[pb + c.lane] == 1));
@@ -894,7 +942,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         if (act) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
         if (c.lane == 0 && t0 + 32 >= T) s.misc[0] = start + __popc(bm);
     }
-    if (st_load) {
+    if (st_load && !bulk) {
 #pragma unroll 1
         for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
         if (RES) {
@@ -910,7 +958,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     c.sub_solve = P.term_floats >= 2048 && P.cell_cap >= 192 && P.sub_solve_off == 0;
     c.pred = pred_in_smem ? s.pred : g_pred;
     // (resident tracker: the whole persistent matrix is loaded once — later frames index it with their own D, quirk Q1)
-    if (cost_in_smem && st_load) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
+    if (cost_in_smem && st_load && !bulk) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
     __syncthreads();
     const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
     stamp(0);
@@ -1026,13 +1074,19 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
             if (tier < 2) lock_pairs(c, s.gate, na, tier > 0);
             if (tier == 0) stamp(14);
             if (tier == 0 && c.warp_auction && na <= 32) {
-                // Every active row matched in tier 1 (the usual frame: everybody found its detection)?  Tiers 2 and 3 then
-                // change nothing but the cells of the inactive rows (cost <- 1.0, :351-354): the locked rows own no gate bit
-                // (lock_pairs), so neither cost pass writes a cell, both solves clear the assignments and stop before
-                // their first iteration, the merges restore them and the locks rewrite the 1e9 cells of tier 1.  Do just
-                // that write and leave the loop: six block barriers less on the chain of dependent frames.
-                const bool unmatched = c.lane < na && s.row[s.act_list[c.lane]] < 0;
-                if (__ballot_sync(FULLM, unmatched) == 0u) {           // the same in every warp (row is final: lock_pairs ended with a barrier)
+                // Every active row matched in tier 1 (the usual frame: everybody found its detection), or every detection
+                // taken (a stream with a track more than it has detections: the frames whose auction ran longest)?  Tiers 2
+                // and 3 then change nothing but the cells of the inactive rows (cost <- 1.0, :351-354).  lock_pairs has
+                // cleared the gate words of the matched rows and the gate bits of the matched columns and set the cells of
+                // both to 1e9 in every active row, so neither cost pass writes a cell, no row finds a column above the -1e9
+                // floor, both solves clear the assignments and stop before their first iteration, the merges restore them
+                // and the locks rewrite the 1e9 cells of tier 1.  Do just that write and leave the loop: six block
+                // barriers (2.5 + 3 us where a row is left over) less on the chain of dependent frames.
+                const bool row_left = c.lane < na && s.row[s.act_list[c.lane]] < 0;
+                bool col_left = false;
+                for (int d = c.lane; d < c.D; d += 32) col_left |= s.col[d] < 0;
+                // (the same in every warp: row and col are final, lock_pairs ended with a barrier)
+                if (__ballot_sync(FULLM, row_left) == 0u || __ballot_sync(FULLM, col_left) == 0u) {
                     cost_inactive_rows(c);
                     __syncthreads();
                     stamp(3);
