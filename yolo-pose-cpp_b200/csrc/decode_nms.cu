@@ -238,6 +238,7 @@ pb_nms_tier_kernel(const __grid_constant__ NmsTierParams F) {
 }
 
 static const void* nms_tier_func(int threads, int per_sm) {
+    if (threads == 1024) return (const void*)pb_nms_tier_kernel<1024, 1>;
     if (threads == 512) return (const void*)pb_nms_tier_kernel<512, 2>;
     if (threads == 384) return (const void*)pb_nms_tier_kernel<384, 3>;
     if (threads == 256 && per_sm == 3) return (const void*)pb_nms_tier_kernel<256, 3>;
@@ -246,13 +247,16 @@ static const void* nms_tier_func(int threads, int per_sm) {
 }
 
 // per_sm CTAs of `threads` threads per SM: 2 x 512 (the default), 3 x 384, 3 x 256 or 4 x 256
-NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin, int threads, int per_sm) {
+// target_kb > 0: shared memory of a CTA (1024 threads: one CTA per SM, sized below the full candidate cap so that the SM keeps
+// the shared-memory / L1 split of the kernels around it)
+NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin, int threads, int per_sm, int target_kb) {
     NmsTierPlan p{};
     p.ok = false;
     p.threads = threads; p.per_sm = per_sm;
     if (!nms_tier_func(threads, per_sm)) return p;
     size_t target = (size_t)(228 - per_sm) * 1024 / (size_t)per_sm;      // 228 KB per SM, 1 KB reserved per resident CTA
     target &= ~(size_t)1023;
+    if (target_kb > 0 && (size_t)target_kb * 1024 < target) target = (size_t)target_kb * 1024;
     if (target > smem_optin) target = smem_optin;
     int ct = 0;
     for (int c = 64; c <= max_cand; c += 16) {
@@ -282,7 +286,8 @@ cudaError_t launch_nms_tier(const NmsTierPlan& tp, const float* d_heads, int N, 
     if (!fn) return cudaErrorInvalidValue;
     const cudaError_t e = ensure_dyn_smem(fn, tp.smem_bytes);
     if (e != cudaSuccess) return e;
-    if (tp.threads == 512) pb_nms_tier_kernel<512, 2><<<B, 512, tp.smem_bytes, stream>>>(F);
+    if (tp.threads == 1024) pb_nms_tier_kernel<1024, 1><<<B, 1024, tp.smem_bytes, stream>>>(F);
+    else if (tp.threads == 512) pb_nms_tier_kernel<512, 2><<<B, 512, tp.smem_bytes, stream>>>(F);
     else if (tp.threads == 384) pb_nms_tier_kernel<384, 3><<<B, 384, tp.smem_bytes, stream>>>(F);
     else if (tp.per_sm == 3) pb_nms_tier_kernel<256, 3><<<B, 256, tp.smem_bytes, stream>>>(F);
     else pb_nms_tier_kernel<256, 4><<<B, 256, tp.smem_bytes, stream>>>(F);
@@ -328,6 +333,15 @@ DecodePlan decode_plan(int B, int N, int max_cand) {
 cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, bool lazy_keypoints, const DecodePlan& plan,
                                  const CandScratch& cs, cudaStream_t stream) {
     const size_t smem1 = (size_t)plan.segcap * sizeof(int);
+    {   // experiment: ask for the shared-memory configuration of the per-stream kernels (percent of 228 KB) so that SMs never re-split
+        static const int pct = getenv("PB_DECODE_CARVEOUT") ? atoi(getenv("PB_DECODE_CARVEOUT")) : -1;
+        static bool done = false;
+        if (pct >= 0 && !done) {
+            cudaFuncSetAttribute((const void*)pb_decode_gather_kernel<HEAD_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute((const void*)pb_decode_gather_kernel<BOX_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            done = true;
+        }
+    }
     if (lazy_keypoints)
         pb_decode_gather_kernel<BOX_ROWS><<<dim3(plan.nseg, B), DG_THREADS, smem1, stream>>>(d_heads, N, plan.nseg, plan.groups_per_seg,
                                                                                             plan.segcap, conf_thr, cs);

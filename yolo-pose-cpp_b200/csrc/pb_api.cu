@@ -206,6 +206,7 @@ void pb_default_config(pb_config* c) {
 
 static void seq_configure(pb_handle_st* h, int sm_count);
 static NmsTierPlan tier_plan_by_id(const pb_config& c, int id);
+static int smem_config_kb(size_t bytes);
 
 static int build_handle(pb_handle_st* h) {
     const pb_config& c = h->cfg;
@@ -395,8 +396,24 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
         const int l = atoi(e);
         if (l >= 0 && l <= 3 && (l <= 1 || (l - 1) * c.num_streams < prop.multiProcessorCount)) h->lanes = l;
     }
-    if (c.pipeline_depth > 1 && !h->fplan.ok)
-        if (const char* e = getenv("PB_PIPE_NMS_TIER")) h->pipe_tier = tier_plan_by_id(c, atoi(e));
+    if (!h->fplan.ok) {
+        // The NMS kernel in the shared-memory configuration of the tracker kernel.  An SM splits its 256 KB between L1 and
+        // shared memory in steps (8 ... 100, 132, 164, 196, 228 KB) and changes the split only when it is empty; NMS CTAs
+        // sized for the full candidate cap (224 KB at 1024 candidates) and tracker CTAs (137 KB: the 164 KB configuration)
+        // then keep draining each other's SMs.  Measured at 64 streams: 31.5 us per step with the 224 KB kernel, 30.6 us at
+        // 200 KB, 26.8 us at 160 KB and below.  So the NMS kernel takes the tracker's configuration: shared memory for the
+        // candidates that fit (704 at 163 KB), the spill path for a stream with more (same results).  PB_PIPE_NMS_TIER: 0 off,
+        // 1-4 the small-CTA variants, >= 64 that many KB.
+        int id = -1;
+        if (const char* e = getenv("PB_PIPE_NMS_TIER")) id = atoi(e);
+        if (id < 0) {
+            const TrackerPlan tp = tracker_plan(c.max_tracks, c.max_detections);
+            const int cls = smem_config_kb(tp.smem_bytes);
+            if (cls >= 100 && (size_t)cls * 1024 < decode_nms_smem_bytes(c.max_candidates, c.max_keep) + 1024) id = cls - 1;
+        }
+        if (id > 0) h->pipe_tier = tier_plan_by_id(c, id);
+        if (h->pipe_tier.ok && h->pipe_tier.CT < 128 && h->pipe_tier.CT < c.max_candidates) h->pipe_tier = NmsTierPlan{};
+    }
     int r = build_handle(h);
     if (r != PB_OK) { pb_destroy(h); return r; }
     *out = h;
@@ -498,6 +515,9 @@ int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, p
         }
         PB_CUDA(launch_nms_tier(h->exp_tier, d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan,
                                 h->cand, h->post, h->exp_spill, (cudaStream_t)stream));
+    } else if (h->pipe_tier.ok) {
+        PB_CUDA(launch_nms_tier(h->pipe_tier, d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan,
+                                h->cand, h->post, h->ring[h->cur].spill, (cudaStream_t)stream));
     } else
     PB_CUDA(launch_nms(d_heads, c.num_anchors, nms_sweep_mode(h), c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, h->cand, h->post, (cudaStream_t)stream));
     if (h->profiling && e0 >= 0 && (e1 = prof_event(h)) >= 0) {
@@ -740,13 +760,22 @@ static int alloc_slot(pb_handle_st* h, PipeSlot& sl, unsigned long long* post_ns
 // Can this handle use the resident path, and with which tracker plan?  Small tables only (the auction runs in one warp, the
 // frame is a chain of short stages: exactly what a resident CTA is good at; large tables keep the row-sliced pre-kernel), and
 // the tracker CTAs must leave at least half of the SMs to the decode and NMS kernels they wait for.
+// smallest shared-memory configuration (KB) of an sm_100 SM that holds a CTA with `bytes` of dynamic shared memory (+ 1 KB reserved)
+static int smem_config_kb(size_t bytes) {
+    static const int cls[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+    for (int k : cls) if (bytes + 1024 <= (size_t)k * 1024) return k;
+    return 228;
+}
+
 // Tiered NMS kernel variants by number: 1 = 2 x 512 threads per SM, 2 = 3 x 384, 3 = 3 x 256, 4 = 4 x 256 (0: none)
 static NmsTierPlan tier_plan_by_id(const pb_config& c, int id) {
+    // id >= 32: 1024 threads, one CTA per SM, id KB of shared memory (the working set of fewer candidates than the cap; more spill)
     static const int threads[5] = {0, 512, 384, 256, 256}, per_sm[5] = {0, 2, 3, 3, 4};
-    if (id < 1 || id > 4) return NmsTierPlan{};
+    if (id < 1 || (id > 4 && id < 32) || id > 227) return NmsTierPlan{};
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (id >= 32) return nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin, 1024, 1, id);
     return nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin, threads[id], per_sm[id]);
 }
 

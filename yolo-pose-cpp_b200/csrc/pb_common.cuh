@@ -133,7 +133,7 @@ cudaError_t launch_nms(const float* d_heads, int N, int sweep /*0 complete, 1 la
 // tiered NMS kernel (decode_nms.cu: pb_nms_tier_kernel): per_sm CTAs of `threads` threads share an SM (2 x 512, 3 x 384, 3 x 256,
 // 4 x 256), shared memory for CT candidates, spill path beyond
 struct NmsTierPlan { bool ok; int CT; size_t smem_bytes, spill_stride; SmemOffsets so_small, so_big; int threads, per_sm; };
-NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin, int threads = 512, int per_sm = 2);
+NmsTierPlan nms_tier_plan(int max_cand, int max_keep, size_t smem_optin, int threads = 512, int per_sm = 2, int target_kb = 0);
 cudaError_t launch_nms_tier(const NmsTierPlan& tp, const float* d_heads, int N, int sweep, int B, int max_cand, int max_keep, float nms_thr,
                             const DecodePlan& plan, const CandScratch& cs, const PostBuffers& out, unsigned char* spill, cudaStream_t stream);
 
