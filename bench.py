@@ -668,8 +668,12 @@ def main():
         kernels.append(roof("pb_decode_gather_kernel", B * bh, gather_us,
                             "dense-read model 224*N B per stream-frame (SURVEY.md 8d); the kernel reads the confidence row and 32 B sectors at "
                             "candidate anchors only, so this is an EFFECTIVE bandwidth; `traffic` is ncu dram bytes per launch"))
+        npl = w.pipe.nms_plan()
         kernels.append(roof("pb_nms_kernel", B * int(cand_mean) * 224, nms_us,
-                            "candidate records (224 B each) read once; latency/issue-bound, working set in shared memory"))
+                            "candidate records (224 B each) read once; latency/issue-bound, working set in shared memory; launched as "
+                            + ("pb_nms_tier_kernel<%d,%d> with %d B of shared memory (working set of %d candidates, spill path beyond: the "
+                               "shared-memory configuration of the tracker kernel)" % (npl["threads"], npl["ctas_per_sm"], npl["smem_bytes"], npl["tier_candidates"])
+                               if npl["tier_candidates"] < w.pipe.cfg.max_candidates else "pb_nms_kernel (full candidate cap in shared memory)")))
     kernels.append(roof("pb_tracker_kernel", B * (bsf - (224 * w.N if c["kind"] == "head" else 0)), track_us,
                         "track state read+written once + TrackOutput records (+ detections for config 5); latency-bound (up to 150 dependent auction "
                         "iterations per stream-frame), HBM is not its limit"))

@@ -127,6 +127,12 @@ int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int per
  * is a loop of pb_step). */
 int pb_step_path(pb_handle_t h, int* per_step, int* seq_chunk);
 
+/* Launch plan of the NMS kernel of the per-step paths: threads per CTA, CTAs that share an SM, dynamic shared memory (bytes)
+ * and the number of candidates whose working set that holds (*tier_candidates == max_candidates: the plain kernel; fewer:
+ * the tiered kernel, sized to the shared-memory configuration of the tracker kernel — streams with more candidates keep
+ * their per-candidate arrays in a global scratch, same results).  Any pointer may be null. */
+int pb_nms_plan(pb_handle_t h, int* threads, int* ctas_per_sm, int* smem_bytes, int* tier_candidates);
+
 /* With pipeline_depth > 1 pb_step returns with NMS and tracker work still running on internal
  * streams.  pb_join makes `stream` wait for all of it (asynchronous, no host blocking); every
  * pb_get_* function and the stage-level entry points join implicitly. */

@@ -34,6 +34,27 @@ def test_postprocess_matches_checker(pb, orc, cuda, canvas, persons, clumps, B, 
                 assert_same(got[b], orc.postprocess(heads[f, b]), f"f{f} b{b} mode{mode}")
 
 
+def test_nms_kernel_in_the_trackers_shared_memory_configuration(pb, orc, cuda, monkeypatch):
+    """By default the NMS kernel is sized to the shared-memory configuration of the tracker kernel (163 KB beside a 137 KB
+    tracker CTA instead of 224 KB for the full cap of 1024 candidates: SMs then keep their L1 / shared-memory split between the
+    two).  Streams with more candidates than that working set holds take the spill path inside the same launch: a crowd of 130
+    persons (about 900 candidates) beside one of 60 — same results as the checker, and as the plain kernel."""
+    cfg_big = pb.synth_config(canvas=1280, persons=130, period=16, clumps=10, kp_drop_prob=0.15)
+    cfg_small = pb.synth_config(canvas=1280, persons=60, period=16, clumps=6, kp_drop_prob=0.15)
+    heads = np.concatenate([pb.synth_heads(cfg_big, 1, 1, 0, 1, frame_major=True)[0], pb.synth_heads(cfg_small, 2, 1, 0, 1, frame_major=True)[0]])
+    pipe, got = run_post(pb, cuda, heads)
+    plan = pipe.nms_plan()
+    assert plan["threads"] == 1024 and plan["tier_candidates"] < 1024 and plan["smem_bytes"] <= 163 * 1024, plan
+    assert got[0]["num_cand"] > plan["tier_candidates"] > got[1]["num_cand"], (got[0]["num_cand"], got[1]["num_cand"], plan)
+    for b in range(2):
+        assert_same(got[b], orc.postprocess(heads[b]), f"b{b}")
+    monkeypatch.setenv("PB_PIPE_NMS_TIER", "0")
+    pipe0, got0 = run_post(pb, cuda, heads)
+    assert pipe0.nms_plan()["tier_candidates"] == 1024
+    for b in range(2):
+        assert_same(got0[b], got[b], f"plain kernel b{b}")
+
+
 def test_empty_and_single(pb, orc, cuda):
     heads = np.zeros((3, 56, 8400), np.float32)
     heads[1, 4, 4242] = 0.9; heads[1, :4, 4242] = [100, 100, 40, 80]

@@ -9,7 +9,7 @@ LIB = os.path.join(ROOT, "yolo-pose-cpp_b200", "lib", "libposebyte_b200.so")
 PAT = collections.OrderedDict([
     ("LDG 128-bit", r"\bLDG\.[A-Z0-9.]*128"), ("LDG (all)", r"\bLDG\."), ("STG", r"\bSTG\."), ("LDS", r"\bLDS"), ("STS", r"\bSTS"),
     ("CREDUX", r"\bCREDUX"), ("REDUX", r"\bREDUX"), ("VOTE", r"\bVOTE"), ("SHFL", r"\bSHFL"), ("MATCH", r"\bMATCH"),
-    ("BAR.SYNC", r"\bBAR\.SYNC"), ("ATOMS", r"\bATOMS"), ("ATOMG/RED", r"\b(ATOMG|RED)\."), ("MEMBAR", r"\bMEMBAR"), ("CCTL", r"\bCCTL"),
+    ("UBLKCP (bulk copy)", r"\bUBLKCP"), ("SYNCS (mbarrier)", r"\bSYNCS"), ("BAR.SYNC", r"\bBAR\.SYNC"), ("ATOMS", r"\bATOMS"), ("ATOMG/RED", r"\b(ATOMG|RED)\."), ("MEMBAR", r"\bMEMBAR"), ("CCTL", r"\bCCTL"),
     ("LDL (spill)", r"\bLDL"), ("STL (spill)", r"\bSTL"), ("MUFU", r"\bMUFU"), ("FFMA", r"\bFFMA"), ("HMMA/UTCMMA", r"\b(HMMA|UTC.MMA|UTCHMMA|IMMA)"),
 ])
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout

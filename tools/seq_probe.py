@@ -64,6 +64,11 @@ for w in which:
     run(name, B, occ, age, 5, {"PB_SEQ": "0", "PB_NO_FUSED": "1"})
     run(name, B, occ, age, 5, {"PB_SEQ": "1"})
     if os.environ.get("SEQ_PROBE_OLD"): run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_COMPACT": "1", "PB_SEQ_NMS_TIER": "1"})
+    if os.environ.get("SEQ_PROBE_TIERS"):
+        for tier in os.environ["SEQ_PROBE_TIERS"].split(","):
+            for lanes in ("3", "4"):
+                run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_NMS_TIER": tier, "PB_SEQ_LANES": lanes})
+        continue
     if os.environ.get("SEQ_PROBE_QUICK"):
         for lanes in ("3", "4"):
             for tier in ("0", "1"):

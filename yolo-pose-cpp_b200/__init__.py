@@ -69,7 +69,7 @@ class SynthConfig(C.Structure):
 # Every symbol include/posebyte_b200.h declares (tests check the library exports them all).
 ABI_SYMBOLS = [
     "pb_last_error", "pb_version", "pb_default_config", "pb_create", "pb_destroy", "pb_reset",
-    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_step_seq", "pb_step_path", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
+    "pb_postprocess", "pb_tracker_update", "pb_step", "pb_step_seq", "pb_step_path", "pb_nms_plan", "pb_join", "pb_step_host", "pb_submit_host", "pb_wait", "pb_get_tracks",
     "pb_get_tracks_all", "pb_get_num_active", "pb_get_kept", "pb_get_state", "pb_get_device_views",
     "pb_get_timing", "pb_get_stream_stage_ns", "pb_debug_timeline", "pb_launch_count", "pb_set_profiling", "pb_get_nms_path_counts", "pb_get_kernel_ms", "pb_get_kernel_us", "pb_get_post_stage_us", "launchPoseNMS", "pb_nms_legacy", "pb_auction_solve",
     "pb_set_output_transform", "pb_state_size", "pb_state_save", "pb_state_load", "pb_pose_distance", "pb_greedy_match",
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         L.pb_step.argtypes = [vp, vp, fp, fp, ip, vp]
         L.pb_step_seq.argtypes = [vp, vp, C.c_size_t, ip, ip, ip, fp, fp, ip, vp]
         L.pb_step_path.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.pb_nms_plan.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
         L.pb_step_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
         L.pb_join.argtypes = [vp, vp]
         L.pb_submit_host.argtypes = [vp, vp, fp, fp, ip, vp, vp]
@@ -261,6 +262,12 @@ class Pipeline:
         a, b = C.c_int(0), C.c_int(0)
         check(lib().pb_step_path(self._h, C.byref(a), C.byref(b)))
         return {"per_step": ("serial", "pipelined three-kernel step", "fused per-stream kernel")[a.value], "seq_chunk": b.value}
+
+    def nms_plan(self) -> dict:
+        """Launch plan of the NMS kernel of the per-step paths (pb_nms_plan)."""
+        v = [C.c_int(0) for _ in range(4)]
+        check(lib().pb_nms_plan(self._h, *[C.byref(x) for x in v]))
+        return dict(threads=v[0].value, ctas_per_sm=v[1].value, smem_bytes=v[2].value, tier_candidates=v[3].value)
 
     def join(self, stream=None):
         """Make `stream` wait for work a pipelined step left on the internal streams."""

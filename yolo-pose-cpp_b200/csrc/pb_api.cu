@@ -928,6 +928,16 @@ int pb_step_path(pb_handle_t h, int* per_step, int* seq_chunk) {
     return PB_OK;
 }
 
+int pb_nms_plan(pb_handle_t h, int* threads, int* ctas_per_sm, int* smem_bytes, int* tier_candidates) {
+    if (!h) { pb_set_error("pb_nms_plan: null handle"); return PB_ERR_INVALID; }
+    const bool tier = h->pipe_tier.ok && !h->fplan.ok;
+    if (threads) *threads = h->fplan.ok ? h->fplan.threads : (tier ? h->pipe_tier.threads : 1024);
+    if (ctas_per_sm) *ctas_per_sm = h->fplan.ok ? (h->fplan.threads <= 512 ? 2 : 1) : (tier ? h->pipe_tier.per_sm : 1);
+    if (smem_bytes) *smem_bytes = (int)(h->fplan.ok ? h->fplan.smem_bytes : (tier ? h->pipe_tier.smem_bytes : decode_nms_smem_bytes(h->cfg.max_candidates, h->cfg.max_keep)));
+    if (tier_candidates) *tier_candidates = h->fplan.ok ? h->fplan.CT : (tier ? h->pipe_tier.CT : h->cfg.max_candidates);
+    return PB_OK;
+}
+
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                  void* h_tracks, int* h_counts) {
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_step_host: null argument"); return PB_ERR_INVALID; }
