@@ -389,7 +389,9 @@ class Workload:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
+        t0 = time.perf_counter()
         self.run(steps)
+        self.host_enqueue_s = time.perf_counter() - t0      # host time to enqueue the K steps (the device runs behind it)
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1)
@@ -580,6 +582,7 @@ def main():
     barrier()
     launches0 = pb.launch_count()
     ms_total = w.timed(args.steps, barrier, stream)
+    host_enqueue_us = w.host_enqueue_s / args.steps * 1e6
     launches = pb.launch_count() - launches0
     outs, counts = w.pipe.get_tracks_all()
     n_out_mean = float(counts.mean())
@@ -637,7 +640,7 @@ def main():
     na = w.pipe.get_num_active()
     h64 = pb.words_checksum(np.frombuffer(outs.tobytes(), np.uint32)[: 1 << 16]) & ((1 << 52) - 1)
     stats = torch.tensor([ms_total, e2e["seconds"], float(launches), float(counts.sum()), kus["gather_us"], kus["nms_us"], kus["track_us"],
-                          float(e2e["tracks"]), latency_us, float(na.sum()), float(h64)], dtype=torch.float64, device=dev)
+                          float(e2e["tracks"]), latency_us, float(na.sum()), float(h64), host_enqueue_us], dtype=torch.float64, device=dev)
     if world > 1:
         gathered = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(gathered, stats)
@@ -685,6 +688,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "us_per_batch": ms_max / args.steps * 1e3,
         "us_per_batch_latency": float(allstats[:, 8].max()),
         "ms_per_step_ranks": {"min": min(per_rank_ms), "median": float(np.median(per_rank_ms)), "max": max(per_rank_ms)},
+        "host_enqueue_us_per_step_ranks": {"min": float(allstats[:, 11].min()), "median": float(np.median(allstats[:, 11])), "max": float(allstats[:, 11].max())},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": c["workload"], "config_id": cid, "streams_per_gpu": B, "total_streams": total_streams,
                    "parallelism": f"stream-sharded x{world}, no data-path collective",

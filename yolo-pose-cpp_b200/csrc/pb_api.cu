@@ -534,7 +534,7 @@ static TrackParams track_params(pb_handle_st* h, int frame_id) {
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
     static const int sub_off = getenv("PB_NO_SUB_SOLVE") ? 1 : 0;
     p.sub_solve_off = sub_off;
-    static const int bulk_off = getenv("PB_NO_BULK") ? 1 : 0;
+    static const int bulk_off = getenv("PB_NO_BULK") ? atoi(getenv("PB_NO_BULK")) : 0;      // 1 none, 2 centres + cost only, 3 slabs only
     p.bulk_off = bulk_off;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
@@ -875,7 +875,11 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
             const int lane = seq % L;
             cudaStream_t ns = h->s_seq_nms[lane];
             const float* heads = d_heads + (size_t)((first + s0 + i) % period) * step_stride;
-            PB_CUDA(launch_decode_gather(heads, c.num_streams, c.num_anchors, conf, false, h->dplan, sl.cand, ns));
+            // (timing experiment PB_SEQ_SKIP_DECODE=n: after the first n steps the decode launch is left out — the NMS kernels then
+            // work on whatever candidates their slot holds: wrong results, the step time of a path without a decode kernel)
+            static const int skip_after = getenv("PB_SEQ_SKIP_DECODE") ? atoi(getenv("PB_SEQ_SKIP_DECODE")) : 0;
+            if (!(skip_after > 0 && h->frames + i >= skip_after))
+                PB_CUDA(launch_decode_gather(heads, c.num_streams, c.num_anchors, conf, false, h->dplan, sl.cand, ns));
             if (s0 + i >= n_steps - L) PB_CUDA(cudaEventRecord(h->ev_seq_dec[lane], ns));
             sl.post.ready = sl.ready; sl.post.ready_seq = seq;
             sl.post.dbg_slot = seq & 63;

@@ -822,8 +822,11 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     if (tid < 32) s.misc[tid] = 0;
     // state slabs by bulk asynchronous copy (stand-alone kernel, everything in shared memory, 16-byte multiples)
     __shared__ __align__(8) unsigned long long state_bar;
-    const bool bulk = BULK && ALLSMEM && !FUSED && !RES && (T & 3) == 0 && P.bulk_off == 0;
-    if (bulk && tid == 0) mbar_init(&state_bar, 1);
+    // (P.bulk_off: 0 everything by bulk copy, 1 nothing, 2 centres + cost matrix only, 3 the six per-slot slabs only)
+    const bool bulk_ok = BULK && ALLSMEM && !FUSED && !RES && (T & 3) == 0 && P.bulk_off != 1;
+    const bool bulk = bulk_ok && P.bulk_off != 2;        // the six per-slot integer slabs
+    const bool bulk_big = bulk_ok && P.bulk_off != 3;    // centres and cost matrix
+    if (bulk_ok && tid == 0) mbar_init(&state_bar, 1);
     if (tid < 20 && st_load) s.acc[tid] = 0ull;     // (resident tracker: accumulated over the frames of the launch)
     if (tid < KP) s.sig[tid] = kSigmas[tid];
     if (D > 0) {
@@ -864,28 +867,34 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
             if (v - want >= 0) break;
             if (globaltimer_ns() - w0 > 500000000ull) { atomicExch(tb.error_flag, 1); s.misc[10] = 1; timed_out = true; break; }
         }
-        if (bulk && !timed_out) {
+        if (bulk_ok && !timed_out) {
             // the predecessor's slabs were written through the generic proxy and released; this thread has acquired them:
             // order that before the reads of the async proxy, then queue the copies (they complete on state_bar)
-            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("fence.proxy.async.global;" ::: "memory");
             const unsigned tb4 = (unsigned)T * 4u, cost_b = (unsigned)T * (unsigned)D * 4u;
-            mbar_expect_tx(&state_bar, 6u * tb4 + 4u * tb4 + cost_b);
-            bulk_g2s(s.active, g_active, tb4, &state_bar);
-            bulk_g2s(s.states, g_states, tb4, &state_bar);
-            bulk_g2s(s.hits, g_hits, tb4, &state_bar);
-            bulk_g2s(s.ids, g_ids, tb4, &state_bar);
-            bulk_g2s(s.ages, g_ages, tb4, &state_bar);
-            bulk_g2s(s.rowbc, gm_dirty, tb4, &state_bar);          // predicted pose changed since its centre was derived
-            bulk_g2s(s.tcent, g_tcent, 4u * tb4, &state_bar);
-            if (cost_b) bulk_g2s(s.cost, g_cost, cost_b, &state_bar);
+            mbar_expect_tx(&state_bar, (bulk ? 6u * tb4 : 0u) + (bulk_big ? 4u * tb4 + cost_b : 0u));
+            if (bulk_big) {
+                if (cost_b) bulk_g2s(s.cost, g_cost, cost_b, &state_bar);
+                bulk_g2s(s.tcent, g_tcent, 4u * tb4, &state_bar);
+            }
+            if (bulk) {
+                bulk_g2s(s.active, g_active, tb4, &state_bar);
+                bulk_g2s(s.states, g_states, tb4, &state_bar);
+                bulk_g2s(s.hits, g_hits, tb4, &state_bar);
+                bulk_g2s(s.ids, g_ids, tb4, &state_bar);
+                bulk_g2s(s.ages, g_ages, tb4, &state_bar);
+                bulk_g2s(s.rowbc, gm_dirty, tb4, &state_bar);      // predicted pose changed since its centre was derived
+            }
         }
         const unsigned long long w1 = globaltimer_ns();
         if (tb.dbg) { unsigned long long* q = tb.dbg + ((size_t)(seq & 63) * P.B + b) * 6; q[0] = t_begin; q[1] = w1; }
         s.acc[15] += w1 - w0;                        // telemetry: time spent waiting for the predecessor
         s.acc[16] += w0 - t_begin;                   // telemetry: detection-only prologue
-        const unsigned long long prev_end = g_ns[18];   // absolute time at which the predecessor released the stream
-        if (prev_end != 0ull && w1 > prev_end) s.acc[17] += w1 - prev_end;              // predecessor's release -> this CTA goes on
-        if (prev_end != 0ull && t_begin > prev_end) s.acc[19] += t_begin - prev_end;    // ... of which: this CTA had not started yet
+        if (tb.dbg) {                                   // (PB_TIMELINE only: a dependent L2 round trip on the chain of frames)
+            const unsigned long long prev_end = g_ns[18];   // absolute time at which the predecessor released the stream
+            if (prev_end != 0ull && w1 > prev_end) s.acc[17] += w1 - prev_end;              // predecessor's release -> this CTA goes on
+            if (prev_end != 0ull && t_begin > prev_end) s.acc[19] += t_begin - prev_end;    // ... of which: this CTA had not started yet
+        }
     }
     __syncthreads();
     if (s.misc[10]) {
@@ -906,7 +915,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     }
 #pragma unroll 1
     for (int d = tid; d < D; d += NT) g_dscore[d] = s.dscore[d];
-    if (bulk) mbar_wait(&state_bar, 0u);            // (one use per CTA: phase 0)
+    if (bulk) mbar_wait(&state_bar, 0u);            // (one use per CTA: phase 0; without the slabs the wait comes after the list, below)
     // State slabs -> shared memory, and in the same pass the ordered active list (ascending t).  The list position of
     // a row is its rank among the active rows — the auction breaks ties between equal bids by it (lowest row,
     // hungarian.cu:100) — so it must not depend on which warp gets here first: every warp derives the number of
@@ -933,8 +942,18 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         }
         const int* act_src = (st_load && !bulk) ? g_active : s.active;
         int start = 0;
+        if (T <= 256) {
+            // all preceding blocks' flags in flight at once (from L2 when the slabs are not in shared memory: one round trip
+            // instead of one per block); blocks at or beyond this warp's own contribute nothing
+            int fl[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) fl[k] = (k * 32 < t0) ? act_src[k * 32 + c.lane] : 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) start += __popc(__ballot_sync(FULLM, fl[k] == 1));
+        } else {
 #pragma unroll 1
-        for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, act_src[pb + c.lane] == 1));
+            for (int pb = 0; pb < t0; pb += 32) start += __popc(__ballot_sync(FULLM, act_src[pb + c.lane] == 1));
+        }
         const bool act = (a == 1);
         const unsigned bm = __ballot_sync(FULLM, act);
         const unsigned lm = __ballot_sync(FULLM, act && st == ST_LOST);
@@ -942,7 +961,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
         if (act) s.act_list[start + __popc(bm & ((1u << c.lane) - 1u))] = t;
         if (c.lane == 0 && t0 + 32 >= T) s.misc[0] = start + __popc(bm);
     }
-    if (st_load && !bulk) {
+    if (st_load && !bulk_big) {
 #pragma unroll 1
         for (int i = tid; i < T * 4; i += NT) s.tcent[i] = g_tcent[i];
         if (RES) {
@@ -958,7 +977,8 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     c.sub_solve = P.term_floats >= 2048 && P.cell_cap >= 192 && P.sub_solve_off == 0;
     c.pred = pred_in_smem ? s.pred : g_pred;
     // (resident tracker: the whole persistent matrix is loaded once — later frames index it with their own D, quirk Q1)
-    if (cost_in_smem && st_load && !bulk) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
+    if (cost_in_smem && st_load && !bulk_big) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
+    if (bulk_big && !bulk) mbar_wait(&state_bar, 0u);
     __syncthreads();
     const int na = s.misc[0];       // num_active_tracks_ at frame start (:1083-1088)
     stamp(0);
