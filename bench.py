@@ -554,11 +554,21 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Rendezvous barriers run over gloo (host side); the NCCL communicator is created for the statistics gather at the end — the run's
+    # only collective — so that no NCCL proxy / watchdog thread shares the host cores and the CUDA context with the thread that
+    # enqueues the timed steps.  BENCH_EARLY_NCCL=1: NCCL from the start (barriers included), for comparison.
+    early_nccl = os.environ.get("BENCH_EARLY_NCCL") == "1"
+    gloo = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if early_nccl:
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group("gloo")
+            gloo = dist.group.WORLD
 
     def barrier():
         if world > 1:
+            torch.cuda.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -642,8 +652,9 @@ def main():
     stats = torch.tensor([ms_total, e2e["seconds"], float(launches), float(counts.sum()), kus["gather_us"], kus["nms_us"], kus["track_us"],
                           float(e2e["tracks"]), latency_us, float(na.sum()), float(h64), host_enqueue_us], dtype=torch.float64, device=dev)
     if world > 1:
+        nccl = None if early_nccl else dist.new_group(backend="nccl", device_id=dev)      # one rank per GPU over NCCL
         gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)
+        dist.all_gather(gathered, stats, group=nccl)
         allstats = torch.stack(gathered).cpu().numpy()
     else:
         allstats = stats.cpu().numpy()[None]
