@@ -292,7 +292,9 @@ __device__ __forceinline__ int nms_body(const NmSmem& s, const float* __restrict
     if (tid == 0) t_stamp = globaltimer_ns();
     if (tid == 0 && out.dbg) out.dbg[((size_t)out.dbg_slot * nstreams + b) * 6 + 3] = t_stamp;
     auto stamp = [&](int slot) {   // thread 0 accumulates in shared memory, flushed once at the end
+#ifndef PB_NO_STAMPS
         if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
+#endif
     };
 
     // ---------------- 0. candidate list = concatenation of the segment lists (anchor order) -----

@@ -4,6 +4,7 @@
 // same buffers per GPUPostprocess / GPUTracker object: gpu_postprocess.cu:319-347,
 // gpu_tracker.cu:925-1010) as struct-of-arrays slabs, plus a pinned staging ring for the
 // host-buffer entry point.  There is no CPU fallback: pb_create fails without a device.
+#include <nvtx3/nvToolsExt.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -46,6 +47,17 @@ void pb_set_error(const char* fmt, ...) {
 }
 
 using namespace pb;
+
+// NVTX range around the entry points of the path (header-only NVTX 3: costs a null check when no tool is attached; the
+// reference marks nothing — SURVEY.md 5 lists the ranges as the tracing aid a profile of the frame loop needs)
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace
 
 // One slot of the step pipeline: candidate scratch (decode+gather -> NMS) and kept detections
 // (NMS -> tracker) with the events that order their reuse.
@@ -496,6 +508,7 @@ int pb_join(pb_handle_t h, pb_stream_t stream) {
 static int nms_sweep_mode(const pb_handle_st* h) { return h->lazy_keypoints ? 1 : (h->cfg.keypoint_fetch == 3 ? 2 : 0); }
 
 int pb_postprocess(pb_handle_t h, const float* d_heads, float conf, float nms, pb_stream_t stream) {
+    NvtxRange nvtx_range("pb_postprocess");
     if (!h || !d_heads) { pb_set_error("pb_postprocess: null argument"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
@@ -543,6 +556,7 @@ static TrackParams track_params(pb_handle_st* h, int frame_id) {
 
 int pb_tracker_update(pb_handle_t h, const float* d_det_poses, const float* d_det_scores,
                       const int* d_num_dets, int det_stride, int frame_id, pb_stream_t stream) {
+    NvtxRange nvtx_range("pb_tracker_update");
     if (!h) { pb_set_error("pb_tracker_update: null handle"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
@@ -710,6 +724,7 @@ static int step_pipelined(pb_handle_st* h, const float* d_heads, float conf, flo
 }
 
 int pb_step(pb_handle_t h, const float* d_heads, float conf, float nms, int frame_id, pb_stream_t stream) {
+    NvtxRange nvtx_range("pb_step");
     if (!h || !d_heads) { pb_set_error("pb_step: null argument"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
     if (h->fplan.ok && !h->profiling) return step_fused(h, d_heads, conf, nms, frame_id, (cudaStream_t)stream);
@@ -915,6 +930,7 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
 
 int pb_step_seq(pb_handle_t h, const float* d_heads, size_t step_stride, int period, int first, int n_steps,
                 float conf, float nms, int frame0, pb_stream_t stream) {
+    NvtxRange nvtx_range("pb_step_seq");
     if (!h || !d_heads || period < 1 || first < 0 || n_steps < 0) { pb_set_error("pb_step_seq: bad argument"); return PB_ERR_INVALID; }
     if (h->seq_chunk > 0 && n_steps >= 2 && !h->profiling && !h->lazy_keypoints && !h->rb_tracks) {
         DevGuard dev_guard(h->cfg.device);
@@ -944,6 +960,7 @@ int pb_nms_plan(pb_handle_t h, int* threads, int* ctas_per_sm, int* smem_bytes, 
 
 int pb_step_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                  void* h_tracks, int* h_counts) {
+    NvtxRange nvtx_range("pb_step_host");
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_step_host: null argument"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
@@ -1056,6 +1073,7 @@ int pb_state_load(pb_handle_t h, const void* h_blob, size_t bytes) {
 
 int pb_submit_host(pb_handle_t h, const float* h_heads, float conf, float nms, int frame_id,
                    void* h_tracks, int* h_counts) {
+    NvtxRange nvtx_range("pb_submit_host");
     if (!h || !h_heads || !h_tracks || !h_counts) { pb_set_error("pb_submit_host: null argument"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
     const pb_config& c = h->cfg;
@@ -1085,6 +1103,7 @@ static int check_order_flag(pb_handle_st* h) {
 }
 
 int pb_wait(pb_handle_t h) {
+    NvtxRange nvtx_range("pb_wait");
     if (!h) { pb_set_error("pb_wait: null handle"); return PB_ERR_INVALID; }
     DevGuard dev_guard(h->cfg.device);
     PB_TRY(join_on(h, h->own_stream));

@@ -798,7 +798,9 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     // stage telemetry (TrackerTiming): thread 0 accumulates globaltimer deltas in shared memory
     // and flushes them once at the end of the kernel
     auto stamp = [&](int slot) {
+#ifndef PB_NO_STAMPS
         if (tid == 0) { const unsigned long long now = globaltimer_ns(); s.acc[slot] += now - t_stamp; t_stamp = now; }
+#endif
     };
 
     // ---------------- prologue (:1065-1088) ----------------
