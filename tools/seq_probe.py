@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import posebyte_b200 as pb
 
-KEYS = ("PB_SEQ_SKIP_DECODE", "PB_SEQ", "PB_SEQ_COMPACT", "PB_SEQ_THREADS", "PB_SEQ_CHUNK", "PB_NO_FUSED", "PB_SEQ_NMS_TIER", "PB_SEQ_RESIDENT_STATE", "PB_SEQ_LANES")
+KEYS = ("PB_SEQ", "PB_SEQ_COMPACT", "PB_SEQ_THREADS", "PB_SEQ_CHUNK", "PB_NO_FUSED", "PB_SEQ_NMS_TIER", "PB_SEQ_RESIDENT_STATE", "PB_SEQ_LANES")
 
 def run(name, B, occlusion, max_age, depth, env, F=16, nstep=320, persons=20, canvas=640, T=128, Dm=64):
     for k in KEYS:
@@ -64,11 +64,6 @@ for w in which:
     run(name, B, occ, age, 5, {"PB_SEQ": "0", "PB_NO_FUSED": "1"})
     run(name, B, occ, age, 5, {"PB_SEQ": "1"})
     if os.environ.get("SEQ_PROBE_OLD"): run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_COMPACT": "1", "PB_SEQ_NMS_TIER": "1"})
-    if os.environ.get("SEQ_PROBE_SKIP"):
-        for tier in ("1", "2", "131", "0"):
-            for lanes in ("3", "4"):
-                run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_NMS_TIER": tier, "PB_SEQ_LANES": lanes, "PB_SEQ_SKIP_DECODE": "200"})
-        continue
     if os.environ.get("SEQ_PROBE_TIERS"):
         for tier in os.environ["SEQ_PROBE_TIERS"].split(","):
             for lanes in ("3", "4"):

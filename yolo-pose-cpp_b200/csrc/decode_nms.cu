@@ -333,15 +333,6 @@ DecodePlan decode_plan(int B, int N, int max_cand) {
 cudaError_t launch_decode_gather(const float* d_heads, int B, int N, float conf_thr, bool lazy_keypoints, const DecodePlan& plan,
                                  const CandScratch& cs, cudaStream_t stream) {
     const size_t smem1 = (size_t)plan.segcap * sizeof(int);
-    {   // experiment: ask for the shared-memory configuration of the per-stream kernels (percent of 228 KB) so that SMs never re-split
-        static const int pct = getenv("PB_DECODE_CARVEOUT") ? atoi(getenv("PB_DECODE_CARVEOUT")) : -1;
-        static bool done = false;
-        if (pct >= 0 && !done) {
-            cudaFuncSetAttribute((const void*)pb_decode_gather_kernel<HEAD_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute((const void*)pb_decode_gather_kernel<BOX_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            done = true;
-        }
-    }
     if (lazy_keypoints)
         pb_decode_gather_kernel<BOX_ROWS><<<dim3(plan.nseg, B), DG_THREADS, smem1, stream>>>(d_heads, N, plan.nseg, plan.groups_per_seg,
                                                                                             plan.segcap, conf_thr, cs);

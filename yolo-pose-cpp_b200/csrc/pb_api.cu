@@ -890,11 +890,7 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
             const int lane = seq % L;
             cudaStream_t ns = h->s_seq_nms[lane];
             const float* heads = d_heads + (size_t)((first + s0 + i) % period) * step_stride;
-            // (timing experiment PB_SEQ_SKIP_DECODE=n: after the first n steps the decode launch is left out — the NMS kernels then
-            // work on whatever candidates their slot holds: wrong results, the step time of a path without a decode kernel)
-            static const int skip_after = getenv("PB_SEQ_SKIP_DECODE") ? atoi(getenv("PB_SEQ_SKIP_DECODE")) : 0;
-            if (!(skip_after > 0 && h->frames + i >= skip_after))
-                PB_CUDA(launch_decode_gather(heads, c.num_streams, c.num_anchors, conf, false, h->dplan, sl.cand, ns));
+            PB_CUDA(launch_decode_gather(heads, c.num_streams, c.num_anchors, conf, false, h->dplan, sl.cand, ns));
             if (s0 + i >= n_steps - L) PB_CUDA(cudaEventRecord(h->ev_seq_dec[lane], ns));
             sl.post.ready = sl.ready; sl.post.ready_seq = seq;
             sl.post.dbg_slot = seq & 63;
