@@ -219,3 +219,15 @@ def test_cell_list_clamp_is_unreachable(pb, cuda):
     with pytest.raises(pb.PbError) as e:
         pb.Pipeline(num_streams=1, max_tracks=4, max_detections=4097)
     assert e.value.status == pb.PB_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("env", [{"PB_NO_BULK": "1"}, {"PB_NO_BULK": "2"}, {"PB_NO_BULK": "3"}, {"PB_NO_SUB_SOLVE": "1"}])
+def test_ab_switches_keep_the_results(pb, orc, cuda, monkeypatch, env):
+    """The stand-alone tracker kernel stages a stream's state slabs by bulk asynchronous copies (all of them, only the centres
+    and the cost matrix, only the per-slot slabs, or element by element: PB_NO_BULK) and, on larger tables, solves tiers 2 and
+    3 on the unmatched sub-problem (PB_NO_SUB_SOLVE turns that off): every variant against the checker, on the tracker's own
+    table size with occlusion gaps (LOST tracks, tier-3 recoveries) and on a crowd (wide solve, sub-problem solve)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert run_sequence(pb, orc, cuda, B=5, F=24, occlusion=1, max_age=4, fuse=0) > 0
+    assert run_sequence(pb, orc, cuda, B=2, F=8, canvas=1280, persons=100, clumps=10, T=256, Dm=128, check_state_every=4, fuse=0) > 0

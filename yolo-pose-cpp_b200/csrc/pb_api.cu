@@ -111,6 +111,7 @@ struct pb_handle_st {
     cudaStream_t s_seq_nms[SEQ_MAX_LANES] = {}, s_seq_trk = nullptr;
     TrackerPlan seq_plan{};
     NmsTierPlan exp_tier{}; unsigned char* exp_spill = nullptr;   // PB_NMS_TIER experiment (serial path)
+    int sub_solve_off = 0, bulk_off = 0;   // A/B switches read at pb_create: PB_NO_SUB_SOLVE, PB_NO_BULK (1 none, 2 centres + cost matrix only, 3 slabs only)
     NmsTierPlan pipe_tier{};       // ok: the pipelined three-kernel step launches the tiered NMS kernel (CTAs that share an SM)
     NmsTierPlan seq_nms{};         // ok: the steps of the resident path use the tiered (half-SM) NMS kernel
     std::vector<void*> allocs;
@@ -381,6 +382,8 @@ int pb_create(const pb_config* cfg, pb_handle_t* out) {
     if (!h) { pb_set_error("pb_create: out of host memory"); return PB_ERR_INVALID; }
     h->cfg = c;
     h->lazy_keypoints = (c.keypoint_fetch == 1);
+    if (getenv("PB_NO_SUB_SOLVE")) h->sub_solve_off = 1;
+    if (const char* e = getenv("PB_NO_BULK")) h->bulk_off = atoi(e);
     // fused per-stream kernel: always when asked for (1); by default (2) where it measured faster than the three-kernel step —
     // handles whose tracker grids cannot overlap (2 * num_streams > SM count): 128 streams 1.95 M against 1.55 M stream-frames/s,
     // 148 streams 2.30 M against 2.02 M; 64 streams 1.88 M against 2.04 M, one stream 25 us against 22 us per frame
@@ -545,10 +548,8 @@ static TrackParams track_params(pb_handle_st* h, int frame_id) {
     TrackParams p{};
     p.seq = h->trk_seq + 1;                 // committed (h->trk_seq = p.seq) once the launch has succeeded: no gap on failure
     p.B = c.num_streams; p.T = c.max_tracks; p.Dm = c.max_detections;
-    static const int sub_off = getenv("PB_NO_SUB_SOLVE") ? 1 : 0;
-    p.sub_solve_off = sub_off;
-    static const int bulk_off = getenv("PB_NO_BULK") ? atoi(getenv("PB_NO_BULK")) : 0;      // 1 none, 2 centres + cost only, 3 slabs only
-    p.bulk_off = bulk_off;
+    p.sub_solve_off = h->sub_solve_off;
+    p.bulk_off = h->bulk_off;
     p.new_track_thresh = c.new_track_thresh; p.max_age = c.max_age; p.min_hits = c.min_hits;
     p.gating_enabled = c.gating_enabled; p.frame_id = frame_id;
     return p;
