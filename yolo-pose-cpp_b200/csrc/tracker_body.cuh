@@ -218,6 +218,7 @@ struct Ctx {
     int T, D, Dw, tid, nthreads, lane, warp, nwarps;
     unsigned magicD, magicW;   // ceil(2^32 / D), ceil(2^32 / words): i / D == __umulhi(i, magicD) for i * D < 2^32 (0: divisor 1)
     bool warp_auction;  // small problem with the cost matrix in shared memory: single-warp solve
+    const int* od_flag; int od_want;   // (may be null) the predecessor's second release flag and the value to see: polled by an idle warp during the tier-1 solve
     bool sub_solve;     // tiers 2 and 3 of larger tables: solve the unmatched rows x unmatched detections only (auction_solve_unlocked)
     int term_floats, cell_cap;
     float* cost;        // shared or global, flat [t*D + d]
@@ -345,6 +346,13 @@ __device__ __forceinline__ void auction_solve(Ctx& c, int na, bool after_lock) {
             unsigned bits;
             if (D <= 32) lean_first_bid<1>(cr0, D, c.T, c.lane, bc, bits); else lean_first_bid<2>(cr0, D, c.T, c.lane, bc, bits);
             if (c.lane == 0) { pre_bc[ai] = bc; pre_bits[ai] = bits; }
+        }
+        if (!after_lock && c.od_flag != nullptr && c.tid == c.nthreads - 32) {
+            // The last warp has no row here: it looks at the predecessor's SECOND release (records assembled, g_poses no longer
+            // read), which the update stage needs — an L2 round trip that would otherwise sit on the chain behind the tiers.
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c.od_flag) : "memory");
+            if (v - c.od_want >= 0) s.misc[15] = 1;
         }
         __syncthreads();
         if (c.tid < 32) {
@@ -515,8 +523,12 @@ static __device__ __forceinline__ void cost_pass_oks(Ctx& c, const unsigned* gat
     const int cells_per_round = c.term_floats / KP;
     for (int a0 = 0; a0 < na; a0 += rows_per_chunk) {
         const int a1 = (a0 + rows_per_chunk < na) ? a0 + rows_per_chunk : na;
-        if (c.tid == 0) s.misc[5] = 0;
-        __syncthreads();
+        // (the first chunk finds the counter at zero: the prologue cleared it and every pass clears it again at its end,
+        // behind barriers — one block barrier less on the chain of frames)
+        if (a0 > 0) {
+            if (c.tid == 0) s.misc[5] = 0;
+            __syncthreads();
+        }
 #pragma unroll 1
         for (int ai = a0 + c.warp; ai < a1; ai += c.nwarps) {
             const int t = s.act_list[ai];
@@ -579,6 +591,7 @@ static __device__ __forceinline__ void cost_pass_oks(Ctx& c, const unsigned* gat
             __syncthreads();
         }
     }
+    if (c.tid == 0) s.misc[5] = 0;               // (every thread has read the count: the last round ended with a barrier, or the count was zero)
 }
 
 // Torso-only OKS (kernelTorsoOKS :455-489): four exponentials per cell, one thread per cell.
@@ -977,6 +990,8 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     c.cost = cost_in_smem ? s.cost : g_cost;
     c.warp_auction = cost_in_smem && T <= 1024 && (long)T * Dm <= 16384;
     c.sub_solve = P.term_floats >= 2048 && P.cell_cap >= 192 && P.sub_solve_off == 0;
+    c.od_flag = (!FUSED && wait_mode != 2) ? (tb.out_done + b) : nullptr;
+    c.od_want = seq - 1;
     c.pred = pred_in_smem ? s.pred : g_pred;
     // (resident tracker: the whole persistent matrix is loaded once — later frames index it with their own D, quirk Q1)
     if (cost_in_smem && st_load && !bulk_big) for (int i = tid; i < (RES ? T * Dm : T * D); i += NT) s.cost[i] = g_cost[i];
@@ -1109,8 +1124,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
                 for (int d = c.lane; d < c.D; d += 32) col_left |= s.col[d] < 0;
                 // (the same in every warp: row and col are final, lock_pairs ended with a barrier)
                 if (__ballot_sync(FULLM, row_left) == 0u || __ballot_sync(FULLM, col_left) == 0u) {
-                    cost_inactive_rows(c);
-                    __syncthreads();
+                    cost_inactive_rows(c);                             // (ordered by the barrier behind the loop)
                     stamp(3);
                     break;
                 }
@@ -1122,7 +1136,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
     // The predecessor's record assembly reads g_poses after it released the state (second release at its end):
     // nothing before this point writes g_poses, tb.outputs or the telemetry slots; wait for it here (it finished
     // long ago unless the launches ran far apart from the usual order).
-    if ((FUSED ? first_of_owner : wait_mode != 2) && tid == 0) {
+    if ((FUSED ? first_of_owner : wait_mode != 2) && tid == 0 && s.misc[15] == 0) {      // (misc[15]: seen during the tier-1 solve)
         const int want = seq - 1;
         const unsigned long long w0 = globaltimer_ns();
         for (;;) {
@@ -1179,8 +1193,7 @@ __device__ __forceinline__ int tracker_body(const TrackBuffers& tb, const TrackP
             else if (st == ST_LOST) s.states[t] = ST_CONFIRMED;
         }
     }
-    __syncthreads();
-    stamp(6);
+    stamp(6);       // (no barrier: the ageing pass below touches the unmatched rows only, the loop above the matched ones)
 
     // ---------------- age unmatched (:1474-1487, kernel :651-688) ----------------
 #pragma unroll 1
