@@ -691,7 +691,20 @@ def main():
     kernels.append(roof("pb_tracker_kernel", B * (bsf - (224 * w.N if c["kind"] == "head" else 0)), track_us,
                         "track state read+written once + TrackOutput records (+ detections for config 5); latency-bound (up to 150 dependent auction "
                         "iterations per stream-frame), HBM is not its limit"))
-    dominant = max(kernels, key=lambda r: r["avg_launch_us"])
+    # `roofline`: the dominant kernel (longest launch) as the task statement defines it — SURVEY.md 8(d)'s per-unit figure (the
+    # algorithmic bytes of a tracked stream-frame through the WHOLE path) x the stream-frames one launch processes, over that
+    # kernel's own launch duration.  The kernel's own bytes and bandwidth are its entry in `roofline_kernels`; the step-level
+    # figure (same bytes over the measured step time) is `roofline_step`.
+    dk = max(kernels, key=lambda r: r["avg_launch_us"])
+    dom_ach = B * bsf / (dk["avg_launch_us"] / 1e6) / 1e9 if dk["avg_launch_us"] > 0 else 0.0
+    dominant = {"kernel": dk["kernel"], "bound": "hbm", "achieved": dom_ach, "peak": peak, "unit": "GB/s", "frac": dom_ach / peak,
+                "traffic": dk["traffic"], "avg_launch_us": dk["avg_launch_us"], "algorithmic_bytes_per_launch": B * bsf,
+                "bytes_per_stream_frame": bsf, "stream_frames_per_launch": B, "peak_source": peak_src,
+                "own_algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_launch"], "own_achieved": dk["achieved"],
+                "note": "SURVEY.md 8(d) bytes per stream-frame (dense-read model of the whole path) x streams per launch over the duration of the "
+                        "longest kernel of the step (CUDA events, serial path); this kernel itself moves `own_algorithmic_bytes_per_launch` "
+                        "(`traffic`: ncu dram bytes per launch) and is bound by the latency of its dependent stages, not by HBM — see "
+                        "`roofline_kernels` and `roofline_step`"}
     step_ach = total_streams * bsf * args.steps / (ms_max / 1e3) / 1e9 / world
     per_rank_ms = [float(x) / args.steps for x in allstats[:, 0]]
     line = {
