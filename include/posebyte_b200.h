@@ -115,7 +115,7 @@ int pb_step(pb_handle_t h, const float* d_heads, float conf_threshold, float nms
  * one library call instead of n_steps crossings of the language boundary.  Same results as the loop it replaces.
  * Knowing the frames ahead lets the library keep every video stream's tracker state ON ITS SM for the whole sequence
  * (the reference's per-stream frame loop, main.cpp:207-224, as one resident CTA per stream): with pipeline_depth > 1 and
- * at most a third of the SMs' worth of streams (PB_SEQ=1 in the environment: up to half), chunks of up to 32 steps run
+ * at most half of the SMs' worth of streams (74 on a B200; PB_SEQ=0 in the environment turns it off), chunks of up to 32 steps run
  * with ONE tracker launch each, whose CTAs take every frame's kept detections from the NMS kernel of its step as soon as
  * they are published.  pb_step_path tells which path a handle takes.  The head batches are borrowed until the work
  * enqueued on `stream` by this call has run (as for pb_step). */

@@ -295,11 +295,12 @@ def test_step_seq_equals_step_loop(pb, cuda):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,occlusion,max_age,chunk,tier,persons", [(6, 1, 4, 0, 0, 12), (6, 1, 4, 16, 0, 12), (64, 0, 10, 16, 0, 12), (70, 1, 30, 7, 0, 12),
                                                                     (64, 0, 10, 16, 3, 12), (70, 1, 30, 7, 4, 12), (12, 0, 10, 5, 2, 12),
-                                                                    (9, 1, 10, 16, 3, 40), (9, 0, 10, 16, 4, 40)])
+                                                                    (9, 1, 10, 16, 3, 40), (9, 0, 10, 16, 4, 40),
+                                                                    (64, 0, 10, 0, -1, 12), (72, 1, 30, 0, -1, 12), (9, 0, 10, 0, -1, 40)])
 def test_resident_tracker_sequence_path(pb, orc, cuda, monkeypatch, B, occlusion, max_age, chunk, tier, persons):
     """pb_step_seq on a pipelined handle takes the resident-tracker path (one tracker CTA per video stream stays on its SM for
     a chunk of up to 16 steps here, the stream's state in shared memory, and is fed by the decode and NMS kernels of those
-    steps; default up to 49 streams, PB_SEQ=1 up to 74): sequences that are not multiples of the chunk, back-to-back calls
+    steps; up to 74 streams): sequences that are not multiples of the chunk, back-to-back calls
     without a join, single steps, a reset and a stage-level call in between — states and records must equal the serial
     handle's bit for bit, and the checker's on some streams."""
     torch = cuda
@@ -307,7 +308,10 @@ def test_resident_tracker_sequence_path(pb, orc, cuda, monkeypatch, B, occlusion
         monkeypatch.setenv("PB_SEQ", "1"); monkeypatch.setenv("PB_SEQ_CHUNK", str(chunk))
     # tier > 0: the steps' NMS kernel is a tiered one (2 x 512, 3 x 384, 3 x 256 or 4 x 256 threads per SM); with 40 persons
     # (about 280 candidates) the streams exceed the shared-memory tier of the small CTAs and take their spill path
-    monkeypatch.setenv("PB_SEQ_NMS_TIER", str(tier))
+    # tier -1: the handle's own choice — pairs of 512-thread NMS CTAs with 81 KB each (the working set of 256 candidates; 40 persons
+    # exceed it: spill path), four lanes, resident path up to 74 streams
+    if tier >= 0:
+        monkeypatch.setenv("PB_SEQ_NMS_TIER", str(tier))
     F = 24
     scfg = pb.synth_config(canvas=640, persons=persons, period=48, occlusion=occlusion)
     host = pb.synth_heads(scfg, 11, B, 0, F, frame_major=True)

@@ -44,6 +44,7 @@ def run(name, B, occlusion, max_age, depth, env, F=16, nstep=320, persons=20, ca
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record(); go(20); e1.record(); torch.cuda.synchronize()
         bursts.append(e0.elapsed_time(e1) / 20 * 1e3)
+    tele["post_stage_us"] = pp.post_stage_us()
     state = pp.state_save()[24:]
     o, c = pp.get_tracks_all()
     same = None
@@ -66,7 +67,7 @@ for w in which:
     if os.environ.get("SEQ_PROBE_OLD"): run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_COMPACT": "1", "PB_SEQ_NMS_TIER": "1"})
     if os.environ.get("SEQ_PROBE_TIERS"):
         for tier in os.environ["SEQ_PROBE_TIERS"].split(","):
-            for lanes in ("3", "4"):
+            for lanes in os.environ.get("SEQ_PROBE_LANES", "3,4").split(","):
                 run(name, B, occ, age, 5, {"PB_SEQ": "1", "PB_SEQ_NMS_TIER": tier, "PB_SEQ_LANES": lanes})
         continue
     if os.environ.get("SEQ_PROBE_QUICK"):

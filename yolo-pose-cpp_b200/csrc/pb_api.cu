@@ -109,6 +109,7 @@ struct pb_handle_st {
     cudaEvent_t ev_seq_dec[SEQ_MAX_LANES] = {};       // per lane: its last decode launch (the last reader of a borrowed head tensor)
     cudaEvent_t ev_seq_start = nullptr;
     cudaStream_t s_seq_nms[SEQ_MAX_LANES] = {}, s_seq_trk = nullptr;
+    unsigned char* seq_spill[SEQ_MAX_LANES] = {};     // per lane: spill scratch of the tiered NMS kernel (its launches on a lane are serial)
     TrackerPlan seq_plan{};
     NmsTierPlan exp_tier{}; unsigned char* exp_spill = nullptr;   // PB_NMS_TIER experiment (serial path)
     int sub_solve_off = 0, bulk_off = 0;   // A/B switches read at pb_create: PB_NO_SUB_SOLVE, PB_NO_BULK (1 none, 2 centres + cost matrix only, 3 slabs only)
@@ -766,7 +767,7 @@ static int alloc_slot(pb_handle_st* h, PipeSlot& sl, unsigned long long* post_ns
     sl.outputs = outp;
     PB_TRY(dev_alloc(h, &sl.num_outputs, B));
     PB_TRY(dev_alloc(h, &sl.ready, B));
-    if (h->seq_nms.ok && h->seq_nms.spill_stride) PB_TRY(dev_alloc(h, &sl.spill, B * h->seq_nms.spill_stride));
+    // (the spill scratch of the tiered NMS kernel belongs to the lane, not to the slot: the NMS launches of a lane run one after the other)
     PB_CUDA(cudaEventCreateWithFlags(&sl.ev_gather, cudaEventDisableTiming));
     PB_CUDA(cudaEventCreateWithFlags(&sl.ev_nms, cudaEventDisableTiming));
     PB_CUDA(cudaEventCreateWithFlags(&sl.ev_trk, cudaEventDisableTiming));
@@ -787,6 +788,13 @@ static int smem_config_kb(size_t bytes) {
 static NmsTierPlan tier_plan_by_id(const pb_config& c, int id) {
     // id >= 32: 1024 threads, one CTA per SM, id KB of shared memory (the working set of fewer candidates than the cap; more spill)
     static const int threads[5] = {0, 512, 384, 256, 256}, per_sm[5] = {0, 2, 3, 3, 4};
+    // 1000 + kb: two 512-thread CTAs per SM with kb KB of shared memory each (81: the pair fills the 164 KB configuration)
+    if (id >= 1032 && id <= 1113) {
+        int dev2 = 0, optin2 = 0;
+        cudaGetDevice(&dev2);
+        cudaDeviceGetAttribute(&optin2, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev2);
+        return nms_tier_plan(c.max_candidates, c.max_keep, (size_t)optin2, 512, 2, id - 1000);
+    }
     if (id < 1 || (id > 4 && id < 32) || id > 227) return NmsTierPlan{};
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
@@ -799,8 +807,7 @@ static void seq_configure(pb_handle_st* h, int sm_count) {
     const pb_config& c = h->cfg;
     h->seq_chunk = 0;
     if (c.pipeline_depth < 2 || h->plan.pre_slices > 0) return;
-    bool forced = false;
-    if (const char* e = getenv("PB_SEQ")) { if (atoi(e) == 0) return; forced = true; }
+    if (const char* e = getenv("PB_SEQ")) { if (atoi(e) == 0) return; }
     bool resident = true, compact = false;
     if (const char* e = getenv("PB_SEQ_RESIDENT_STATE")) resident = atoi(e) != 0;
     if (const char* e = getenv("PB_SEQ_COMPACT")) compact = atoi(e) != 0;
@@ -810,14 +817,19 @@ static void seq_configure(pb_handle_st* h, int sm_count) {
     if (!(p.cost_in_smem && p.det_in_smem && p.pred_in_smem)) return;
     if ((long)c.max_tracks * c.max_detections > 16384) return;
     // One tracker CTA per SM (1024 threads), resident for a whole chunk: the decode and NMS kernels that feed them get the other
-    // SMs.  Measured (tools/seq_probe.py, 640x640 heads, 20 persons): up to 48 streams the tracker CTAs are never kept waiting and
-    // the step takes 25.9-26.9 us against 28.9-29.6 us for the per-step path; at 64 streams the 84 SMs left cannot feed them
-    // (38.8 us against 32.3), so the per-step path stays the default there.  PB_SEQ=1 asks for the resident path wherever it
-    // cannot deadlock (half of the SMs free).
+    // SMs.  What those SMs must deliver is one step's NMS results per tracker frame (18-21 us): with one 1024-thread NMS CTA per
+    // SM (33-35 us each) the 84 SMs left beside 64 streams cannot (26.7-39 us per step; the per-step path: 26.8 us).  The steps of
+    // this path therefore launch the NMS kernel as pairs of 512-thread CTAs with 81 KB of shared memory each — the working set of
+    // 256 candidates, the spill path beyond — so that a pair fills the SM's 164 KB configuration: no SM re-splits L1 / shared
+    // memory between the kernels that alternate on it (pairs of 113 KB, which need the 228 KB configuration: 31-32 us per step).
+    // Measured (tools/seq_probe.py, 640x640 heads, 20 persons, four lanes): 64 streams 23.3 us per step against 26.8 us for the
+    // per-step path (20-step bursts 26.2-26.7 against 30.2), 72 streams 25.8 against 29.0, 48 streams 22.5 against 25.5, 32
+    // streams 22.0 against 25.1; the tracker CTAs wait 0.2-0.5 us per frame.  Three or five lanes: 24.4 us at 64 streams.
+    // The path needs half of the SMs free for the kernels the tracker CTAs wait for (no deadlock): 2 * streams <= SM count.
     if (2 * c.num_streams > sm_count) return;
-    if (!forced && 3 * c.num_streams > sm_count) return;
     h->seq_plan = p;
-    h->seq_nms = NmsTierPlan{};
+    h->seq_nms = tier_plan_by_id(c, 1081);
+    h->seq_lanes = 4;
     if (const char* e = getenv("PB_SEQ_NMS_TIER")) h->seq_nms = tier_plan_by_id(c, atoi(e));
     if (const char* e = getenv("PB_SEQ_LANES")) { const int v = atoi(e); if (v >= 1 && v <= pb_handle_st::SEQ_MAX_LANES) h->seq_lanes = v; }
     int chunk = PB_SEQ_MAX;
@@ -832,6 +844,8 @@ static int seq_prepare(pb_handle_st* h) {
     for (PipeSlot& sl : ring) PB_TRY(alloc_slot(h, sl, h->ring[0].post.stage_ns));
     for (int i = 0; i < 2; ++i) PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_trk[i], cudaEventDisableTiming));
     for (int i = 0; i < h->seq_lanes; ++i) {
+        if (h->seq_nms.ok && h->seq_nms.spill_stride)
+            PB_TRY(dev_alloc(h, &h->seq_spill[i], (size_t)h->cfg.num_streams * h->seq_nms.spill_stride));
         PB_CUDA(cudaStreamCreateWithFlags(&h->s_seq_nms[i], cudaStreamNonBlocking));
         PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_nms[i], cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&h->ev_seq_dec[i], cudaEventDisableTiming));
@@ -897,7 +911,7 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
             sl.post.dbg_slot = seq & 63;
             if (h->seq_nms.ok)
                 PB_CUDA(launch_nms_tier(h->seq_nms, heads, c.num_anchors, 0, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand,
-                                        sl.post, sl.spill, ns));
+                                        sl.post, h->seq_spill[lane], ns));
             else
                 PB_CUDA(launch_nms(heads, c.num_anchors, 0, c.num_streams, c.max_candidates, c.max_keep, nms, h->dplan, sl.cand, sl.post, ns));
             if (s0 + i >= n_steps - L) PB_CUDA(cudaEventRecord(h->ev_seq_nms[lane], ns));
