@@ -399,6 +399,9 @@ class Workload:
     def kernel_us(self, n):
         """Serial path (one stream), every launch bracketed by CUDA events on the launching stream."""
         self.pipe.set_profiling(True)
+        for _ in range(3):                     # the serial path's kernels may not have run yet (pb_step_seq takes other kernels: the
+            self.step()                        # first launch of a kernel loads its code): warm-up launches, discarded
+        self.pipe.kernel_us()
         for _ in range(n):
             self.step()
         k = self.pipe.kernel_us()

@@ -892,7 +892,11 @@ static int step_seq_resident(pb_handle_st* h, const float* d_heads, size_t step_
         // The tracker launch first: its CTAs are resident (and waiting for frame 0) while the host enqueues the steps.  Where
         // kernels cannot overlap — a profiler that replays kernels one at a time (ncu), CUDA_LAUNCH_BLOCKING=1 — a kernel must
         // not wait for one launched after it: PB_SEQ_TRACKER_LAST=1 (or CUDA_LAUNCH_BLOCKING) enqueues it behind the chunk's steps.
-        static const bool tracker_last = (getenv("PB_SEQ_TRACKER_LAST") && atoi(getenv("PB_SEQ_TRACKER_LAST")) != 0) ||
+        // A tool injected into the process (Nsight Compute sets CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_* for its target) is
+        // taken for a serialising one: the order costs some overlap and nothing else.
+        static const bool tracker_last = (getenv("PB_SEQ_TRACKER_LAST") ? atoi(getenv("PB_SEQ_TRACKER_LAST")) != 0
+                                                                         : (getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                                                                            getenv("NV_NSIGHT_COMPUTE_INJECTION") != nullptr)) ||
                                          (getenv("CUDA_LAUNCH_BLOCKING") && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
         if (!tracker_last) {
             PB_CUDA(launch_tracker_seq(h->trk, tp, q, h->seq_plan, h->s_seq_trk));
