@@ -198,7 +198,10 @@ class Tracker:
 
     def __del__(self):
         if getattr(self, "_t", None):
-            lib().orc_tracker_destroy(self._t)
+            try:
+                lib().orc_tracker_destroy(self._t)
+            except TypeError:           # interpreter shutdown: the module's globals are gone already
+                pass
             self._t = None
 
     def update(self, det_poses, det_scores, frame_id: int) -> int:

@@ -30,8 +30,20 @@ for case in range(N):
     trk = [orc.Tracker(max_tracks=T, max_detections=Dm, **kw) for _ in range(B)]
     d = torch.from_numpy(heads).cuda()
     ok = True
-    for f in range(F):
-        pipe.step(d[f], f); pipe.join(); torch.cuda.synchronize()
+    seq = depth > 1 and rng.random() < 0.5          # pb_step_seq in calls of random length (the resident-tracker path where it applies)
+    f = 0
+    while f < F:
+        n = int(rng.integers(1, 8)) if seq else 1
+        n = min(n, F - f)
+        if seq:
+            pipe.step_seq(d, f, n, f)
+        else:
+            pipe.step(d[f], f)
+        pipe.join(); torch.cuda.synchronize()
+        for g in range(f, f + n - 1):               # the checker catches up to the last frame of the call
+            for b in range(B):
+                ref = orc.postprocess(heads[g, b]); trk[b].update(ref["poses"], ref["scores"], g)
+        f += n - 1
         na = pipe.get_num_active()
         for b in range(B):
             ref = orc.postprocess(heads[f, b])
@@ -45,7 +57,8 @@ for case in range(N):
                 if diff:
                     ok = False; print("MISMATCH state", case, diff[:3]); break
         if not ok: break
-    print(f"case {case}: canvas {canvas} persons {persons} clumps {clumps} T {T} Dm {Dm} B {B} F {F} occ {occ} fuse {fuse} depth {depth} {kw} -> {'ok' if ok else 'FAIL'}", flush=True)
+        f += 1
+    print(f"case {case}: seq {int(seq)} canvas {canvas} persons {persons} clumps {clumps} T {T} Dm {Dm} B {B} F {F} occ {occ} fuse {fuse} depth {depth} {kw} -> {'ok' if ok else 'FAIL'}", flush=True)
     bad += 0 if ok else 1
     pipe.close()
 print("fuzz", "FAILED" if bad else "ok", N, "cases", f"{time.time() - t0:.0f} s")
