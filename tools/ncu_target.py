@@ -1,6 +1,6 @@
 """Short fixed workloads for ncu captures.  PB_CASE = cfg2 (64 streams x [56,8400], the three-kernel step; default),
 cfg4 (128 streams, occlusion, max-age 30: the fused per-stream kernel), cfg5 (512 x 512 tracker tables, 8 streams:
-row-sliced pre-kernel + per-stream kernel), res32 (32 streams through pb_step_seq: the resident tracker kernel; under ncu, which
+row-sliced pre-kernel + per-stream kernel), res32 / res64 (32 / 64 streams through pb_step_seq: the resident tracker kernel and the paired NMS CTAs; under ncu, which
 replays kernels one at a time, run it with PB_SEQ_TRACKER_LAST=1 PB_SEQ_CHUNK=8)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,8 +8,8 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import posebyte_b200 as pb
 case = os.environ.get("PB_CASE", "cfg2"); steps = int(os.environ.get("PB_STEPS", "24"))
-if case == "res32":
-    B = 32
+if case in ("res32", "res64"):
+    B = 32 if case == "res32" else 64
     scfg = pb.synth_config(canvas=640, persons=20, period=32)
     d = torch.from_numpy(pb.synth_heads(scfg, 0, B, 0, 8, frame_major=True)).cuda()
     pipe = pb.Pipeline(num_streams=B, num_anchors=scfg.num_anchors, pipeline_depth=5)
